@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the appearance-flow training hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: one "step" = forward + backward + Adam of the single-view appearance-flow model on a
+synthetic 224x224 car-render batch of 64 per GPU (BASELINE configs[1]; data parallel over N
+GPUs = weak scaling, configs[2] shape of work per GPU), replayed from a captured CUDA graph.
+  value  : samples/s with the batch resident in HBM (CUDA events, max over ranks)
+  e2e    : samples/s through the public API with pinned-host inputs copied H2D and the loss
+           read back D2H inside the timed region, every step
+  roofline / sampler : the dominant kernel of the step and the standalone sampler kernels
+           against MEASURED_PEAKS.json
+  cpu_baseline : the oracle's torch-CPU port of the same step on the host cores (rank 0, N=1)
+Reference arm (--impl reference): that CPU port alone, on a bounded batch-8 sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, V, BATCH = 224, 19, 64
+FWD_GFLOP_PER_SAMPLE = 3.39
+METRIC = "train samples/s @224^2 appflow"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            d = json.load(open(f))
+            p.update({k: d[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in d})
+            p["src"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+        sm = sorted(x for x in (num(r[0]) for r in self.rows if r) if x is not None)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        smax = num(self.rows[0][1]) if self.rows else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, rank):
+    """The reference path's CPU implementation (oracle torch-CPU port), bounded sample."""
+    if rank != 0:
+        return
+    from oracle import cpu_step
+    b = 8
+    wu = max(1, min(args.warmup, 2))
+    sps, ts, cores = cpu_step.time_steps(b, H, V, steps=max(1, min(args.steps, 10)), warmup=wu)
+    ms = 1e3 * sorted(ts)[len(ts) // 2]
+    sample = "batch %d of the 224^2 single-view app-flow step, fp32 fwd+bwd+Adam, torch-CPU port of the oracle graph" % b
+    line = {"impl": "reference", "metric": METRIC, "value": round(sps, 3), "unit": "samples/s", "n_gpus": args.gpus, "steps": len(ts),
+            "warmup": wu, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "single-view appearance-flow train step, 224x224, one-hot azimuth V=19, batch 8 (configs[0])",
+                       "per_gpu_batch": b, "image": H, "threads": cores},
+            "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def sampler_microbench(torch, pk, iters=20):
+    """Standalone sampler kernels at 64 x 224^2 x 3; four rotating input sets (4 x 103 MB > L2)."""
+    from dynamic_multiview_3d_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(1)
+    sets = []
+    for _ in range(4):
+        data = torch.rand((BATCH, H, H, 3), device=dev, generator=g)
+        flow = (torch.rand((BATCH, H, H, 2), device=dev, generator=g) - 0.5) * 6
+        go = torch.randn((BATCH, H, H, 3), device=dev, generator=g)
+        sets.append((data, flow, go))
+    px = BATCH * H * H
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty((BATCH, H, H, 3), device=dev)
+    gw = torch.empty((BATCH, H, H, 2), device=dev)
+    gd = torch.empty((BATCH, H, H, 3), device=dev)
+    ws = torch.empty(max(1, _lib.load().dmv_sampler_bwd_workspace_size(BATCH, H, H, 3, H, H)), dtype=torch.uint8, device=dev)
+
+    def fwd(d, f, go):
+        _lib.call("dmv_sampler_fwd", d.data_ptr(), f.data_ptr(), out.data_ptr(), None, None, BATCH, H, H, 3, H, H, 1, st)
+
+    def bwd_flow(d, f, go):
+        _lib.call("dmv_sampler_bwd", d.data_ptr(), f.data_ptr(), go.data_ptr(), None, gw.data_ptr(), BATCH, H, H, 3, H, H, 1,
+                  ws.data_ptr(), ws.numel(), st)
+
+    def bwd_both(d, f, go):
+        _lib.call("dmv_sampler_bwd", d.data_ptr(), f.data_ptr(), go.data_ptr(), gd.data_ptr(), gw.data_ptr(), BATCH, H, H, 3, H, H, 1,
+                  ws.data_ptr(), ws.numel(), st)
+
+    def timeit(fn, nbytes):
+        for i in range(3):
+            fn(*sets[i % 4])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(*sets[i % 4])
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / iters
+        gbs = nbytes / (us * 1e-6) / 1e9
+        return {"us": round(us, 2), "gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 4), "bytes": nbytes}
+
+    return {"fwd": timeit(fwd, px * (8 + 8 * 3)),                    # 8 + 8C B/px
+            "bwd_grad_flow": timeit(bwd_flow, px * (16 + 8 * 3)),    # 16 + 8C (source is a network input)
+            "bwd_both": timeit(bwd_both, px * (16 + 12 * 3)),        # 16 + 12C
+            "shape": "64x224x224x3 fp32, flow U(-3,3), reference (Y,X) grid fused", "l2_policy": "4 rotating input sets (412 MB)"}
+
+
+def layer_gflop(B):
+    """fwd GFLOP per layer at 224^2 (2*M*N*K), SURVEY 8(a) table."""
+    t = {}
+
+    def conv(name, hw, k, cin, cout):
+        t[name] = 2.0 * B * hw * hw * k * k * cin * cout / 1e9
+    conv("e0", 112, 5, 3, 32); conv("e0_0", 112, 5, 32, 32); conv("e1", 56, 5, 32, 32); conv("e1_0", 56, 5, 32, 32)
+    conv("e2", 28, 5, 32, 64); conv("e2_0", 28, 5, 64, 64); conv("e3", 14, 3, 64, 128); conv("e3_0", 14, 3, 128, 128)
+    conv("e4", 7, 3, 128, 256); conv("e4_0", 7, 3, 256, 256)
+    for n, k_, n_ in [("fc1", 12544, 4096), ("a3", 4160, 4096), ("a4", 4096, 4096), ("a5", 4096, 12544), ("a0", V, 64),
+                      ("a1", 64, 64), ("a2", 64, 64)]:
+        t[n] = 2.0 * B * k_ * n_ / 1e9
+    conv("d4", 7, 3, 256, 128); conv("d4_0", 14, 3, 128, 128); conv("d3", 14, 3, 128, 64); conv("d3_0", 28, 5, 64, 64)
+    conv("d2", 28, 5, 64, 32); conv("d2_0", 56, 5, 32, 64); conv("d1", 56, 5, 64, 32); conv("d1_0", 112, 5, 32, 32)
+    conv("flow_field", 112, 5, 32, 2)
+    return t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--algo", default=None, help="auto|simt|tcgen05 (default: library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture a CUDA graph")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200 import _lib, data_parallel, functional as F
+    from dynamic_multiview_3d_b200.synthetic import make_batch
+    from dynamic_multiview_3d_b200.train import GraphedTrainStep
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    conf = {"batch_size": BATCH, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "loss": "l2", "seed": 0}
+    if args.algo:
+        conf["algo"] = args.algo
+    model = pkg.AppearanceFlowModel(conf)
+    if world > 1:
+        data_parallel.attach(model, bucket_mb=32.0)
+    b = make_batch(BATCH, H, "onehot19", seed=1234, rank=rank)
+    host = {k: torch.from_numpy(b[k]).pin_memory() for k in ("image0", "image1", "disp")}
+    devb = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    if args.eager:
+        def step_fn(i0, i1, d):
+            return model.train_step(i0.to(dev, non_blocking=True), i1.to(dev, non_blocking=True), d.to(dev, non_blocking=True))
+        n0 = _lib.launch_count()
+        step_fn(devb["image0"], devb["image1"], devb["disp"])
+        launches = _lib.launch_count() - n0
+    else:
+        step = GraphedTrainStep(model, warmup=2)
+        step(devb["image0"], devb["image1"], devb["disp"])
+        step_fn = step
+        launches = step.launches_per_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    for _ in range(W):
+        step_fn(devb["image0"], devb["image1"], devb["disp"])
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step_fn(devb["image0"], devb["image1"], devb["disp"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    # ---------------- end-to-end timing (pinned host in, loss out, every step)
+    barrier()
+    t0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    last = 0.0
+    for _ in range(K):
+        loss = step_fn(host["image0"], host["image1"], host["disp"])
+        last = float(loss)                       # D2H read of the step's result
+    ee1.record()
+    barrier()
+    ms_e2e = max(ee0.elapsed_time(ee1), 1e3 * (time.perf_counter() - t0)) / K
+    clocks = sampler.summary() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    value = world * BATCH / (ms * 1e-3)
+    e2e = world * BATCH / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- per-kernel profile of one eager step -> dominant kernel + roofline
+    roof, top = None, []
+    if world == 1:
+        try:
+            model.train_step(devb["image0"], devb["image1"], devb["disp"])
+            with F.profile_calls() as prof:
+                model.train_step(devb["image0"], devb["image1"], devb["disp"])
+            agg = {}
+            for name, tag, t_ms in prof.records:
+                agg[(name, tag)] = agg.get((name, tag), 0.0) + t_ms
+            total = sum(agg.values())
+            ranked = sorted(agg.items(), key=lambda kv: -kv[1])
+            top = [{"call": k[0], "var": k[1], "ms": round(v, 4), "share": round(v / total, 4)} for k, v in ranked[:8]]
+            (dname, dtag), dms = ranked[0]
+            gf = layer_gflop(BATCH)
+            lname = dtag.split("/")[0]
+            if lname in gf:
+                tf = gf[lname] / dms          # GFLOP / ms == TFLOP/s
+                peak = pk["bf16_tflops_sustained"]
+                roof = {"bound": "tensor", "kernel": "%s[%s]" % (dname, dtag), "achieved": round(tf, 2), "peak": peak,
+                        "unit": "TFLOP/s", "frac": round(tf / peak, 5), "traffic": None, "peak_src": pk["src"] + " (sustained)",
+                        "flops_per_launch": gf[lname] * 1e9, "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
+            elif dtag == "adam":
+                nbytes = 30.0 * model.store.total
+                gbs = nbytes / (dms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "kernel": "dmv_adam_multi", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": None, "peak_src": pk["src"], "bytes_per_launch": nbytes,
+                        "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
+        except Exception as ex:      # the profile is explanatory; never lose the bench line over it
+            roof = {"error": repr(ex)[:200]}
+    micro = None
+    if not args.no_micro:
+        try:
+            micro = sampler_microbench(torch, pk)
+        except Exception as ex:
+            micro = {"error": repr(ex)[:200]}
+    if roof is None and micro and "fwd" in micro:
+        roof = {"bound": "hbm", "kernel": "sampler_fwd", "achieved": micro["fwd"]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": micro["fwd"]["frac"], "traffic": None, "peak_src": pk["src"]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_step
+        sps, ts, cores = cpu_step.time_steps(8, H, V, steps=3, warmup=1)
+        cpu = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "batch 8 of the same 224^2 step (configs[0]): fp32 fwd+bwd+Adam, torch-CPU port of the oracle graph, 3 timed steps"}
+
+    step_tflops = 3 * FWD_GFLOP_PER_SAMPLE * BATCH / ms       # GFLOP/ms = TFLOP/s per GPU
+    line = {"metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "single-view appearance-flow train step (fwd+bwd+Adam), 224x224 synthetic car renders, "
+                                   "one-hot azimuth V=19, batch 64 per GPU (configs[1]; N>1 = batch-sharded data parallel)",
+                       "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": H, "loss": "l2 (reference)",
+                       "parallelism": "dp%d" % world, "cuda_graph": not args.eager, "algo": args.algo or F.get_default_algo(),
+                       "l2_policy": "per-step working set (parameters, Adam state, activations: several GB) >> 126 MB L2"},
+            "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(ms_e2e, 4)},
+            "gpu_launches": int(launches * K), "launches_per_step": int(launches),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sampler": micro, "top_kernels": top,
+            "step_tflops_per_gpu": round(step_tflops, 2), "final_loss": last}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,128 @@
+// Public conv / deconv / linear entry points (include/dmv3d.h): argument checks and the
+// choice between the tcgen05 implicit-GEMM kernels (conv_tc.cu) and the SIMT kernels
+// (conv_simt.cu).  DMV_ALGO_AUTO takes the tensor-core path whenever the shape qualifies.
+#include "common.cuh"
+#include "conv_impl.h"
+
+using namespace dmv;
+
+#define DMV_CHECK_ALGO(algo) \
+    DMV_REQUIRE((algo) == DMV_ALGO_AUTO || (algo) == DMV_ALGO_SIMT || (algo) == DMV_ALGO_TCGEN05, DMV_E_INVALID_ARG, "unknown algo")
+
+extern "C" {
+
+size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels) {
+    if (taps <= 0 || Cin <= 0 || Cout <= 0 || pixels <= 0) return 0;
+    size_t a = simt_wgrad_workspace(taps, Cin, Cout, pixels);
+    size_t b = tc_wgrad_workspace(taps, Cin, Cout, pixels);
+    return a > b ? a : b;
+}
+
+int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype, int B, int H, int W,
+                   int Cin, int Cout, int kh, int kw, int stride, int act, int algo, void* stream) {
+    DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "conv2d_fwd: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, st);
+}
+
+int dmv_conv2d_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                     int algo, void* stream) {
+    DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "conv2d_dgrad: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, st);
+}
+
+int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                     int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
+    DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "conv2d_wgrad: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_conv_wgrad(x, x_dtype, dy, dw, db, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_conv_wgrad(x, x_dtype, dy, dw, db, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+}
+
+int dmv_deconv2d_fwd(const void* x, const void* w, void* y, int y_dtype, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                     int kw, int stride, int act, int algo, void* stream) {
+    DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "deconv2d_fwd: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, st);
+}
+
+int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout,
+                       int kh, int kw, int stride, int algo, void* stream) {
+    DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "deconv2d_dgrad: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, st);
+}
+
+int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, int B, int Hout, int Wout, int Cin, int Cout,
+                       int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
+    DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "deconv2d_wgrad: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_deconv_wgrad(x, dy, dy_dtype, dw, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_deconv_wgrad(x, dy, dy_dtype, dw, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+}
+
+// linear == 1x1 conv over M "pixels"
+int dmv_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, int algo,
+                   void* stream) {
+    DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "linear_fwd: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_linear_fwd(x, w, bias, y, M, K, N, act, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_conv_fwd(x, DMV_DT_BF16, w, bias, y, DMV_DT_BF16, M, 1, 1, K, N, 1, 1, 1, act, st);
+}
+
+int dmv_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, int algo, void* stream) {
+    DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "linear_dgrad: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_linear_dgrad(dy, w, dx, M, K, N, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_conv_dgrad(dy, w, dx, M, 1, 1, K, N, 1, 1, 1, st);
+}
+
+int dmv_linear_wgrad(const void* x, const void* dy, float* dw, float* db, int M, int K, int N, void* workspace,
+                     size_t workspace_bytes, int algo, void* stream) {
+    DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "linear_wgrad: null pointer");
+    DMV_CHECK_ALGO(algo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT) {
+        int rc = tc_linear_wgrad(x, dy, dw, db, M, K, N, workspace, workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+    }
+    return simt_conv_wgrad(x, DMV_DT_BF16, dy, dw, db, M, 1, 1, K, N, 1, 1, 1, workspace, workspace_bytes, st);
+}
+}

@@ -1,0 +1,40 @@
+// Internal interfaces between the public dispatchers (conv_api.cu) and the two kernel
+// families.  tc_* return DMV_E_UNSUPPORTED_SHAPE when the tensor-core path does not cover
+// a shape; DMV_ALGO_AUTO then falls through to the SIMT kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace dmv {
+size_t simt_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
+int simt_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin,
+                  int Cout, int kh, int kw, int stride, int act, cudaStream_t st);
+int simt_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                    cudaStream_t st);
+int simt_conv_wgrad(const void* x, int xdt, const void* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, int kh,
+                    int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
+int simt_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hout, int Wout, int Cin, int Cout, int kh, int kw,
+                    int stride, int act, cudaStream_t st);
+int simt_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                      int kw, int stride, cudaStream_t st);
+int simt_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                      int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
+
+size_t tc_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
+int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin, int Cout,
+                int kh, int kw, int stride, int act, cudaStream_t st);
+int tc_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                  cudaStream_t st);
+int tc_conv_wgrad(const void* x, int xdt, const void* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, int kh,
+                  int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hout, int Wout, int Cin, int Cout, int kh, int kw,
+                  int stride, int act, cudaStream_t st);
+int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                    int kw, int stride, cudaStream_t st);
+int tc_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                    int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, cudaStream_t st);
+int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, cudaStream_t st);
+int tc_linear_wgrad(const void* x, const void* dy, float* dw, float* db, int M, int K, int N, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+}  // namespace dmv

@@ -1,0 +1,377 @@
+// CUDA-core (SIMT) conv / deconv / linear kernels: the bring-up path and the on-GPU
+// cross-check for the tcgen05 implicit-GEMM kernels (DMV_ALGO_SIMT).  bf16 (or fp32 image)
+// operands, fp32 accumulation, TF-SAME padding.
+//
+// Three kernel forms over one geometry cover all nine entry points.  "big" is the side a
+// SAME conv reads (H x W x Cin), "small" the side it writes (Ho x Wo x Cout); weights are
+// w[r][s][ci][co] with ci on the big side:
+//   F  small[n,oh,ow,co] = act( sum_{r,s,ci} big[n,oh*st+r-pt,ow*st+s-pl,ci] w[r,s,ci,co] + b[co] )
+//        conv fwd (big = x), deconv dgrad (big = dy)
+//   G  big[n,ih,iw,ci]   = act( sum_{r,s,co} small[n,(ih+pt-r)/st,(iw+pl-s)/st,co] w[r,s,ci,co] )
+//        conv dgrad (small = dy), deconv fwd (small = x; tf.nn.conv2d_transpose is by
+//        definition the input-gradient of a SAME conv)
+//   W  dw[r,s,ci,co]     = sum_{n,oh,ow} big[...,ci] * small[n,oh,ow,co]
+//        conv wgrad (big = x, small = dy), deconv wgrad (big = dy, small = x)
+// W is a deterministic split-K: partial tiles go to the workspace and a second kernel adds
+// them in split order.
+#include "common.cuh"
+
+namespace {
+using namespace dmv;
+typedef __nv_bfloat16 bf16;
+
+struct ConvGeom {
+    int B, H, W, Cin, Ho, Wo, Cout, kh, kw, st, pt, pl;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 t = __bfloat1622float2(p[k]);
+        f[2 * k] = t.x;
+        f[2 * k + 1] = t.y;
+    }
+}
+
+// ---------------------------------------------------------------- form F
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(128) conv_f_kernel(const TX* __restrict__ X, const bf16* __restrict__ Wt,
+                                                      const float* __restrict__ bias, TY* __restrict__ Y, ConvGeom g, int act) {
+    const long long total = (long long)g.B * g.Ho * g.Wo;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int co0 = blockIdx.y * 8;
+    if (pix >= total) return;
+    const int ow = (int)(pix % g.Wo);
+    const int oh = (int)((pix / g.Wo) % g.Ho);
+    const int n = (int)(pix / ((long long)g.Wo * g.Ho));
+    const bool wvec = (g.Cout % 8 == 0);
+    const int nco = min(8, g.Cout - co0);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < g.kh; ++r) {
+        const int ih = oh * g.st + r - g.pt;
+        if (ih < 0 || ih >= g.H) continue;
+        for (int s = 0; s < g.kw; ++s) {
+            const int iw = ow * g.st + s - g.pl;
+            if (iw < 0 || iw >= g.W) continue;
+            const TX* xp = X + (((long long)n * g.H + ih) * g.W + iw) * g.Cin;
+            const bf16* wp = Wt + ((long long)(r * g.kw + s) * g.Cin) * g.Cout + co0;
+            for (int ci = 0; ci < g.Cin; ++ci) {
+                const float xv = load_as_float(xp + ci);
+                if (wvec) {
+                    float wf[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(wp + (long long)ci * g.Cout)), wf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wf[j], acc[j]);
+                } else {
+                    for (int j = 0; j < nco; ++j) acc[j] = fmaf(xv, bf2f(wp[(long long)ci * g.Cout + j]), acc[j]);
+                }
+            }
+        }
+    }
+    TY* yp = Y + pix * g.Cout + co0;
+    for (int j = 0; j < nco; ++j) {
+        float v = acc[j] + (bias ? __ldg(bias + co0 + j) : 0.f);
+        store_from_float(yp + j, apply_act(v, act));
+    }
+}
+
+// ---------------------------------------------------------------- form G
+template <typename TS, typename TB>
+__global__ void __launch_bounds__(128) conv_g_kernel(const TS* __restrict__ S, const bf16* __restrict__ Wt,
+                                                      TB* __restrict__ Bg, ConvGeom g, int act) {
+    const long long total = (long long)g.B * g.H * g.W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci0 = blockIdx.y * 8;
+    if (pix >= total) return;
+    const int iw = (int)(pix % g.W);
+    const int ih = (int)((pix / g.W) % g.H);
+    const int n = (int)(pix / ((long long)g.W * g.H));
+    const int nci = min(8, g.Cin - ci0);
+    const bool vec = (g.Cout % 8 == 0) && (sizeof(TS) == 2);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < g.kh; ++r) {
+        const int t = ih + g.pt - r;
+        if (t < 0 || (t % g.st) != 0) continue;
+        const int oh = t / g.st;
+        if (oh >= g.Ho) continue;
+        for (int s = 0; s < g.kw; ++s) {
+            const int u = iw + g.pl - s;
+            if (u < 0 || (u % g.st) != 0) continue;
+            const int ow = u / g.st;
+            if (ow >= g.Wo) continue;
+            const TS* sp = S + (((long long)n * g.Ho + oh) * g.Wo + ow) * g.Cout;
+            const bf16* wp = Wt + ((long long)(r * g.kw + s) * g.Cin + ci0) * g.Cout;
+            if (vec) {
+                for (int co = 0; co < g.Cout; co += 8) {
+                    float sv[8];
+                    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(sp) + co), sv);
+                    for (int j = 0; j < nci; ++j) {
+                        float wf[8];
+                        unpack8(__ldg(reinterpret_cast<const uint4*>(wp + (long long)j * g.Cout + co)), wf);
+                        float d = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) d = fmaf(sv[k], wf[k], d);
+                        acc[j] += d;
+                    }
+                }
+            } else {
+                for (int co = 0; co < g.Cout; ++co) {
+                    const float sv = load_as_float(sp + co);
+                    for (int j = 0; j < nci; ++j) acc[j] = fmaf(sv, bf2f(wp[(long long)j * g.Cout + co]), acc[j]);
+                }
+            }
+        }
+    }
+    TB* bp = Bg + pix * g.Cin + ci0;
+    for (int j = 0; j < nci; ++j) store_from_float(bp + j, apply_act(acc[j], act));
+}
+
+// ---------------------------------------------------------------- form W
+constexpr int kWT = 32;  // ci x co tile
+template <typename TBig, typename TSm>
+__global__ void __launch_bounds__(256) conv_w_kernel(const TBig* __restrict__ Big, const TSm* __restrict__ Sm,
+                                                      float* __restrict__ part, ConvGeom g, int ci_tiles, int co_tiles,
+                                                      long long chunk) {
+    __shared__ float xs[32][kWT + 1];
+    __shared__ float ys[32][kWT + 1];
+    int t = blockIdx.x;
+    const int cot = t % co_tiles; t /= co_tiles;
+    const int cit = t % ci_tiles; t /= ci_tiles;
+    const int tap = t;
+    const int r = tap / g.kw, s = tap - r * g.kw;
+    const int ci0 = cit * kWT, co0 = cot * kWT;
+    const long long total = (long long)g.B * g.Ho * g.Wo;
+    const long long p_begin = (long long)blockIdx.y * chunk;
+    const long long p_end = min(total, p_begin + chunk);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // thread computes ci {ty, ty+16} x co {tx, tx+16}
+    const int lp = threadIdx.x >> 3, lc = (threadIdx.x & 7) * 4;  // loader: pixel lp, channels lc..lc+3
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
+        const long long p = p0 + lp;
+        float xv[4] = {0.f, 0.f, 0.f, 0.f}, yv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p < p_end) {
+            const int ow = (int)(p % g.Wo);
+            const int oh = (int)((p / g.Wo) % g.Ho);
+            const int n = (int)(p / ((long long)g.Wo * g.Ho));
+            const int ih = oh * g.st + r - g.pt, iw = ow * g.st + s - g.pl;
+            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+                const TBig* xp = Big + (((long long)n * g.H + ih) * g.W + iw) * g.Cin + ci0 + lc;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (ci0 + lc + k < g.Cin) xv[k] = load_as_float(xp + k);
+            }
+            const TSm* yp = Sm + p * g.Cout + co0 + lc;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (co0 + lc + k < g.Cout) yv[k] = load_as_float(yp + k);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xs[lp][lc + k] = xv[k];
+            ys[lp][lc + k] = yv[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const float x0 = xs[q][ty], x1 = xs[q][ty + 16], y0 = ys[q][tx], y1 = ys[q][tx + 16];
+            a00 = fmaf(x0, y0, a00);
+            a01 = fmaf(x0, y1, a01);
+            a10 = fmaf(x1, y0, a10);
+            a11 = fmaf(x1, y1, a11);
+        }
+    }
+    float* out = part + (long long)blockIdx.y * g.kh * g.kw * g.Cin * g.Cout + (long long)tap * g.Cin * g.Cout;
+    const int ci_a = ci0 + ty, ci_b = ci0 + ty + 16, co_a = co0 + tx, co_b = co0 + tx + 16;
+    if (ci_a < g.Cin && co_a < g.Cout) out[(long long)ci_a * g.Cout + co_a] = a00;
+    if (ci_a < g.Cin && co_b < g.Cout) out[(long long)ci_a * g.Cout + co_b] = a01;
+    if (ci_b < g.Cin && co_a < g.Cout) out[(long long)ci_b * g.Cout + co_a] = a10;
+    if (ci_b < g.Cin && co_b < g.Cout) out[(long long)ci_b * g.Cout + co_b] = a11;
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int splits) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[(long long)z * n + i];
+        out[i] = s;
+    }
+}
+
+// column sums of a [pixels, C] matrix (bias gradient), deterministic two-stage
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ Y, float* __restrict__ part, long long pixels, int C,
+                                                      long long chunk) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int lane_p = threadIdx.x >> 5;
+    const long long p_begin = (long long)blockIdx.y * chunk, p_end = min(pixels, p_begin + chunk);
+    float s = 0.f;
+    if (c < C)
+        for (long long p = p_begin + lane_p; p < p_end; p += 8) s += load_as_float(Y + p * C + c);
+    red[lane_p][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (lane_p == 0 && c < C) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+        part[(long long)blockIdx.y * C + c] = t;
+    }
+}
+
+int make_geom(ConvGeom& g, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride) {
+    DMV_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0, DMV_E_INVALID_ARG,
+                "conv: non-positive dimension");
+    const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Ho = ph.out; g.Wo = pw.out; g.Cout = Cout;
+    g.kh = kh; g.kw = kw; g.st = stride; g.pt = ph.before; g.pl = pw.before;
+    return DMV_OK;
+}
+
+struct SplitPlan {
+    int ci_tiles, co_tiles, splits;
+    long long chunk;
+};
+SplitPlan plan_split(int taps, int Cin, int Cout, long long pixels) {
+    SplitPlan p;
+    p.ci_tiles = ceil_div(Cin, kWT);
+    p.co_tiles = ceil_div(Cout, kWT);
+    const long long tiles = (long long)taps * p.ci_tiles * p.co_tiles;
+    long long want = ceil_div_ll(148 * 8, tiles);
+    long long max_by_pixels = ceil_div_ll(pixels, 1024);
+    long long s = want < max_by_pixels ? want : max_by_pixels;
+    if (s < 1) s = 1;
+    if (s > 512) s = 512;
+    p.chunk = ceil_div_ll(ceil_div_ll(pixels, s), 32) * 32;
+    p.splits = (int)ceil_div_ll(pixels, p.chunk);
+    return p;
+}
+
+template <typename TBig, typename TSm>
+int run_wgrad(const TBig* big, const TSm* sm, float* dw, const ConvGeom& g, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int taps = g.kh * g.kw;
+    const long long pixels = (long long)g.B * g.Ho * g.Wo;
+    const SplitPlan p = plan_split(taps, g.Cin, g.Cout, pixels);
+    const long long n = (long long)taps * g.Cin * g.Cout;
+    DMV_REQUIRE(ws && ws_bytes >= (size_t)p.splits * n * sizeof(float), DMV_E_WORKSPACE, "wgrad: workspace too small");
+    float* part = reinterpret_cast<float*>(ws);
+    dim3 grid(taps * p.ci_tiles * p.co_tiles, p.splits);
+    conv_w_kernel<TBig, TSm><<<grid, 256, 0, st>>>(big, sm, part, g, p.ci_tiles, p.co_tiles, p.chunk);
+    int rc = check_launch("conv_wgrad_simt");
+    if (rc) return rc;
+    long long blocks = ceil_div_ll(n, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, dw, n, p.splits);
+    return check_launch("splitk_reduce");
+}
+
+template <typename T>
+int run_colsum(const T* y, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+    long long splits = ceil_div_ll(pixels, 2048);
+    if (splits > 256) splits = 256;
+    const long long chunk = ceil_div_ll(pixels, splits);
+    splits = ceil_div_ll(pixels, chunk);
+    DMV_REQUIRE(ws && ws_bytes >= (size_t)splits * C * sizeof(float), DMV_E_WORKSPACE, "bias grad: workspace too small");
+    float* part = reinterpret_cast<float*>(ws);
+    dim3 grid(ceil_div(C, 32), (int)splits);
+    colsum_kernel<T><<<grid, 256, 0, st>>>(y, part, pixels, C, chunk);
+    int rc = check_launch("colsum");
+    if (rc) return rc;
+    splitk_reduce_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, db, C, (int)splits);
+    return check_launch("colsum_reduce");
+}
+
+template <typename TX, typename TY>
+int run_f(const void* x, const void* w, const float* bias, void* y, const ConvGeom& g, int act, cudaStream_t st) {
+    const long long pixels = (long long)g.B * g.Ho * g.Wo;
+    dim3 grid((unsigned)ceil_div_ll(pixels, 128), ceil_div(g.Cout, 8));
+    conv_f_kernel<TX, TY><<<grid, 128, 0, st>>>((const TX*)x, (const bf16*)w, bias, (TY*)y, g, act);
+    return check_launch("conv_f_simt");
+}
+template <typename TS, typename TB>
+int run_g(const void* s, const void* w, void* b, const ConvGeom& g, int act, cudaStream_t st) {
+    const long long pixels = (long long)g.B * g.H * g.W;
+    dim3 grid((unsigned)ceil_div_ll(pixels, 128), ceil_div(g.Cin, 8));
+    conv_g_kernel<TS, TB><<<grid, 128, 0, st>>>((const TS*)s, (const bf16*)w, (TB*)b, g, act);
+    return check_launch("conv_g_simt");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ SIMT entry points
+// (called by the public dispatchers in conv_api.cu)
+namespace dmv {
+
+size_t simt_wgrad_workspace(int taps, int Cin, int Cout, long long pixels) {
+    const SplitPlan p = plan_split(taps, Cin, Cout, pixels);
+    size_t a = (size_t)p.splits * taps * Cin * Cout * sizeof(float);
+    size_t b = (size_t)256 * Cout * sizeof(float);
+    return (a > b ? a : b) + 256;
+}
+
+int simt_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin,
+                  int Cout, int kh, int kw, int stride, int act, cudaStream_t st) {
+    ConvGeom g;
+    int rc = make_geom(g, B, H, W, Cin, Cout, kh, kw, stride);
+    if (rc) return rc;
+    if (xdt == DMV_DT_F32 && ydt == DMV_DT_BF16) return run_f<float, bf16>(x, w, bias, y, g, act, st);
+    if (xdt == DMV_DT_F32 && ydt == DMV_DT_F32) return run_f<float, float>(x, w, bias, y, g, act, st);
+    if (xdt == DMV_DT_BF16 && ydt == DMV_DT_BF16) return run_f<bf16, bf16>(x, w, bias, y, g, act, st);
+    if (xdt == DMV_DT_BF16 && ydt == DMV_DT_F32) return run_f<bf16, float>(x, w, bias, y, g, act, st);
+    return fail(DMV_E_INVALID_ARG, "conv_fwd: unknown dtype");
+}
+
+// big side gradient of a conv whose big side is [B,H,W,Cin]: small = dy (bf16), writes dx (bf16)
+int simt_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                    cudaStream_t st) {
+    ConvGeom g;
+    int rc = make_geom(g, B, H, W, Cin, Cout, kh, kw, stride);
+    if (rc) return rc;
+    return run_g<bf16, bf16>(dy, w, dx, g, DMV_ACT_NONE, st);
+}
+
+int simt_conv_wgrad(const void* x, int xdt, const void* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, int kh,
+                    int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st) {
+    ConvGeom g;
+    int rc = make_geom(g, B, H, W, Cin, Cout, kh, kw, stride);
+    if (rc) return rc;
+    if (xdt == DMV_DT_F32) rc = run_wgrad<float, bf16>((const float*)x, (const bf16*)dy, dw, g, ws, ws_bytes, st);
+    else rc = run_wgrad<bf16, bf16>((const bf16*)x, (const bf16*)dy, dw, g, ws, ws_bytes, st);
+    if (rc) return rc;
+    if (db) rc = run_colsum<bf16>((const bf16*)dy, db, (long long)g.B * g.Ho * g.Wo, Cout, ws, ws_bytes, st);
+    return rc;
+}
+
+// deconv: big side is the OUTPUT [B,Hout,Wout,Cout_t]; geometry ci := Cout_t, co := Cin_t
+int simt_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hout, int Wout, int Cin, int Cout, int kh, int kw,
+                    int stride, int act, cudaStream_t st) {
+    ConvGeom g;
+    int rc = make_geom(g, B, Hout, Wout, /*ci=*/Cout, /*co=*/Cin, kh, kw, stride);
+    if (rc) return rc;
+    if (ydt == DMV_DT_F32) return run_g<bf16, float>(x, w, y, g, act, st);
+    return run_g<bf16, bf16>(x, w, y, g, act, st);
+}
+
+int simt_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                      int kw, int stride, cudaStream_t st) {
+    ConvGeom g;
+    int rc = make_geom(g, B, Hout, Wout, Cout, Cin, kh, kw, stride);
+    if (rc) return rc;
+    if (dydt == DMV_DT_F32) return run_f<float, bf16>(dy, w, nullptr, dx, g, DMV_ACT_NONE, st);
+    return run_f<bf16, bf16>(dy, w, nullptr, dx, g, DMV_ACT_NONE, st);
+}
+
+int simt_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B, int Hout, int Wout, int Cin, int Cout, int kh,
+                      int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st) {
+    ConvGeom g;
+    int rc = make_geom(g, B, Hout, Wout, Cout, Cin, kh, kw, stride);
+    if (rc) return rc;
+    if (dydt == DMV_DT_F32) return run_wgrad<float, bf16>((const float*)dy, (const bf16*)x, dw, g, ws, ws_bytes, st);
+    return run_wgrad<bf16, bf16>((const bf16*)dy, (const bf16*)x, dw, g, ws, ws_bytes, st);
+}
+
+}  // namespace dmv

@@ -1,0 +1,431 @@
+// Bilinear sampler (tf.contrib.resampler semantics) for sm_100a.
+//
+//   forward / grad_warp : one CTA per 1024-pixel OUTPUT tile.  The CTA loads its flow
+//     vectors (coalesced float2), forms warp = flow + grid in registers, reduces the
+//     bounding box of the taps it needs, stages that SOURCE window into shared memory with
+//     coalesced row-segment loads, then gathers the four taps from shared memory.  When the
+//     window does not fit (arbitrary warps) it gathers straight from global (L1/L2).
+//     The arithmetic uses non-contracted fp32 ops in the reference's summation order, so
+//     the forward values and grad_warp are bit-equal to the NumPy oracle.
+//   grad_data : owner-computes scatter.  One CTA owns a 32x16 SOURCE tile; it visits every
+//     output tile whose tap box intersects it (box table from a pre-pass), and each warp
+//     accumulates into a warp-private shared-memory copy of the tile.  Lanes that hit the
+//     same cell in one step are serialised by lane rank (__match_any_sync), warps are
+//     summed in warp order, and every grad_data element is written exactly once: no global
+//     atomics, no memset, same inputs -> same bits.
+//
+// HBM-bound: algorithmic bytes per output pixel are 8 + 8C (fwd), 16 + 8C (grad_warp only),
+// 8 + 8C (grad_data pass).
+#include "common.cuh"
+
+namespace {
+
+using namespace dmv;
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTilePix = 1024;
+constexpr int kPPT = kTilePix / kThreads;  // pixels per thread
+constexpr int kStageFloats = 10240;        // 40 KB source window
+constexpr int kSrcTileW = 32, kSrcTileH = 16;
+
+struct Geom {
+    int B, H, W, C, Ho, Wo;
+    int tw_shift;  // output tile is (1024 >> tw_shift) rows x (1 << tw_shift) cols
+    int tiles_x, tiles_y;
+    unsigned flags;
+};
+
+struct Sample {
+    float x, y;
+    bool valid;
+};
+
+__device__ __forceinline__ Sample load_sample(const float* __restrict__ wf, const Geom& g, int b, int i, int j) {
+    Sample s;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(wf) + ((long long)b * g.Ho + i) * g.Wo + j);
+    s.x = f.x;
+    s.y = f.y;
+    if (g.flags & DMV_SAMPLER_ADD_GRID) {
+        if (g.flags & DMV_SAMPLER_GRID_XY) {
+            s.x = __fadd_rn(f.x, (float)j);
+            s.y = __fadd_rn(f.y, (float)i);
+        } else {  // reference (Y,X) order: channel 0 += row index, channel 1 += column index
+            s.x = __fadd_rn(f.x, (float)i);
+            s.y = __fadd_rn(f.y, (float)j);
+        }
+    }
+    s.valid = (s.x > -1.0f) && (s.y > -1.0f) && (s.x < (float)g.W) && (s.y < (float)g.H);
+    return s;
+}
+
+__device__ __forceinline__ void tile_origin(const Geom& g, int tile, int& b, int& i0, int& j0) {
+    const int per_img = g.tiles_x * g.tiles_y;
+    b = tile / per_img;
+    const int t = tile - b * per_img;
+    const int ty = t / g.tiles_x;
+    const int tx = t - ty * g.tiles_x;
+    i0 = ty * (kTilePix >> g.tw_shift);
+    j0 = tx << g.tw_shift;
+}
+
+// Reduce the tap bounding box of a tile into s_box = {xmin, xmax, ymin, ymax} (clipped to the image).
+__device__ __forceinline__ void reduce_box(int* s_box, bool valid, int fx, int fy, int W, int H) {
+    int xlo = 0x7fffffff, xhi = -0x7fffffff, ylo = 0x7fffffff, yhi = -0x7fffffff;
+    if (valid) {
+        xlo = max(fx, 0);
+        xhi = min(fx + 1, W - 1);
+        ylo = max(fy, 0);
+        yhi = min(fy + 1, H - 1);
+    }
+    xlo = __reduce_min_sync(0xffffffffu, xlo);
+    xhi = __reduce_max_sync(0xffffffffu, xhi);
+    ylo = __reduce_min_sync(0xffffffffu, ylo);
+    yhi = __reduce_max_sync(0xffffffffu, yhi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&s_box[0], xlo);
+        atomicMax(&s_box[1], xhi);
+        atomicMin(&s_box[2], ylo);
+        atomicMax(&s_box[3], yhi);
+    }
+}
+
+// MODE 0: forward.  MODE 1: grad wrt warp/flow.
+template <int CT, int MODE>
+__global__ void __launch_bounds__(kThreads) sampler_tile_kernel(
+    const float* __restrict__ data, const float* __restrict__ wf, const float* __restrict__ grad_out,
+    float* __restrict__ out, int32_t* __restrict__ dbg_idx, uint8_t* __restrict__ dbg_mask, Geom g) {
+    extern __shared__ float s_win[];
+    __shared__ int s_box[4];
+    const int C = CT ? CT : g.C;
+    const int tid = threadIdx.x;
+    int b, i0, j0;
+    tile_origin(g, blockIdx.x, b, i0, j0);
+    if (tid < 4) s_box[tid] = (tid & 1) ? -0x7fffffff : 0x7fffffff;
+    __syncthreads();
+
+    Sample smp[kPPT];
+    int pi[kPPT], pj[kPPT];
+    bool inb[kPPT];
+    const int tw_mask = (1 << g.tw_shift) - 1;
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+        const int p = k * kThreads + tid;
+        pi[k] = i0 + (p >> g.tw_shift);
+        pj[k] = j0 + (p & tw_mask);
+        inb[k] = (pi[k] < g.Ho) && (pj[k] < g.Wo);
+        smp[k].valid = false;
+        smp[k].x = smp[k].y = 0.f;
+        if (inb[k]) smp[k] = load_sample(wf, g, b, pi[k], pj[k]);
+        const int fx = smp[k].valid ? (int)floorf(smp[k].x) : 0;
+        const int fy = smp[k].valid ? (int)floorf(smp[k].y) : 0;
+        reduce_box(s_box, smp[k].valid, fx, fy, g.W, g.H);
+    }
+    __syncthreads();
+    const int xmin = s_box[0], xmax = s_box[1], ymin = s_box[2], ymax = s_box[3];
+    const bool any_valid = xmin <= xmax;
+    const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
+    const int seg = nx * C;
+    const int pitch = seg | 1;  // odd pitch: a column read by 32 lanes hits 32 banks
+    const bool staged = any_valid && ((long long)ny * pitch <= kStageFloats);
+    if (staged) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < ny; r += kWarps) {
+            const float* src = data + (((long long)b * g.H + ymin + r) * g.W + xmin) * C;
+            float* dst = s_win + r * pitch;
+            for (int e = lane; e < seg; e += 32) dst[e] = __ldg(src + e);
+        }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+        if (!inb[k]) continue;
+        const long long opix = ((long long)b * g.Ho + pi[k]) * g.Wo + pj[k];
+        const Sample s = smp[k];
+        int fx = 0, fy = 0, cx = 0, cy = 0;
+        unsigned mask = 0;
+        float dx = 0.f, dy = 0.f;
+        if (s.valid) {
+            fx = (int)floorf(s.x);
+            fy = (int)floorf(s.y);
+            cx = fx + 1;
+            cy = fy + 1;
+            dx = __fsub_rn((float)cx, s.x);
+            dy = __fsub_rn((float)cy, s.y);
+            const bool fxi = fx >= 0, cxi = cx <= g.W - 1, fyi = fy >= 0, cyi = cy <= g.H - 1;
+            mask = 1u | ((fxi && fyi) ? 2u : 0u) | ((cxi && cyi) ? 4u : 0u) | ((fxi && cyi) ? 8u : 0u) |
+                   ((cxi && fyi) ? 16u : 0u);
+        }
+        if (MODE == 0) {
+            if (dbg_idx) reinterpret_cast<int4*>(dbg_idx)[opix] = make_int4(fx, fy, cx, cy);
+            if (dbg_mask) dbg_mask[opix] = (uint8_t)mask;
+        }
+        const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
+        const float w_ff = __fmul_rn(dx, dy), w_cc = __fmul_rn(omdx, omdy), w_fc = __fmul_rn(dx, omdy),
+                    w_cf = __fmul_rn(omdx, dy);
+        // base offsets of the four taps (shared window or global)
+        long long o_ff, o_cc, o_fc, o_cf;
+        const float* base;
+        if (staged) {
+            base = s_win;
+            o_ff = (long long)(fy - ymin) * pitch + (fx - xmin) * C;
+            o_cf = o_ff + C;
+            o_fc = o_ff + pitch;
+            o_cc = o_fc + C;
+        } else {
+            base = data;
+            o_ff = (((long long)b * g.H + fy) * g.W + fx) * C;
+            o_cf = o_ff + C;
+            o_fc = o_ff + (long long)g.W * C;
+            o_cc = o_fc + C;
+        }
+        float gw0 = 0.f, gw1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < (CT ? CT : 16); ++c) {
+            if (!CT && c >= C) break;
+            float p_ff = 0.f, p_cc = 0.f, p_fc = 0.f, p_cf = 0.f;
+            if (mask & 2u) p_ff = base[o_ff + c];
+            if (mask & 4u) p_cc = base[o_cc + c];
+            if (mask & 8u) p_fc = base[o_fc + c];
+            if (mask & 16u) p_cf = base[o_cf + c];
+            if (MODE == 0) {
+                float v = __fmul_rn(w_ff, p_ff);
+                v = __fadd_rn(v, __fmul_rn(w_cc, p_cc));
+                v = __fadd_rn(v, __fmul_rn(w_fc, p_fc));
+                v = __fadd_rn(v, __fmul_rn(w_cf, p_cf));
+                out[opix * C + c] = s.valid ? v : 0.f;
+            } else {
+                const float gc = s.valid ? __ldg(grad_out + opix * C + c) : 0.f;
+                const float a0 = __fadd_rn(__fmul_rn(omdy, __fsub_rn(p_cc, p_fc)), __fmul_rn(dy, __fsub_rn(p_cf, p_ff)));
+                const float a1 = __fadd_rn(__fmul_rn(omdx, __fsub_rn(p_cc, p_cf)), __fmul_rn(dx, __fsub_rn(p_fc, p_ff)));
+                gw0 = __fadd_rn(gw0, __fmul_rn(gc, a0));
+                gw1 = __fadd_rn(gw1, __fmul_rn(gc, a1));
+            }
+        }
+        if (MODE == 1) reinterpret_cast<float2*>(out)[opix] = s.valid ? make_float2(gw0, gw1) : make_float2(0.f, 0.f);
+    }
+}
+
+// Pre-pass of grad_data: tap box of every output tile.
+__global__ void __launch_bounds__(kThreads) sampler_box_kernel(const float* __restrict__ wf, int4* __restrict__ boxes, Geom g) {
+    __shared__ int s_box[4];
+    const int tid = threadIdx.x;
+    int b, i0, j0;
+    tile_origin(g, blockIdx.x, b, i0, j0);
+    if (tid < 4) s_box[tid] = (tid & 1) ? -0x7fffffff : 0x7fffffff;
+    __syncthreads();
+    const int tw_mask = (1 << g.tw_shift) - 1;
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+        const int p = k * kThreads + tid;
+        const int i = i0 + (p >> g.tw_shift), j = j0 + (p & tw_mask);
+        Sample s;
+        s.valid = false;
+        s.x = s.y = 0.f;
+        if (i < g.Ho && j < g.Wo) s = load_sample(wf, g, b, i, j);
+        reduce_box(s_box, s.valid, s.valid ? (int)floorf(s.x) : 0, s.valid ? (int)floorf(s.y) : 0, g.W, g.H);
+    }
+    __syncthreads();
+    if (tid == 0) boxes[blockIdx.x] = make_int4(s_box[0], s_box[1], s_box[2], s_box[3]);
+}
+
+template <int CT>
+__device__ __forceinline__ void accumulate_ranked(float* acc, int key, const float (&val)[CT ? CT : 8], int C) {
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+    const int rank = __popc(peers & lt);
+    const int rounds = __reduce_max_sync(0xffffffffu, key >= 0 ? __popc(peers) : 0);
+    for (int r = 0; r < rounds; ++r) {
+        if (key >= 0 && rank == r) {
+#pragma unroll
+            for (int c = 0; c < (CT ? CT : 8); ++c) {
+                if (!CT && c >= C) break;
+                acc[key * C + c] += val[c];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kThreads) sampler_grad_data_kernel(
+    const float* __restrict__ wf, const float* __restrict__ grad_out, const int4* __restrict__ boxes,
+    float* __restrict__ grad_data, Geom g, int src_tiles_x, int src_tiles_y) {
+    extern __shared__ float s_acc[];  // [kWarps][kSrcTileH*kSrcTileW*C]
+    const int C = CT ? CT : g.C;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int per_img = src_tiles_x * src_tiles_y;
+    const int b = blockIdx.x / per_img;
+    const int st = blockIdx.x - b * per_img;
+    const int sty = st / src_tiles_x, stx = st - sty * src_tiles_x;
+    const int sx0 = stx * kSrcTileW, sy0 = sty * kSrcTileH;
+    const int sx1 = min(sx0 + kSrcTileW, g.W) - 1, sy1 = min(sy0 + kSrcTileH, g.H) - 1;
+    const int tile_floats = kSrcTileH * kSrcTileW * C;
+    for (int e = tid; e < kWarps * tile_floats; e += kThreads) s_acc[e] = 0.f;
+    __syncthreads();
+    float* acc = s_acc + warp * tile_floats;
+
+    const int out_tiles = g.tiles_x * g.tiles_y;
+    const int tw_mask = (1 << g.tw_shift) - 1;
+    for (int t = 0; t < out_tiles; ++t) {
+        const int4 box = __ldg(boxes + (long long)b * out_tiles + t);
+        if (box.x > sx1 || box.y < sx0 || box.z > sy1 || box.w < sy0) continue;  // CTA-uniform
+        const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
+        const int i0 = ty * (kTilePix >> g.tw_shift), j0 = tx << g.tw_shift;
+        for (int q = warp; q < kTilePix / 32; q += kWarps) {  // fixed chunk -> warp assignment
+            const int p = q * 32 + lane;
+            const int i = i0 + (p >> g.tw_shift), j = j0 + (p & tw_mask);
+            Sample s;
+            s.valid = false;
+            s.x = s.y = 0.f;
+            if (i < g.Ho && j < g.Wo) s = load_sample(wf, g, b, i, j);
+            int key[4] = {-1, -1, -1, -1};
+            float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+            if (s.valid) {
+                const int fx = (int)floorf(s.x), fy = (int)floorf(s.y);
+                const int cx = fx + 1, cy = fy + 1;
+                const float dx = (float)cx - s.x, dy = (float)cy - s.y;
+                const bool fxo = fx >= sx0 && fx <= sx1, cxo = cx >= sx0 && cx <= sx1;
+                const bool fyo = fy >= sy0 && fy <= sy1, cyo = cy >= sy0 && cy <= sy1;
+                if (fxo && fyo) { key[0] = (fy - sy0) * kSrcTileW + (fx - sx0); wgt[0] = dx * dy; }
+                if (cxo && cyo) { key[1] = (cy - sy0) * kSrcTileW + (cx - sx0); wgt[1] = (1.f - dx) * (1.f - dy); }
+                if (fxo && cyo) { key[2] = (cy - sy0) * kSrcTileW + (fx - sx0); wgt[2] = dx * (1.f - dy); }
+                if (cxo && fyo) { key[3] = (fy - sy0) * kSrcTileW + (cx - sx0); wgt[3] = (1.f - dx) * dy; }
+            }
+            const bool mine = key[0] >= 0 || key[1] >= 0 || key[2] >= 0 || key[3] >= 0;
+            if (!__any_sync(0xffffffffu, mine)) continue;
+            float gv[CT ? CT : 8];
+#pragma unroll
+            for (int c = 0; c < (CT ? CT : 8); ++c) {
+                gv[c] = 0.f;
+                if ((CT || c < C) && mine) gv[c] = __ldg(grad_out + (((long long)b * g.Ho + i) * g.Wo + j) * C + c);
+            }
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                float val[CT ? CT : 8];
+#pragma unroll
+                for (int c = 0; c < (CT ? CT : 8); ++c) val[c] = gv[c] * wgt[tap];
+                accumulate_ranked<CT>(acc, key[tap], val, C);
+            }
+        }
+    }
+    __syncthreads();
+    // fixed-order sum of the warp-private tiles; each grad_data element is written once
+    const int seg = (sx1 - sx0 + 1) * C;
+    for (int r = warp; r <= sy1 - sy0; r += kWarps) {
+        float* dst = grad_data + (((long long)b * g.H + sy0 + r) * g.W + sx0) * C;
+        for (int e = lane; e < seg; e += 32) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) sum += s_acc[w * tile_floats + r * kSrcTileW * C + e];
+            dst[e] = sum;
+        }
+    }
+}
+
+int make_geom(Geom& g, int B, int H, int W, int C, int Ho, int Wo, unsigned flags) {
+    DMV_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, DMV_E_INVALID_ARG, "sampler: non-positive dimension");
+    DMV_REQUIRE(C <= 16, DMV_E_UNSUPPORTED_SHAPE, "sampler: C > 16 unsupported");
+    DMV_REQUIRE((flags & ~3u) == 0, DMV_E_INVALID_ARG, "sampler: unknown flag");
+    g.B = B; g.H = H; g.W = W; g.C = C; g.Ho = Ho; g.Wo = Wo; g.flags = flags;
+    g.tw_shift = (Ho == 1) ? 10 : 5;  // 1-D sample lists use 1x1024 tiles, images 32x32
+    g.tiles_x = ceil_div(Wo, 1 << g.tw_shift);
+    g.tiles_y = ceil_div(Ho, kTilePix >> g.tw_shift);
+    DMV_REQUIRE((long long)B * g.tiles_x * g.tiles_y < (1ll << 31), DMV_E_UNSUPPORTED_SHAPE, "sampler: too many tiles");
+    return DMV_OK;
+}
+
+template <int MODE>
+int launch_tile(const float* data, const float* wf, const float* go, float* out, int32_t* di, uint8_t* dm,
+                const Geom& g, cudaStream_t st) {
+    const int grid = g.B * g.tiles_x * g.tiles_y;
+    const size_t smem = kStageFloats * sizeof(float);
+#define DMV_LAUNCH_TILE(CT)                                                                              \
+    do {                                                                                                 \
+        static bool attr_done = false;                                                                   \
+        if (!attr_done) {                                                                                \
+            cudaFuncSetAttribute(sampler_tile_kernel<CT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            attr_done = true;                                                                            \
+        }                                                                                                \
+        sampler_tile_kernel<CT, MODE><<<grid, kThreads, smem, st>>>(data, wf, go, out, di, dm, g);       \
+    } while (0)
+    switch (g.C) {
+        case 1: DMV_LAUNCH_TILE(1); break;
+        case 3: DMV_LAUNCH_TILE(3); break;
+        case 4: DMV_LAUNCH_TILE(4); break;
+        default: DMV_LAUNCH_TILE(0); break;
+    }
+#undef DMV_LAUNCH_TILE
+    return check_launch(MODE == 0 ? "sampler_fwd" : "sampler_grad_warp");
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmv_sampler_fwd(const float* data, const float* wf, float* out, int32_t* dbg_idx, uint8_t* dbg_mask, int B,
+                    int H, int W, int C, int Hout, int Wout, unsigned flags, void* stream) {
+    DMV_REQUIRE(data && wf && out, DMV_E_INVALID_ARG, "sampler_fwd: null pointer");
+    DMV_REQUIRE(((uintptr_t)wf & 7) == 0, DMV_E_ALIGN, "sampler_fwd: warp/flow must be 8-byte aligned");
+    DMV_REQUIRE(!dbg_idx || ((uintptr_t)dbg_idx & 15) == 0, DMV_E_ALIGN, "sampler_fwd: dbg_idx must be 16-byte aligned");
+    Geom g;
+    int rc = make_geom(g, B, H, W, C, Hout, Wout, flags);
+    if (rc) return rc;
+    return launch_tile<0>(data, wf, nullptr, out, dbg_idx, dbg_mask, g, (cudaStream_t)stream);
+}
+
+size_t dmv_sampler_bwd_workspace_size(int B, int H, int W, int C, int Hout, int Wout) {
+    (void)H; (void)W; (void)C;
+    if (B <= 0 || Hout <= 0 || Wout <= 0) return 0;
+    const int tw_shift = (Hout == 1) ? 10 : 5;
+    const long long tiles = (long long)B * ceil_div(Wout, 1 << tw_shift) * ceil_div(Hout, kTilePix >> tw_shift);
+    return (size_t)tiles * sizeof(int4);
+}
+
+int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out, float* grad_data, float* grad_wf,
+                    int B, int H, int W, int C, int Hout, int Wout, unsigned flags, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    DMV_REQUIRE(data && wf && grad_out, DMV_E_INVALID_ARG, "sampler_bwd: null pointer");
+    DMV_REQUIRE(grad_data || grad_wf, DMV_E_INVALID_ARG, "sampler_bwd: nothing to compute");
+    DMV_REQUIRE(((uintptr_t)wf & 7) == 0 && ((uintptr_t)grad_wf & 7) == 0, DMV_E_ALIGN, "sampler_bwd: warp buffers must be 8-byte aligned");
+    Geom g;
+    int rc = make_geom(g, B, H, W, C, Hout, Wout, flags);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_wf) {
+        rc = launch_tile<1>(data, wf, grad_out, grad_wf, nullptr, nullptr, g, st);
+        if (rc) return rc;
+    }
+    if (grad_data) {
+        DMV_REQUIRE(C <= 8, DMV_E_UNSUPPORTED_SHAPE, "sampler_bwd: grad_data supports C <= 8");
+        const size_t need = dmv_sampler_bwd_workspace_size(B, H, W, C, Hout, Wout);
+        DMV_REQUIRE(workspace && workspace_bytes >= need, DMV_E_WORKSPACE, "sampler_bwd: workspace too small");
+        DMV_REQUIRE(((uintptr_t)workspace & 15) == 0, DMV_E_ALIGN, "sampler_bwd: workspace must be 16-byte aligned");
+        int4* boxes = reinterpret_cast<int4*>(workspace);
+        const int out_tiles = g.B * g.tiles_x * g.tiles_y;
+        sampler_box_kernel<<<out_tiles, kThreads, 0, st>>>(wf, boxes, g);
+        rc = check_launch("sampler_box");
+        if (rc) return rc;
+        const int stx = ceil_div(W, kSrcTileW), sty = ceil_div(H, kSrcTileH);
+        const int grid = B * stx * sty;
+        const size_t smem = (size_t)kWarps * kSrcTileH * kSrcTileW * C * sizeof(float);
+#define DMV_LAUNCH_GD(CT)                                                                                         \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(sampler_grad_data_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        sampler_grad_data_kernel<CT><<<grid, kThreads, smem, st>>>(wf, grad_out, boxes, grad_data, g, stx, sty);   \
+    } while (0)
+        switch (C) {
+            case 1: DMV_LAUNCH_GD(1); break;
+            case 3: DMV_LAUNCH_GD(3); break;
+            case 4: DMV_LAUNCH_GD(4); break;
+            default: DMV_LAUNCH_GD(0); break;
+        }
+#undef DMV_LAUNCH_GD
+        rc = check_launch("sampler_grad_data");
+        if (rc) return rc;
+    }
+    return DMV_OK;
+}
+
+}  // extern "C"

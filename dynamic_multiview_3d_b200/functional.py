@@ -1,0 +1,481 @@
+"""torch.autograd glue over the C ABI of libdmv3d.so.
+
+PyTorch owns device memory, streams and the autograd tape; every computation here is one
+call into libdmv3d with raw device pointers on the current CUDA stream.  Nothing falls back
+to PyTorch or CPU arithmetic: a tensor that is not on a CUDA device raises.
+
+Parameter gradients are NOT routed through autograd: the wgrad kernels write them straight
+into the variable's slot of the flat gradient buffer (variables.py) and backward returns
+None for parameters.  ``anchor`` is a dummy leaf that keeps the tape alive when the only
+differentiable inputs are parameters (first layer on a network input).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, ALGO, DT_BF16, DT_F32, LOSS, SAMPLER_ADD_GRID, SAMPLER_GRID_XY
+from ._lib import call as _real_call
+
+_workspaces = {}
+_default_algo = "auto"
+
+
+def set_default_algo(name):
+    """'auto' (tcgen05 where covered, else SIMT), 'simt', or 'tcgen05'."""
+    global _default_algo
+    if name not in ALGO:
+        raise ValueError(name)
+    _default_algo = name
+
+
+def get_default_algo():
+    return _default_algo
+
+
+def _algo(a):
+    return ALGO[_default_algo if a is None else a]
+
+
+def _stream(t):
+    if t.is_meta:
+        return None
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def call(name, *args):
+    """Launch through the C ABI.  Tensors on the ``meta`` device carry shapes only (used by the
+    CPU host-logic tests to build a model's variable table without a GPU): their data
+    pointers are 0 and nothing is launched -- and nothing is computed either."""
+    if _meta_depth[0]:
+        return
+    if _profile[0] is None:
+        _real_call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _real_call(name, *args)
+    e1.record()
+    _profile[0].append((name, _tag[0], e0, e1))
+
+
+_profile = [None]
+_tag = [""]
+
+
+class profile_calls:
+    """Context: time every C-ABI call with CUDA events on the current stream.
+    ``records`` -> [(entry point, variable tag, milliseconds)] after exit."""
+
+    def __enter__(self):
+        self._raw = []
+        _profile[0] = self._raw
+        return self
+
+    def __exit__(self, *a):
+        _profile[0] = None
+        torch.cuda.synchronize()
+        self.records = [(n, t, e0.elapsed_time(e1)) for n, t, e0, e1 in self._raw]
+
+
+_meta_depth = [0]
+
+
+class meta_mode:
+    """Context: shape inference only (inputs on the meta device)."""
+
+    def __enter__(self):
+        _meta_depth[0] += 1
+
+    def __exit__(self, *a):
+        _meta_depth[0] -= 1
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda and not t.is_meta:
+            raise _lib.DmvError("tensor on %s: the path runs on CUDA only (no CPU fallback)" % t.device)
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    if t.dtype == torch.float32:
+        return DT_F32
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _p(t):
+    return None if (t is None or t.is_meta) else t.data_ptr()
+
+
+def workspace(nbytes, device):
+    """One growable scratch buffer per device (all launches are stream-ordered on one stream)."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def same_out(n, s):
+    return -(-n // s)
+
+
+def _anchor_for(t):
+    a = torch.zeros(1, device=t.device, requires_grad=True)
+    return a
+
+
+# ----------------------------------------------------------------------------- conv / deconv / linear
+class _Conv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, x, wvar, bvar, stride, act, algo, out_dtype):
+        _need_cuda(x)
+        x = x.contiguous()
+        B, H, W, Cin = x.shape
+        kh, kw, wcin, Cout = wvar.shape
+        assert wcin == Cin, (wvar.name, wvar.shape, x.shape)
+        y = torch.empty((B, same_out(H, stride), same_out(W, stride), Cout), dtype=out_dtype, device=x.device)
+        _tag[0] = wvar.name
+        call("dmv_conv2d_fwd", _p(x), _dt(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
+             B, H, W, Cin, Cout, kh, kw, stride, ACT[act], algo, _stream(x))
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (wvar, bvar, stride, act, algo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        wvar, bvar, stride, act, algo = ctx.cfg
+        B, H, W, Cin = x.shape
+        kh, kw, _, Cout = wvar.shape
+        st = _stream(x)
+        _tag[0] = wvar.name
+        dy = dy.contiguous()
+        if dy.dtype != torch.bfloat16 or ACT[act]:
+            dpre = torch.empty(y.shape, dtype=y.dtype, device=y.device)
+            call("dmv_act_bwd", _p(dy), _p(y), _p(dpre), _dt(y), y.numel(), ACT[act], st)
+            if dpre.dtype != torch.bfloat16:
+                h = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
+                call("dmv_cast_f32_to_bf16", _p(dpre), _p(h), h.numel(), st)
+                dpre = h
+        else:
+            dpre = dy
+        dx = None
+        if ctx.needs_input_grad[1]:
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), B, H, W, Cin, Cout, kh, kw, stride, algo, st)
+            if x.dtype != torch.bfloat16:
+                dxf = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+                call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
+                dx = dxf
+        pixels = B * y.shape[1] * y.shape[2]
+        nws = _lib.load().dmv_wgrad_workspace_size(kh * kw, Cin, Cout, pixels)
+        ws = workspace(nws, x.device)
+        call("dmv_conv2d_wgrad", _p(x), _dt(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if bvar is not None else None,
+             B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
+        store = wvar.store
+        if bvar is not None:
+            store.notify_grad(bvar)
+        store.notify_grad(wvar)
+        return None, dx, None, None, None, None, None, None
+
+
+class _Deconv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, x, wvar, out_hw, stride, act, algo, out_dtype):
+        _need_cuda(x)
+        x = x.contiguous()
+        if x.dtype != torch.bfloat16:
+            raise TypeError("deconv input must be bf16")
+        B, Hin, Win, Cin = x.shape
+        kh, kw, Cout, wcin = wvar.shape
+        assert wcin == Cin, (wvar.name, wvar.shape, x.shape)
+        Ho, Wo = out_hw
+        assert same_out(Ho, stride) == Hin and same_out(Wo, stride) == Win, "output_shape inconsistent with input"
+        y = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
+        _tag[0] = wvar.name
+        call("dmv_deconv2d_fwd", _p(x), _p(wvar.half), _p(y), _dt(y), B, Ho, Wo, Cin, Cout, kh, kw, stride, ACT[act], algo,
+             _stream(x))
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (wvar, stride, act, algo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        wvar, stride, act, algo = ctx.cfg
+        B, Ho, Wo, Cout = y.shape
+        kh, kw, _, Cin = wvar.shape
+        st = _stream(x)
+        _tag[0] = wvar.name
+        dy = dy.contiguous()
+        if ACT[act]:
+            dpre = torch.empty(y.shape, dtype=y.dtype, device=y.device)
+            call("dmv_act_bwd", _p(dy), _p(y), _p(dpre), _dt(y), y.numel(), ACT[act], st)
+        else:
+            dpre = dy
+        dx = None
+        if ctx.needs_input_grad[1]:
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            call("dmv_deconv2d_dgrad", _p(dpre), _dt(dpre), _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, algo, st)
+        pixels = B * x.shape[1] * x.shape[2]
+        nws = _lib.load().dmv_wgrad_workspace_size(kh * kw, Cout, Cin, pixels)
+        ws = workspace(nws, x.device)
+        call("dmv_deconv2d_wgrad", _p(x), _p(dpre), _dt(dpre), _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
+             ws.numel(), algo, st)
+        wvar.store.notify_grad(wvar)
+        return None, dx, None, None, None, None, None, None
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, x, wvar, bvar, act, algo):
+        _need_cuda(x)
+        x = x.contiguous()
+        if x.dtype != torch.bfloat16:
+            raise TypeError("linear input must be bf16")
+        M, K = x.shape
+        wk, N = wvar.shape
+        assert wk == K, (wvar.name, wvar.shape, x.shape)
+        y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+        _tag[0] = wvar.name
+        call("dmv_linear_fwd", _p(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), M, K, N, ACT[act],
+             algo, _stream(x))
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (wvar, bvar, act, algo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        wvar, bvar, act, algo = ctx.cfg
+        M, K = x.shape
+        N = wvar.shape[1]
+        st = _stream(x)
+        _tag[0] = wvar.name
+        dy = dy.contiguous()
+        if ACT[act]:
+            dpre = torch.empty_like(y)
+            call("dmv_act_bwd", _p(dy), _p(y), _p(dpre), DT_BF16, y.numel(), ACT[act], st)
+        else:
+            dpre = dy
+        dx = None
+        if ctx.needs_input_grad[1]:
+            dx = torch.empty_like(x)
+            call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, algo, st)
+        nws = _lib.load().dmv_wgrad_workspace_size(1, K, N, M)
+        ws = workspace(nws, x.device)
+        call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if bvar is not None else None, M, K, N,
+             _p(ws), ws.numel(), algo, st)
+        if bvar is not None:
+            wvar.store.notify_grad(bvar)
+        wvar.store.notify_grad(wvar)
+        return None, dx, None, None, None, None
+
+
+def conv2d(x, wvar, bvar, stride, act=None, algo=None, out_dtype=torch.bfloat16):
+    return _Conv2d.apply(wvar.store.anchor, x, wvar, bvar, int(stride), act, _algo(algo), out_dtype)
+
+
+def deconv2d(x, wvar, out_hw, stride, act=None, algo=None, out_dtype=torch.bfloat16):
+    return _Deconv2d.apply(wvar.store.anchor, x, wvar, (int(out_hw[0]), int(out_hw[1])), int(stride), act, _algo(algo), out_dtype)
+
+
+def linear(x, wvar, bvar, act=None, algo=None):
+    return _Linear.apply(wvar.store.anchor, x, wvar, bvar, act, _algo(algo))
+
+
+# ----------------------------------------------------------------------------- activations
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        _need_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("dmv_act_fwd", _p(x), _p(y), _dt(x), x.numel(), ACT[act], _stream(x))
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(y)
+        call("dmv_act_bwd", _p(dy), _p(y), _p(dx), _dt(y), y.numel(), ACT[ctx.act], _stream(y))
+        return dx, None
+
+
+def activation(x, act):
+    return _Act.apply(x, act)
+
+
+# ----------------------------------------------------------------------------- sampler
+class _Resampler(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, wf, flags):
+        _need_cuda(data, wf)
+        if data.dtype != torch.float32 or wf.dtype != torch.float32:
+            raise TypeError("resampler runs in float32 (reference precision)")
+        data = data.contiguous()
+        wf = wf.contiguous()
+        B, H, W, Cc = data.shape
+        assert wf.shape[0] == B and wf.shape[-1] == 2
+        out_shape = tuple(wf.shape[:-1]) + (Cc,)
+        if wf.dim() == 4:
+            Ho, Wo = wf.shape[1], wf.shape[2]
+        else:                                   # [B, N, 2] sample lists
+            Ho, Wo = 1, int(wf.numel() // (2 * B))
+        out = torch.empty(out_shape, dtype=torch.float32, device=data.device)
+        _tag[0] = "sampler"
+        call("dmv_sampler_fwd", _p(data), _p(wf), _p(out), None, None, B, H, W, Cc, Ho, Wo, flags, _stream(data))
+        ctx.save_for_backward(data, wf)
+        ctx.geom = (B, H, W, Cc, Ho, Wo, flags)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        data, wf = ctx.saved_tensors
+        B, H, W, Cc, Ho, Wo, flags = ctx.geom
+        go = go.contiguous()
+        need_d, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gd = torch.empty_like(data) if need_d else None
+        gw = torch.empty_like(wf) if need_w else None
+        if not (need_d or need_w):
+            return None, None, None
+        nws = _lib.load().dmv_sampler_bwd_workspace_size(B, H, W, Cc, Ho, Wo)
+        ws = workspace(nws, data.device)
+        _tag[0] = "sampler"
+        call("dmv_sampler_bwd", _p(data), _p(wf), _p(go), _p(gd), _p(gw), B, H, W, Cc, Ho, Wo, flags, _p(ws), ws.numel(),
+             _stream(data))
+        return gd, gw, None
+
+
+def resampler(data, warp):
+    """tf.contrib.resampler.resampler(data[B,H,W,C], warp[B,...,2]); warp[...,0] = x, [...,1] = y."""
+    return _Resampler.apply(data, warp, 0)
+
+
+def flow_resampler(data, flow, grid_order="ref_yx"):
+    """resample_layer(src, warp_pts_layer(flow)) with the grid formed inside the kernel."""
+    flags = SAMPLER_ADD_GRID | (SAMPLER_GRID_XY if grid_order == "xy" else 0)
+    if grid_order not in ("ref_yx", "xy"):
+        raise ValueError(grid_order)
+    return _Resampler.apply(data, flow, flags)
+
+
+def resampler_debug(data, wf, flags=0):
+    """Forward plus the bit-exact targets: corner indices [.,4] int32 and predicate mask uint8."""
+    _need_cuda(data, wf)
+    data, wf = data.contiguous(), wf.contiguous()
+    B, H, W, Cc = data.shape
+    Ho, Wo = (wf.shape[1], wf.shape[2]) if wf.dim() == 4 else (1, int(wf.numel() // (2 * B)))
+    out = torch.empty(tuple(wf.shape[:-1]) + (Cc,), dtype=torch.float32, device=data.device)
+    idx = torch.empty(tuple(wf.shape[:-1]) + (4,), dtype=torch.int32, device=data.device)
+    mask = torch.empty(tuple(wf.shape[:-1]), dtype=torch.uint8, device=data.device)
+    call("dmv_sampler_fwd", _p(data), _p(wf), _p(out), _p(idx), _p(mask), B, H, W, Cc, Ho, Wo, flags, _stream(data))
+    return out, idx, mask
+
+
+# ----------------------------------------------------------------------------- losses
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gen, logits, target, mask, weights, mode, inv_count, want_fused):
+        _need_cuda(gen, target)
+        gen = gen.contiguous()
+        target = target.contiguous()
+        V = 1 if logits is None else gen.shape[0]
+        Cc = gen.shape[-1]
+        pixels = target.numel() // Cc
+        if logits is not None:
+            logits = logits.contiguous()
+        if mask is not None:
+            mask = mask.contiguous()
+        w = (C.c_float * Cc)(*[float(x) for x in weights])
+        loss = torch.empty((), dtype=torch.float32, device=gen.device)
+        need_g = ctx.needs_input_grad[0]
+        need_l = logits is not None and ctx.needs_input_grad[1]
+        gg = torch.empty_like(gen) if need_g else None
+        gl = torch.empty_like(logits) if need_l else None
+        fused = torch.empty_like(target) if (want_fused and V > 1) else None
+        nws = _lib.load().dmv_loss_workspace_size(pixels)
+        ws = _loss_ws(gen.device, nws)
+        _tag[0] = "loss"
+        call("dmv_loss_fused_fwd_bwd", _p(gen), _p(logits), V, _p(target), _p(mask), w, LOSS[mode], float(inv_count), _p(loss),
+             _p(gg), _p(gl), _p(fused), pixels, Cc, _p(ws), ws.numel(), _stream(gen))
+        ctx.grads = (gg, gl)
+        ctx.mark_non_differentiable(*([fused] if fused is not None else []))
+        if fused is not None:
+            return loss, fused
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        gg, gl = ctx.grads
+        st = _stream(gloss)
+        _tag[0] = "loss"
+        gloss = gloss.contiguous().to(torch.float32)
+        # chain the upstream scalar on the device (1.0 for a plain loss.backward())
+        if gg is not None:
+            call("dmv_scale_by_device_scalar", _p(gg), _p(gloss), gg.numel(), st)
+        if gl is not None:
+            call("dmv_scale_by_device_scalar", _p(gl), _p(gloss), gl.numel(), st)
+        return gg, gl, None, None, None, None, None, None
+
+
+_loss_wss = {}
+
+
+def _loss_ws(device, nbytes):
+    """The loss workspace holds a self-resetting counter, so it is zero-initialised once and
+    never shared with other kernels."""
+    key = (device.type, device.index)
+    ws = _loss_wss.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+        _loss_wss[key] = ws
+    return ws
+
+
+def reconstruction_loss(gen, target, mode="l2", weights=None, inv_count=None, mask=None):
+    """mean_{b,h,w} sum_c w_c * (d^2 | |d|), d = (gen - target) * mask; gradient fused in."""
+    Cc = gen.shape[-1]
+    weights = [1.0] * Cc if weights is None else list(weights)
+    if inv_count is None:
+        inv_count = 1.0 / (target.numel() // Cc)
+    return _FusedLoss.apply(gen, None, target, mask, tuple(weights), mode, inv_count, False)
+
+
+def fused_views_loss(gens, logits, target, mode="l2", weights=None, inv_count=None, mask=None, want_fused=True):
+    """Confidence-weighted fusion of V warped views + loss:
+    gens [V,B,H,W,C], logits [V,B,H,W] -> (loss, fused [B,H,W,C])."""
+    Cc = gens.shape[-1]
+    weights = [1.0] * Cc if weights is None else list(weights)
+    if inv_count is None:
+        inv_count = 1.0 / (target.numel() // Cc)
+    return _FusedLoss.apply(gens, logits, target, mask, tuple(weights), mode, inv_count, want_fused)
+
+
+# ----------------------------------------------------------------------------- casts (network inputs)
+def to_bf16(x):
+    """fp32 -> bf16 for non-differentiable network inputs (viewpoint codes)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype == torch.bfloat16:
+        return x
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("dmv_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _stream(x))
+    return y
+
+
+def to_f32(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype == torch.float32:
+        return x
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call("dmv_cast_bf16_to_f32", _p(x), _p(y), x.numel(), _stream(x))
+    return y

@@ -1,0 +1,63 @@
+"""Deterministic synthetic "car-render-shaped" batches.
+
+float32 NHWC images in [0,1] on the reference renderer's 0.5-grey background
+(multi_view_model/utils/renderer.py:44-47), a filled rotated ellipse as the car blob,
+N(0, 0.02) noise; image1 is the same blob rotated by the sampled azimuth difference.
+Depth: 1.0 far plane, blob at 0.3-0.6.  Viewpoint: one-hot azimuth (V=19 bins of 20 deg) or
+the reference-native (d_elevation, d_azimuth) radians (collect_data_node.py:125-131).
+Host-side NumPy: this is input generation, not part of the measured path.
+"""
+import numpy as np
+
+
+def make_batch(batch, size=224, viewpoint="onehot19", seed=1234, rank=0, depth=False, views=1):
+    rng = np.random.default_rng(seed + rank)
+    H = W = size
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    cy, cx = (H - 1) / 2.0, (W - 1) / 2.0
+
+    def blob(yaw, colour, jitter):
+        c, s = np.cos(yaw), np.sin(yaw)
+        u = ((xx - cx - jitter[0]) * c + (yy - cy - jitter[1]) * s) / (0.275 * W)
+        v = (-(xx - cx - jitter[0]) * s + (yy - cy - jitter[1]) * c) / (0.125 * H)
+        m = (u * u + v * v) <= 1.0
+        img = np.full((H, W, 3), 0.5, np.float32)
+        img[m] = colour
+        return img, m
+
+    n_src = max(1, views)
+    image0 = np.empty((batch, n_src, H, W, 3), np.float32)
+    image1 = np.empty((batch, H, W, 3), np.float32)
+    depth0 = np.ones((batch, H, W, 1), np.float32)
+    depth1 = np.ones((batch, H, W, 1), np.float32)
+    mask1 = np.zeros((batch, H, W, 1), np.float32)
+    bins = rng.integers(0, 19, size=batch)
+    disp = np.zeros((batch, 19 if viewpoint == "onehot19" else 2), np.float32)
+    for b in range(batch):
+        colour = rng.uniform(0.1, 0.9, size=3).astype(np.float32)
+        jit = rng.uniform(-4, 4, size=2)
+        yaw1 = rng.uniform(0, 2 * np.pi)
+        daz = np.deg2rad(20.0 * bins[b])
+        img1, m1 = blob(yaw1, colour, jit)
+        image1[b] = img1
+        dval = rng.uniform(0.3, 0.6)
+        depth1[b, m1, 0] = dval
+        mask1[b, m1, 0] = 1.0
+        for v in range(n_src):
+            yaw0 = yaw1 - daz - np.deg2rad(10.0 * v)
+            img0, m0 = blob(yaw0, colour, jit)
+            image0[b, v] = img0
+            if v == 0:
+                depth0[b, m0, 0] = dval
+        if viewpoint == "onehot19":
+            disp[b, bins[b]] = 1.0
+        else:
+            disp[b] = (0.0, daz)
+    image0 += rng.normal(0, 0.02, image0.shape).astype(np.float32)
+    image1 += rng.normal(0, 0.02, image1.shape).astype(np.float32)
+    np.clip(image0, 0, 1, out=image0)
+    np.clip(image1, 0, 1, out=image1)
+    out = {"image0": image0[:, 0] if views <= 1 else image0, "image1": image1, "disp": disp}
+    if depth:
+        out.update(depth0=depth0, depth1=depth1, mask1=mask1)
+    return out

@@ -1,0 +1,190 @@
+"""Variable store: the stand-in for TensorFlow's variable scopes on this path.
+
+The reference creates variables lazily by name inside ``tf.variable_scope(name)``
+(dyn_mult_view/mv3d/utils/tf_utils.py:60-65, 71-80, 88-95): ``name/Matrix``, ``name/b``
+(FC), ``name/w``, ``name/b`` (conv), ``name/w`` (deconv).  The same names are kept here so a
+checkpoint maps 1:1.
+
+Layout in HBM: after the first forward has created every variable, ``finalize()`` moves the
+fp32 masters, their gradients, Adam's m and v, and the bf16 compute copies into five flat
+buffers in creation order.  Gradients are written straight into the flat gradient buffer by
+the wgrad kernels (no autograd accumulation pass); data-parallel buckets are contiguous
+slices of it, and Adam is one multi-tensor launch over the flat views.
+"""
+import contextlib
+import math
+
+import torch
+
+_ALIGN = 64  # elements; keeps every view 128/256-byte aligned for vector and TMA access
+
+
+class Variable:
+    __slots__ = ("name", "shape", "master", "grad", "m", "v", "half", "trainable", "offset", "numel", "store", "used")
+
+    def __init__(self, name, tensor, trainable=True):
+        self.name = name
+        self.shape = tuple(tensor.shape)
+        self.master = tensor
+        self.numel = tensor.numel()
+        self.grad = self.m = self.v = self.half = None
+        self.trainable = trainable
+        self.offset = -1
+        self.used = False
+
+
+class VariableStore:
+    def __init__(self, device, seed=0):
+        self.device = torch.device(device)
+        self.vars = {}          # name -> Variable, in creation order
+        self._scope = []
+        self.finalized = False
+        self.gen = torch.Generator(device="cpu")
+        self.gen.manual_seed(seed)
+        self.grad_ready_hook = None     # called with a Variable when its gradient has been written
+        self.flat = {}
+        # dummy differentiable leaf: keeps the autograd tape alive for layers whose only
+        # differentiable inputs are parameters (gradients of parameters bypass autograd)
+        self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
+
+    # -- scopes -------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def scope(self, name):
+        self._scope.append(name)
+        try:
+            yield
+        finally:
+            self._scope.pop()
+
+    def full_name(self, name):
+        return "/".join(self._scope + [name])
+
+    # -- creation (reference initialisers, tf_utils.py:54-98) -----------------------------
+    def get(self, name, shape, init, stddev=0.0):
+        full = self.full_name(name)
+        v = self.vars.get(full)
+        if v is not None:
+            if tuple(shape) != v.shape:
+                raise ValueError("variable %s exists with shape %s, requested %s" % (full, v.shape, tuple(shape)))
+            v.used = True
+            return v
+        if self.finalized:
+            raise RuntimeError("variable store is finalized; cannot create %s" % full)
+        shape = tuple(int(s) for s in shape)
+        if self.device.type == "meta":         # shape-only build (CPU host-logic tests)
+            v = Variable(full, torch.empty(shape, dtype=torch.float32, device="meta"))
+            v.used, v.store = True, self
+            v.grad = torch.empty(shape, dtype=torch.float32, device="meta")
+            v.half = torch.empty(shape, dtype=torch.bfloat16, device="meta")
+            self.vars[full] = v
+            return v
+        if init == "zeros":
+            t = torch.zeros(shape, dtype=torch.float32)
+        elif init == "normal":                 # tf.random_normal_initializer(stddev)
+            t = torch.randn(shape, generator=self.gen, dtype=torch.float32) * stddev
+        elif init == "truncated_normal":       # tf.truncated_normal_initializer: re-draw beyond 2 sigma
+            t = torch.randn(shape, generator=self.gen, dtype=torch.float32)
+            bad = t.abs() > 2
+            while bool(bad.any()):
+                t[bad] = torch.randn(int(bad.sum()), generator=self.gen, dtype=torch.float32)
+                bad = t.abs() > 2
+            t = t * stddev
+        else:
+            raise ValueError(init)
+        v = Variable(full, t.to(self.device))
+        v.used = True
+        v.store = self
+        # stand-alone buffers until finalize() re-homes them into the flat storage
+        v.grad = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        v.half = torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+        self._cast(v.master, v.half, v.numel)
+        self.vars[full] = v
+        return v
+
+    def _cast(self, src, dst, n):
+        from . import _lib
+        if self.device.type != "cuda":
+            raise _lib.DmvError("variables live on a CUDA device; there is no CPU path")
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("dmv_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), n, st)
+
+    # -- flat storage -----------------------------------------------------------------------
+    def finalize(self, trainable=None):
+        """Flatten.  ``trainable`` is an optional predicate name -> bool; variables that never
+        receive a gradient (the dead FCs of highdim_angle.py:8-9) must be excluded."""
+        if self.finalized:
+            return
+        total = 0
+        for v in self.vars.values():
+            if trainable is not None:
+                v.trainable = bool(trainable(v.name))
+            v.offset = total
+            total += int(math.ceil(v.numel / _ALIGN)) * _ALIGN
+        dev = self.device
+        self.total = total
+        if dev.type == "meta":
+            self.finalized = True
+            return
+        self.flat = {
+            "master": torch.zeros(total, dtype=torch.float32, device=dev),
+            "grad": torch.zeros(total, dtype=torch.float32, device=dev),
+            "m": torch.zeros(total, dtype=torch.float32, device=dev),
+            "v": torch.zeros(total, dtype=torch.float32, device=dev),
+            "half": torch.zeros(total, dtype=torch.bfloat16, device=dev),
+        }
+        for v in self.vars.values():
+            sl = slice(v.offset, v.offset + v.numel)
+            self.flat["master"][sl].copy_(v.master.reshape(-1))
+            v.master = self.flat["master"][sl].view(v.shape)
+            v.grad = self.flat["grad"][sl].view(v.shape)
+            v.m = self.flat["m"][sl].view(v.shape)
+            v.v = self.flat["v"][sl].view(v.shape)
+            v.half = self.flat["half"][sl].view(v.shape)
+        self.total = total
+        self.finalized = True
+        self.refresh_half()
+
+    def refresh_half(self):
+        """bf16 compute copies of every master (Adam keeps them current afterwards)."""
+        self._cast(self.flat["master"], self.flat["half"], self.total)
+
+    def trainable_vars(self):
+        return [v for v in self.vars.values() if v.trainable]
+
+    def notify_grad(self, var):
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(var)
+
+    # -- checkpoint surface (names as in a TF-1.3 checkpoint) --------------------------------
+    def state_dict(self):
+        return {k: v.master.detach().cpu().clone() for k, v in self.vars.items()}
+
+    def load_state_dict(self, sd):
+        for k, t in sd.items():
+            v = self.vars[k]
+            v.master.copy_(torch.as_tensor(t).to(self.device).reshape(v.shape))
+            if not self.finalized:
+                self._cast(v.master, v.half, v.numel)
+        if self.finalized:
+            self.refresh_half()
+
+    def num_params(self):
+        return sum(v.numel for v in self.vars.values())
+
+
+_current = []
+
+
+def current_store():
+    if not _current:
+        raise RuntimeError("no active VariableStore; wrap the graph in `with use_store(store):`")
+    return _current[-1]
+
+
+@contextlib.contextmanager
+def use_store(store):
+    _current.append(store)
+    try:
+        yield store
+    finally:
+        _current.pop()

@@ -1,0 +1,190 @@
+/*
+ * dmv3d.h -- C ABI of libdmv3d.so: hand-written sm_100a CUDA kernels for the
+ * appearance-flow training hot path of aclike/dynamic_multiview_3d.
+ *
+ * The reference has no FFI of its own (it is pure Python on TensorFlow 1.3); each entry
+ * point below replaces one TensorFlow library op that the reference's op helpers
+ * (dyn_mult_view/mv3d/utils/tf_utils.py) or its optimizer call dispatch to.  The
+ * "replaces" notes give the reference call site (paths relative to the reference root).
+ *
+ * Conventions:
+ *   - every function returns int: 0 = DMV_OK, negative = DMV_E_*; dmv_last_error() has the
+ *     message of the calling thread's last failure; nothing throws or aborts;
+ *   - all tensor pointers are DEVICE pointers, NHWC contiguous; the caller owns every
+ *     buffer (including workspaces, sized by the matching *_workspace_size call);
+ *   - every launch is asynchronous on the cudaStream_t passed as `stream` (void*);
+ *     no host synchronisation, no persistent allocation, no global mutable state
+ *     besides a diagnostic launch counter;
+ *   - "bf16" buffers hold __nv_bfloat16 (uint16_t storage).
+ */
+#ifndef DMV3D_H_
+#define DMV3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMV_OK 0
+#define DMV_E_INVALID_ARG (-1)
+#define DMV_E_ALIGN (-2)
+#define DMV_E_UNSUPPORTED_SHAPE (-3)
+#define DMV_E_CUDA (-4)
+#define DMV_E_WORKSPACE (-5)
+
+/* sampler flags */
+#define DMV_SAMPLER_ADD_GRID 1u /* input is a flow field; warp = flow + grid is formed in-kernel
+                                   (replaces warp_pts_layer + coords, tf_utils.py:35-52)        */
+#define DMV_SAMPLER_GRID_XY 2u  /* grid channel 0 = column, channel 1 = row.  Default (flag clear)
+                                   is the reference's (Y,X) order: channel 0 = ROW index,
+                                   tf_utils.py:48-51 -- zero flow then yields the transpose      */
+
+/* activations fused into epilogues (tf_utils.py:25-33; tanh heads main_model.py:79) */
+#define DMV_ACT_NONE 0
+#define DMV_ACT_LRELU 1 /* 0.6x + 0.4|x| */
+#define DMV_ACT_RELU 2  /* 0.5x + 0.5|x| */
+#define DMV_ACT_TANH 3
+
+/* loss modes */
+#define DMV_LOSS_L2 0 /* euclidean_loss, tf_utils.py:18-19 */
+#define DMV_LOSS_L1 1 /* l1_loss,        tf_utils.py:22-23 */
+
+/* element types of activation tensors at the conv/linear boundary */
+#define DMV_DT_BF16 0
+#define DMV_DT_F32 1
+
+/* implementation selector for conv/deconv/linear entry points */
+#define DMV_ALGO_AUTO 0    /* tcgen05/TMEM/TMA implicit GEMM where the shape allows, else SIMT */
+#define DMV_ALGO_SIMT 1    /* straightforward CUDA-core kernels (bring-up + on-GPU cross-check)  */
+#define DMV_ALGO_TCGEN05 2 /* force the tensor-core path; DMV_E_UNSUPPORTED_SHAPE if it cannot  */
+
+/* ---- library info ------------------------------------------------------------------- */
+int dmv_version(void);                      /* MAJOR*10000 + MINOR*100 + PATCH */
+const char* dmv_arch(void);                 /* "sm_100a" */
+int dmv_last_error(char* buf, size_t n);    /* copies the thread's last error text */
+long long dmv_launch_count(void);           /* kernels launched by this library so far */
+
+/* ---- bilinear sampler --------------------------------------------------------------- *
+ * replaces tf.contrib.resampler.resampler -- tf_utils.py:40-42 (resample_layer) and
+ * multi_view_model/tests/test_resampler.py:44; with DMV_SAMPLER_ADD_GRID also
+ * warp_pts_layer/coords (tf_utils.py:35-52).
+ *   data  [B,H,W,C] f32      wf [B,Hout,Wout,2] f32 (warp points, or flow with ADD_GRID)
+ *   out   [B,Hout,Wout,C] f32
+ *   dbg_idx  optional int32 [B,Hout,Wout,4] = (fx,fy,cx,cy), 0 for invalid samples
+ *   dbg_mask optional uint8 [B,Hout,Wout]: bit0 sample valid, bits1..4 taps
+ *            (fx,fy),(cx,cy),(fx,cy),(cx,fy) in range
+ * wf channel 0 is x (column of `data`), channel 1 is y (row).                          */
+int dmv_sampler_fwd(const float* data, const float* wf, float* out, int32_t* dbg_idx,
+                    uint8_t* dbg_mask, int B, int H, int W, int C, int Hout, int Wout,
+                    unsigned flags, void* stream);
+
+/* replaces the registered gradient "ResamplerGrad" (implicit via
+ * tf.train.AdamOptimizer.minimize, appearance_flow_model.py:77).
+ *   grad_data [B,H,W,C] f32 or NULL (skip: the source is a network input)
+ *   grad_wf   [B,Hout,Wout,2] f32 (gradient wrt warp == wrt flow)
+ * grad_data is produced by a deterministic owner-computes scatter (no fp32 atomics on
+ * global memory): same inputs -> same bits.  workspace: dmv_sampler_bwd_workspace_size. */
+size_t dmv_sampler_bwd_workspace_size(int B, int H, int W, int C, int Hout, int Wout);
+int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out,
+                    float* grad_data, float* grad_wf, int B, int H, int W, int C, int Hout,
+                    int Wout, unsigned flags, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- fused loss (+ multi-view confidence fusion) forward and backward ----------------- *
+ * replaces euclidean_loss / l1_loss (tf_utils.py:18-23) and the weighted sums of
+ * main_model.py:144-154, multiobject_appflow.py:223-283, plus their gradients.
+ *   gen     [V,B,H,W,C] f32 (V = 1: plain loss)       target [B,H,W,C] f32
+ *   logits  [V,B,H,W] f32 confidence logits, NULL when V == 1
+ *           fused = sum_v softmax_v(logits)_v * gen_v   (not in the reference)
+ *   mask    optional [B,H,W,1] f32: diff = (fused - target) * mask (masked_image_loss)
+ *   chan_weight host float[C]: per-channel loss weights (e.g. 1,1,1,0.1 for RGB-D)
+ *   inv_count  1 / (global B*H*W): the mean's divisor (global batch under data parallelism)
+ *   loss_out   device float[1]: sum_c w_c * L(diff_c) * inv_count   (overwritten)
+ *   grad_gen   [V,B,H,W,C] f32 or NULL; grad_logits [V,B,H,W] f32 or NULL
+ *   fused_out  optional [B,H,W,C] f32 (V > 1)
+ *   workspace  dmv_loss_workspace_size(B*H*W) bytes                                      */
+size_t dmv_loss_workspace_size(long long pixels);
+int dmv_loss_fused_fwd_bwd(const float* gen, const float* logits, int V, const float* target,
+                           const float* mask, const float* chan_weight, int mode,
+                           float inv_count, float* loss_out, float* grad_gen,
+                           float* grad_logits, float* fused_out, long long pixels, int C,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* x[i] *= *scalar (device scalar): chains an upstream loss gradient without a host sync */
+int dmv_scale_by_device_scalar(float* x, const float* scalar, long long n, void* stream);
+
+/* ---- conv / deconv / linear ----------------------------------------------------------- *
+ * TF-SAME padding is computed inside (out = ceil(in/s), extra padding bottom/right).
+ * Weights are bf16 copies of the fp32 masters in the REFERENCE layouts:
+ *   conv   w[kh,kw,Cin,Cout]   (tf_utils.py:75-77)      deconv w[kh,kw,Cout,Cin] (tf_utils.py:93-95)
+ *   linear Matrix[K,N]         (tf_utils.py:62-64)
+ * x_dtype / y_dtype are DMV_DT_*; accumulation is fp32.  bias may be NULL.
+ * `act` is fused into the forward epilogue; backward entry points take the gradient wrt
+ * the PRE-activation (dmv_act_bwd produces it from the post-activation output).          */
+
+/* replaces tf.nn.conv2d(...,'SAME') + b  -- conv2d_msra, tf_utils.py:70-84 */
+int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w_bf16, const float* bias, void* y,
+                   int y_dtype, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                   int stride, int act, int algo, void* stream);
+/* replaces Conv2DBackpropInput (implicit, appearance_flow_model.py:77) */
+int dmv_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int B, int H, int W,
+                     int Cin, int Cout, int kh, int kw, int stride, int algo, void* stream);
+/* replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 [kh,kw,Cin,Cout], db f32 [Cout] or NULL.
+ * Deterministic split-K (fixed-order second pass).  workspace: dmv_wgrad_workspace_size.   */
+size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels);
+int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy_bf16, float* dw, float* db, int B,
+                     int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                     void* workspace, size_t workspace_bytes, int algo, void* stream);
+
+/* replaces tf.nn.conv2d_transpose(x, w, output_shape, strides) -- deconv2d_msra,
+ * tf_utils.py:87-98 (no bias).  x [B,Hin,Win,Cin] -> y [B,Hout,Wout,Cout], where
+ * Hin == ceil(Hout/stride).                                                               */
+int dmv_deconv2d_fwd(const void* x_bf16, const void* w_bf16, void* y, int y_dtype, int B, int Hout,
+                     int Wout, int Cin, int Cout, int kh, int kw, int stride, int act, int algo,
+                     void* stream);
+int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w_bf16, void* dx_bf16, int B,
+                       int Hout, int Wout, int Cin, int Cout, int kh, int kw, int stride,
+                       int algo, void* stream);
+int dmv_deconv2d_wgrad(const void* x_bf16, const void* dy, int dy_dtype, float* dw, int B, int Hout,
+                       int Wout, int Cin, int Cout, int kh, int kw, int stride, void* workspace,
+                       size_t workspace_bytes, int algo, void* stream);
+
+/* replaces tf.matmul(x, Matrix) + b -- linear_msra, tf_utils.py:54-67, and its gradients */
+int dmv_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, void* y_bf16, int M,
+                   int K, int N, int act, int algo, void* stream);
+int dmv_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int M, int K, int N,
+                     int algo, void* stream);
+int dmv_linear_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, float* db, int M, int K,
+                     int N, void* workspace, size_t workspace_bytes, int algo, void* stream);
+
+/* ---- elementwise ---------------------------------------------------------------------- *
+ * replaces relu / lrelu (tf_utils.py:25-33), tf.nn.tanh and their gradients.
+ * dmv_act_bwd: dpre = dy * act'(y) computed from the POST-activation output y
+ * (lrelu/relu: slope by sign(y), TF's value at 0; tanh: 1 - y^2).                          */
+int dmv_act_fwd(const void* x, void* y, int dtype, long long n, int act, void* stream);
+int dmv_act_bwd(const void* dy, const void* y, void* dpre, int dtype, long long n, int act,
+                void* stream);
+int dmv_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+int dmv_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------ *
+ * replaces tf.train.AdamOptimizer(lr).minimize -- appearance_flow_model.py:77 (ApplyAdam):
+ *   m += (g - m)(1-b1);  v += (g*g - v)(1-b2);  theta -= (m * lr_t) / (sqrt(v) + eps)
+ * with lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) (eps NOT bias-corrected).
+ * dmv_adam_tick advances the device-resident state {b1^t, b2^t, lr_t, t} by one step so a
+ * captured CUDA graph needs no host-side scalar updates: state is float[4], initialise to
+ * {1, 1, 0, 0}.  dmv_adam_multi updates `count` tensors (host arrays of device pointers),
+ * optionally writing a bf16 copy of the new parameters; grad_scale multiplies the gradient
+ * first (e.g. 1/world_size).                                                               */
+int dmv_adam_tick(float* state4, float lr, float beta1, float beta2, void* stream);
+int dmv_adam_multi(float* const* params, const float* const* grads, float* const* m,
+                   float* const* v, void* const* bf16_copy, const long long* n, int count,
+                   const float* state4, float beta1, float beta2, float eps, float grad_scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMV3D_H_ */

@@ -1,0 +1,508 @@
+"""Restatement of the reference's model graphs -- TEST INFRASTRUCTURE ONLY.
+
+The graphs are written once against a tiny backend interface and run on either
+  * ``NumpyOps``  -- the NumPy oracle of oracle/tf_ops.py (semantic authority), or
+  * ``TorchCpuOps`` -- the same ops expressed with torch CPU kernels (oneDNN convs with
+    explicit TF-SAME padding, crop-form transposed convs, matmul, an index-based
+    resampler).  It is (a) the autograd cross-check for the conv/FC gradients and
+    (b) the multi-threaded "reference CPU path" stand-in timed by bench.py
+    (BASELINE.md section 5), since TensorFlow 1.3 cannot run in this image.
+
+Graph sources (paths relative to /root/reference/dyn_mult_view/multi_view_model):
+  appearance_flow_model.py:63-66,83-127   AppearanceFlowModel  (M1, M2 base)
+  highdim_angle.py:7-10, lowdim_angle.py:7-8   viewpoint-encoder variants (M2)
+  appearance_flow_tinghui.py:7-46           lighter Zhou-style net
+  main_model.py:57-154                      Base_Prediction_Model (M3, colour+depth)
+  multiobject_appflow.py:80-286             MultiObjectAppFlow (M4)
+Shape rule: every hard-coded 128-derived size is H/2^k, so the graphs
+are parametric in H (multiple of 32); at H=128 they equal the reference literally.
+Parameters are a dict keyed by TF variable names ("e0/w", "fc1/Matrix", ...).
+"""
+import numpy as np
+
+from . import tf_ops as T
+
+
+# --------------------------------------------------------------------------- #
+# backends
+# --------------------------------------------------------------------------- #
+class NumpyOps:
+    name = "numpy"
+
+    def asarray(self, x):
+        return np.asarray(x)
+
+    def conv(self, x, w, b, s):
+        return T.conv2d_same(x, w, b, s, s)
+
+    def deconv(self, x, w, out_shape, s):
+        return T.conv2d_transpose_same(x, w, out_shape, s, s)
+
+    def linear(self, x, m, b):
+        return T.linear(x, m, b)
+
+    def lrelu(self, x):
+        return T.lrelu(x)
+
+    def relu(self, x):
+        return T.relu(x)
+
+    def tanh(self, x):
+        return np.tanh(x)
+
+    def concat(self, xs, axis):
+        return np.concatenate(xs, axis=axis)
+
+    def flatten_hwc(self, x):
+        return x.reshape(x.shape[0], -1)
+
+    def unflatten_hwc(self, x, h, w, c):
+        return x.reshape(x.shape[0], h, w, c)
+
+    def split_c(self, x, n):
+        return list(np.split(x, n, axis=3))
+
+    def tile_hw(self, v, h, w):
+        return np.tile(v[:, None, None, :], (1, h, w, 1))
+
+    def warp_pts(self, flow):
+        return T.warp_pts_layer(flow)
+
+    def resample(self, img, warp):
+        return T.resampler(img, warp)
+
+    def nhwc(self, x):
+        return x
+
+    def from_nhwc(self, x):
+        return np.asarray(x)
+
+    def euclidean(self, a, b):
+        return T.euclidean_loss(a, b)
+
+    def l1(self, a, b):
+        return T.l1_loss(a, b)
+
+    def masked_l2(self, a, b, m):
+        d = (a - b) * m
+        return np.mean(np.sum(d * d, axis=3, dtype=np.float64), dtype=np.float64)
+
+    def softmax_views(self, logits):  # [V,B,H,W,1] over axis 0
+        e = np.exp(logits - logits.max(axis=0, keepdims=True))
+        return e / e.sum(axis=0, keepdims=True)
+
+
+class TorchCpuOps:
+    """Activations are carried NCHW-logical / channels_last so oneDNN runs its fast path;
+    NHWC numpy arrays go in and come out at the graph boundary."""
+    name = "torch-cpu"
+
+    def __init__(self, dtype=None):
+        import torch
+        self.t = torch
+        self.F = torch.nn.functional
+        self.dtype = dtype or torch.float32
+
+    def asarray(self, x):
+        t = self.t
+        return x if isinstance(x, t.Tensor) else t.as_tensor(np.asarray(x), dtype=self.dtype)
+
+    def from_nhwc(self, x):
+        x = self.asarray(x)
+        return x.permute(0, 3, 1, 2).contiguous(memory_format=self.t.channels_last)
+
+    def nhwc(self, x):
+        return x.permute(0, 2, 3, 1)
+
+    def conv(self, x, w, b, s):
+        kh, kw = w.shape[0], w.shape[1]
+        H, W = x.shape[2], x.shape[3]
+        _, pt, pb = T.same_pad(H, kh, s)
+        _, pl, pr = T.same_pad(W, kw, s)
+        xp = self.F.pad(x, (pl, pr, pt, pb))
+        return self.F.conv2d(xp, w.permute(3, 2, 0, 1), b, stride=s)
+
+    def deconv(self, x, w, out_shape, s):
+        # TF conv2d_transpose(SAME) == full transposed conv cropped [before : before+out]
+        kh, kw = w.shape[0], w.shape[1]
+        Ho, Wo = out_shape[1], out_shape[2]
+        _, pt, _ = T.same_pad(Ho, kh, s)
+        _, pl, _ = T.same_pad(Wo, kw, s)
+        full = self.F.conv_transpose2d(x, w.permute(3, 2, 0, 1), None, stride=s)
+        need_h, need_w = pt + Ho, pl + Wo
+        if full.shape[2] < need_h or full.shape[3] < need_w:
+            full = self.F.pad(full, (0, max(0, need_w - full.shape[3]), 0, max(0, need_h - full.shape[2])))
+        return full[:, :, pt:pt + Ho, pl:pl + Wo]
+
+    def linear(self, x, m, b):
+        return x @ m + b
+
+    def lrelu(self, x):
+        return 0.6 * x + 0.4 * x.abs()
+
+    def relu(self, x):
+        return 0.5 * x + 0.5 * x.abs()
+
+    def tanh(self, x):
+        return self.t.tanh(x)
+
+    def concat(self, xs, axis):
+        if xs[0].dim() == 4:
+            axis = {0: 0, 1: 2, 2: 3, 3: 1}[axis]
+        return self.t.cat(xs, dim=axis)
+
+    def flatten_hwc(self, x):
+        return x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+
+    def unflatten_hwc(self, x, h, w, c):
+        return x.reshape(x.shape[0], h, w, c).permute(0, 3, 1, 2)
+
+    def split_c(self, x, n):
+        return list(self.t.chunk(x, n, dim=1))
+
+    def tile_hw(self, v, h, w):
+        return v[:, :, None, None].expand(-1, -1, h, w)
+
+    def warp_pts(self, flow):                      # flow NCHW [B,2,H,W] -> NHWC warp [B,H,W,2]
+        f = flow.permute(0, 2, 3, 1)
+        B, H, W, _ = f.shape
+        return f + self.asarray(T.coords(H, W, B)).to(f.dtype)
+
+    def resample(self, img, warp):
+        """TF resampler rule with torch indexing; img NCHW, warp NHWC [B,H,W,2] -> NCHW."""
+        t = self.t
+        data = img.permute(0, 2, 3, 1)              # NHWC view
+        B, H, W, C = data.shape
+        x, y = warp[..., 0], warp[..., 1]
+        valid = (x > -1) & (y > -1) & (x < W) & (y < H)
+        xs = t.where(valid, x, t.zeros_like(x))
+        ys = t.where(valid, y, t.zeros_like(y))
+        fx = t.floor(xs.detach()).long()
+        fy = t.floor(ys.detach()).long()
+        cx, cy = fx + 1, fy + 1
+        dx = cx.to(x.dtype) - xs
+        dy = cy.to(y.dtype) - ys
+        bidx = t.arange(B).reshape(B, 1, 1).expand_as(fx)
+
+        def P(u, v):
+            ok = (u >= 0) & (u <= W - 1) & (v >= 0) & (v <= H - 1)
+            vals = data[bidx, v.clamp(0, H - 1), u.clamp(0, W - 1)]
+            return vals * ok[..., None].to(vals.dtype)
+
+        dxe, dye = dx[..., None], dy[..., None]
+        out = (dxe * dye) * P(fx, fy) + ((1 - dxe) * (1 - dye)) * P(cx, cy) \
+            + (dxe * (1 - dye)) * P(fx, cy) + ((1 - dxe) * dye) * P(cx, fy)
+        out = out * valid[..., None].to(out.dtype)
+        return out.permute(0, 3, 1, 2)
+
+    def euclidean(self, a, b):
+        d = a - b
+        return (d * d).sum(dim=1).mean()
+
+    def l1(self, a, b):
+        return (a - b).abs().sum(dim=1).mean()
+
+    def masked_l2(self, a, b, m):
+        d = (a - b) * m
+        return (d * d).sum(dim=1).mean()
+
+    def softmax_views(self, logits):
+        return self.t.softmax(logits, dim=0)
+
+
+# --------------------------------------------------------------------------- #
+# parameter shapes (TF variable names) -- shared by oracle users
+# --------------------------------------------------------------------------- #
+def _conv(shapes, name, k, cin, cout):
+    shapes[name + "/w"] = ("conv", (k, k, cin, cout))
+    shapes[name + "/b"] = ("zero", (cout,))
+
+
+def _deconv(shapes, name, k, cout, cin, stride=2):
+    shapes[name + "/w"] = ("deconv%d" % stride, (k, k, cout, cin))
+
+
+def _fc(shapes, name, kin, nout):
+    shapes[name + "/Matrix"] = ("fc", (kin, nout))
+    shapes[name + "/b"] = ("zero", (nout,))
+
+
+def appflow_param_shapes(H, V, kind="base"):
+    """Variable shapes of AppearanceFlowModel and its viewpoint variants at side H."""
+    s = {}
+    h5 = H // 32
+    if kind == "tinghui":
+        for name, cin, cout in [("e0", 3, 16), ("e1", 16, 32), ("e2", 32, 64), ("e3", 64, 128), ("e4", 128, 256)]:
+            _conv(s, name, 3, cin, cout)
+        _fc(s, "e_fc0", h5 * h5 * 256, 2048)
+        _fc(s, "e_fc1", 2048, 2048)
+        _fc(s, "a0", V, 64); _fc(s, "a1", 64, 64); _fc(s, "a2", 64, 64)
+        _fc(s, "a3", 2048 + 64, 2048)
+        _fc(s, "a4", 2048, (H // 16) ** 2 * 32)
+        _deconv(s, "d3", 3, 128, 32); _deconv(s, "d2", 3, 64, 128)
+        _deconv(s, "d1", 3, 32, 64); _deconv(s, "d0", 3, 16, 32)
+        _deconv(s, "flow_field", 3, 2, 16, stride=1)
+        return s
+    for name, k, cin, cout in [("e0", 5, 3, 32), ("e0_0", 5, 32, 32), ("e1", 5, 32, 32), ("e1_0", 5, 32, 32),
+                               ("e2", 5, 32, 64), ("e2_0", 5, 64, 64), ("e3", 3, 64, 128), ("e3_0", 3, 128, 128),
+                               ("e4", 3, 128, 256), ("e4_0", 3, 256, 256)]:
+        _conv(s, name, k, cin, cout)
+    _fc(s, "fc1", h5 * h5 * 256, 4096)
+    if kind == "base":
+        _fc(s, "a0", V, 64); _fc(s, "a1", 64, 64); _fc(s, "a2", 64, 64); A = 64
+    elif kind == "highdim":          # highdim_angle.py:8-10 : a0, a1 are dead variables
+        _fc(s, "a0", V, 19); _fc(s, "a1", V, 128); _fc(s, "a2", V, 256); A = 256
+    elif kind == "lowdim":           # lowdim_angle.py:8
+        _fc(s, "a0", V, 10); A = 10
+    else:
+        raise ValueError(kind)
+    _fc(s, "a3", 4096 + A, 4096)
+    _fc(s, "a4", 4096, 4096)
+    _fc(s, "a5", 4096, h5 * h5 * 256)
+    _deconv(s, "d4", 3, 128, 256); _conv(s, "d4_0", 3, 128, 128)
+    _deconv(s, "d3", 3, 64, 128); _conv(s, "d3_0", 5, 64, 64)
+    _deconv(s, "d2", 5, 32, 64); _conv(s, "d2_0", 5, 32, 64)
+    _deconv(s, "d1", 5, 32, 64); _conv(s, "d1_0", 5, 32, 32)
+    _deconv(s, "flow_field", 5, 2, 32)
+    return s
+
+
+def init_params(shapes, seed=0):
+    """Reference initialisers (tf_utils.py:54-98) drawn with NumPy for oracle-only use."""
+    rng = np.random.default_rng(seed)
+    p = {}
+    for name, (kind, shp) in shapes.items():
+        if kind == "zero":
+            p[name] = np.zeros(shp, np.float32)
+        elif kind == "fc":
+            p[name] = (rng.standard_normal(shp) * T.linear_stddev(shp[0])).astype(np.float32)
+        elif kind == "conv":
+            sd = T.conv_stddev(shp[0], shp[1], shp[2])
+            v = rng.standard_normal(shp)
+            bad = np.abs(v) > 2
+            while bad.any():                       # truncated_normal: re-draw beyond 2 sigma
+                v[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(v) > 2
+            p[name] = (v * sd).astype(np.float32)
+        elif kind.startswith("deconv"):
+            st = int(kind[6:])
+            p[name] = (rng.standard_normal(shp) * T.deconv_stddev(shp[0], shp[1], shp[3], st, st)).astype(np.float32)
+        else:
+            raise ValueError(kind)
+    return p
+
+
+# --------------------------------------------------------------------------- #
+# graphs
+# --------------------------------------------------------------------------- #
+def _decode_angle(ops, P, disp, kind):
+    if kind in ("base", "tinghui"):          # appearance_flow_model.py:63-66 / tinghui :7-11
+        act = ops.lrelu
+        a0 = act(ops.linear(disp, P["a0/Matrix"], P["a0/b"]))
+        a1 = act(ops.linear(a0, P["a1/Matrix"], P["a1/b"]))
+        return act(ops.linear(a1, P["a2/Matrix"], P["a2/b"]))
+    if kind == "highdim":                    # highdim_angle.py:8-10 (a0, a1 outputs unused)
+        return ops.lrelu(ops.linear(disp, P["a2/Matrix"], P["a2/b"]))
+    if kind == "lowdim":                     # lowdim_angle.py:8
+        return ops.lrelu(ops.linear(disp, P["a0/Matrix"], P["a0/b"]))
+    raise ValueError(kind)
+
+
+def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False):
+    """appearance_flow_model.py:83-127 (kind base/highdim/lowdim) or
+    appearance_flow_tinghui.py:13-46 (kind tinghui).  image0 NHWC [B,H,H,3], disp [B,V].
+    Returns dict with flow_field, warp_pts, gen (NHWC) and, if keep, every activation."""
+    P = {k: ops.asarray(v) for k, v in params.items()}
+    x = ops.from_nhwc(image0)
+    disp = ops.asarray(disp)
+    B, H = image0.shape[0], image0.shape[1]
+    acts = {}
+
+    def C(name, inp, s, act=ops.lrelu):
+        y = ops.conv(inp, P[name + "/w"], P[name + "/b"], s)
+        y = act(y) if act is not None else y
+        acts[name] = y
+        return y
+
+    def D(name, inp, side, cout, s=2, act=ops.lrelu):
+        y = ops.deconv(inp, P[name + "/w"], (B, side, side, cout), s)
+        y = act(y) if act is not None else y
+        acts[name] = y
+        return y
+
+    def FC(name, inp, act=ops.lrelu):
+        y = act(ops.linear(inp, P[name + "/Matrix"], P[name + "/b"]))
+        acts[name] = y
+        return y
+
+    h5 = H // 32
+    if kind == "tinghui":
+        r = ops.relu
+        e = C("e0", x, 2, r); e = C("e1", e, 2, r); e = C("e2", e, 2, r); e = C("e3", e, 2, r); e = C("e4", e, 2, r)
+        f = FC("e_fc0", ops.flatten_hwc(e), r)
+        f = FC("e_fc1", f, r)
+        ang = _decode_angle(ops, P, disp, kind)
+        j = FC("a3", ops.concat([f, ang], 1), r)
+        j = FC("a4", j, r)
+        d = ops.unflatten_hwc(j, H // 16, H // 16, 32)
+        d = D("d3", d, H // 8, 128, 2, r); d = D("d2", d, H // 4, 64, 2, r)
+        d = D("d1", d, H // 2, 32, 2, r); d = D("d0", d, H, 16, 2, r)
+        flow = D("flow_field", d, H, 2, 1, None)
+    else:
+        e = C("e0", x, 2); e = C("e0_0", e, 1); e = C("e1", e, 2); e = C("e1_0", e, 1)
+        e = C("e2", e, 2); e = C("e2_0", e, 1); e = C("e3", e, 2); e = C("e3_0", e, 1)
+        e = C("e4", e, 2); e = C("e4_0", e, 1)
+        e5 = FC("fc1", ops.flatten_hwc(e))
+        ang = _decode_angle(ops, P, disp, kind)
+        acts["angle"] = ang
+        j = FC("a3", ops.concat([e5, ang], 1)); j = FC("a4", j); j = FC("a5", j)
+        d = ops.unflatten_hwc(j, h5, h5, 256)
+        d = D("d4", d, 2 * h5, 128); d = C("d4_0", d, 1)
+        d = D("d3", d, 4 * h5, 64); d = C("d3_0", d, 1)
+        d = D("d2", d, 8 * h5, 32); d = C("d2_0", d, 1)
+        d = D("d1", d, 16 * h5, 32); d = C("d1_0", d, 1)
+        flow = D("flow_field", d, H, 2, 2, None)
+    warp = ops.warp_pts(flow)
+    gen = ops.resample(x, warp)
+    out = {"flow_field": ops.nhwc(flow), "warp_pts": warp, "gen": ops.nhwc(gen)}
+    if keep:
+        out["acts"] = {k: (ops.nhwc(v) if getattr(v, "ndim", 0) == 4 else v) for k, v in acts.items()}
+    return out
+
+
+def appearance_flow_loss(ops, out, image1, mode="l2"):
+    """appearance_flow_model.py:73 (euclidean) or the north-star's L1 (tf_utils.py:22)."""
+    tgt = ops.asarray(image1)
+    gen = out["gen"]
+    if ops.name == "torch-cpu":
+        gen = gen.permute(0, 3, 1, 2)
+        tgt = tgt.permute(0, 3, 1, 2)
+    return ops.euclidean(gen, tgt) if mode == "l2" else ops.l1(gen, tgt)
+
+
+# --- M3 : main_model.py ------------------------------------------------------ #
+def _pre_encoder_shapes(s, scope, cin):
+    for name, ci, co in [("e0", cin, 32), ("e0_0", 32, 32), ("e1", 32, 32), ("e1_0", 32, 32), ("e2", 32, 64)]:
+        _conv(s, scope + "/" + name, 5, ci, co)
+
+
+def _decoder_shapes(s, scope, cout):
+    _deconv(s, scope + "/d2", 5, 32, 64); _conv(s, scope + "/d2_0", 5, 32, 64)
+    _deconv(s, scope + "/d1", 5, 32, 64); _conv(s, scope + "/d1_0", 5, 32, 32)
+    _deconv(s, scope + "/d0", 5, cout, 32)
+
+
+def _trunk_shapes(s, H, V, n_in, num_decode, fully_conv=False):
+    h5 = H // 32
+    _conv(s, "e2_0", 5, 64 * n_in, 64); _conv(s, "e3", 3, 64, 128); _conv(s, "e3_0", 3, 128, 128)
+    _conv(s, "e4", 3, 128, 256); _conv(s, "e4_0", 3, 256, 256)
+    _fc(s, "a0", V, 64); _fc(s, "a1", 64, 64); _fc(s, "a2", 64, 64)
+    if fully_conv:
+        _conv(s, "e4_1", 3, 256 + 64, 256); _conv(s, "e4_2", 3, 256, 256)
+    else:
+        _fc(s, "fc1", h5 * h5 * 256, 4096)
+        _fc(s, "a3", 4096 + 64, 4096); _fc(s, "a4", 4096, 4096); _fc(s, "a5", 4096, h5 * h5 * 256)
+    _deconv(s, "d4", 3, 128, 256); _conv(s, "d4_0", 3, 128, 128)
+    _deconv(s, "d3", 3, 64, 128); _conv(s, "d3_0", 5, 64, 64 * num_decode)
+
+
+def colordepth_param_shapes(H, V, conf):
+    """Base_Prediction_Model (main_model.py:83-142).  ``head`` mode 'tanh' is the
+    reference; 'flow' replaces each tanh head by a 2-ch flow head + sampler."""
+    s = {}
+    n = 0
+    if "use_color" in conf:
+        _pre_encoder_shapes(s, "pre_image0", 3); n += 1
+    if "use_depth" in conf:
+        _pre_encoder_shapes(s, "pre_dimage0", 1); n += 1
+    _trunk_shapes(s, H, V, n, n)
+    flow = conf.get("head", "tanh") == "flow"
+    if "use_color" in conf:
+        _decoder_shapes(s, "dec_image1", 2 if flow else 3)
+    if "use_depth" in conf:
+        _decoder_shapes(s, "dec_dimage1", 2 if flow else 1)
+    return s
+
+
+def _pre_encode(ops, P, x, scope):
+    for name, st in [("e0", 2), ("e0_0", 1), ("e1", 2), ("e1_0", 1), ("e2", 2)]:
+        x = ops.lrelu(ops.conv(x, P["%s/%s/w" % (scope, name)], P["%s/%s/b" % (scope, name)], st))
+    return x
+
+
+def _trunk(ops, P, comb, disp, B, H, fully_conv=False):
+    h5 = H // 32
+    c = lambda n, x, s: ops.lrelu(ops.conv(x, P[n + "/w"], P[n + "/b"], s))
+    f = lambda n, x: ops.lrelu(ops.linear(x, P[n + "/Matrix"], P[n + "/b"]))
+    e = c("e2_0", comb, 1); e = c("e3", e, 2); e = c("e3_0", e, 1); e = c("e4", e, 2); e = c("e4_0", e, 1)
+    a2 = f("a2", f("a1", f("a0", disp)))
+    if fully_conv:                      # multiobject_appflow.py:147-153
+        sm = ops.tile_hw(a2, h5, h5)
+        e = c("e4_1", ops.concat([e, sm], 3), 1)
+        a5r = c("e4_2", e, 1)
+    else:
+        e5 = f("fc1", ops.flatten_hwc(e))
+        j = f("a5", f("a4", f("a3", ops.concat([e5, a2], 1))))
+        a5r = ops.unflatten_hwc(j, h5, h5, 256)
+    d = ops.lrelu(ops.deconv(a5r, P["d4/w"], (B, 2 * h5, 2 * h5, 128), 2))
+    d = c("d4_0", d, 1)
+    d = ops.lrelu(ops.deconv(d, P["d3/w"], (B, 4 * h5, 4 * h5, 64), 2))
+    return c("d3_0", d, 1)
+
+
+def _decode(ops, P, x, scope, B, H, cout):
+    h5 = H // 32
+    d = ops.lrelu(ops.deconv(x, P[scope + "/d2/w"], (B, 8 * h5, 8 * h5, 32), 2))
+    d = ops.lrelu(ops.conv(d, P[scope + "/d2_0/w"], P[scope + "/d2_0/b"], 1))
+    d = ops.lrelu(ops.deconv(d, P[scope + "/d1/w"], (B, 16 * h5, 16 * h5, 32), 2))
+    d = ops.lrelu(ops.conv(d, P[scope + "/d1_0/w"], P[scope + "/d1_0/b"], 1))
+    return ops.deconv(d, P[scope + "/d0/w"], (B, H, H, cout), 2)
+
+
+def colordepth_forward(ops, params, conf, image0, dimage0, disp):
+    """main_model.py:83-142.  split_list.pop() hands out channel groups from the END."""
+    P = {k: ops.asarray(v) for k, v in params.items()}
+    B, H = image0.shape[0], image0.shape[1]
+    disp = ops.asarray(disp)
+    feats, srcs = [], {}
+    if "use_color" in conf:
+        srcs["color"] = ops.from_nhwc(image0)
+        feats.append(_pre_encode(ops, P, srcs["color"], "pre_image0"))
+    if "use_depth" in conf:
+        srcs["depth"] = ops.from_nhwc(dimage0)
+        feats.append(_pre_encode(ops, P, srcs["depth"], "pre_dimage0"))
+    d3_0 = _trunk(ops, P, ops.concat(feats, 3), disp, B, H)
+    split = ops.split_c(d3_0, len(feats))
+    flow = conf.get("head", "tanh") == "flow"
+    out = {}
+    for key, scope, name, cout in [("color", "dec_image1", "gen_image1", 3), ("depth", "dec_dimage1", "gen_dimage1", 1)]:
+        if ("use_" + key) not in conf:
+            continue
+        pre = _decode(ops, P, split.pop(), scope, B, H, 2 if flow else cout)
+        if flow:
+            out[name] = ops.nhwc(ops.resample(srcs[key], ops.warp_pts(pre)))
+            out[name + "_flow"] = ops.nhwc(pre)
+        else:
+            out[name] = ops.nhwc(ops.tanh(pre))
+    return out
+
+
+def colordepth_loss(ops, out, conf, image1, dimage1, mode="l2"):
+    """main_model.py:144-154: L(color) + depth_lr_factor * L(depth); mode 'l1' is the
+    BASELINE config-4 "per-channel L1" (tf_utils.py:22, weights as mv3d/nobg_dm.py:91-92)."""
+    L = ops.euclidean if mode == "l2" else ops.l1
+    tot = 0.0
+    perm = (lambda x: x.permute(0, 3, 1, 2)) if ops.name == "torch-cpu" else (lambda x: x)
+    if "use_color" in conf:
+        tot = tot + L(perm(out["gen_image1"]), perm(ops.asarray(image1)))
+    if "use_depth" in conf:
+        tot = tot + L(perm(out["gen_dimage1"]), perm(ops.asarray(dimage1))) * conf["depth_lr_factor"]
+    return tot
+
+
+# --- 8(f)-3 : multi-view confidence-weighted fusion (NOT in the reference) ----- #
+def fuse_views(ops, gens, logits):
+    """out = sum_v softmax_v(c)_v * gen_v ; gens [V,B,H,W,C], logits [V,B,H,W,1].
+    Definition adopted in SURVEY 8(f)-3 (after Zhou et al. 2016) -- parity unpinned."""
+    w = ops.softmax_views(logits)
+    return (w * gens).sum(0)

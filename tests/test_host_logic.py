@@ -1,0 +1,157 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol,
+the model classes build the reference's variable tables (meta device, no compute), bucket
+planning, and the world_size-2 gradient exchange over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "dmv3d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dmv_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from dynamic_multiview_3d_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "dynamic_multiview_3d_b200", "csrc"), "-j8"], check=True)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 26
+    for s in syms:
+        assert hasattr(lib, s), "libdmv3d.so does not export %s" % s
+    # the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == syms
+    assert _lib.load().dmv_arch() == b"sm_100a"
+    assert _lib.load().dmv_version() >= 100
+
+
+def test_error_reporting_without_gpu():
+    from dynamic_multiview_3d_b200 import _lib
+    lib = _lib.load()
+    rc = lib.dmv_sampler_fwd(None, None, None, None, None, 1, 2, 2, 1, 2, 2, 0, None)
+    assert rc == -1 and "null" in _lib.last_error()
+    with pytest.raises(_lib.DmvError):
+        _lib.check(rc, "dmv_sampler_fwd")
+    assert lib.dmv_sampler_bwd_workspace_size(64, 224, 224, 3, 224, 224) == 64 * 49 * 16
+    assert lib.dmv_wgrad_workspace_size(25, 32, 32, 802816) > 0
+
+
+def test_cpu_tensors_are_rejected():
+    from dynamic_multiview_3d_b200 import _lib, functional as F
+    with pytest.raises(_lib.DmvError):
+        F.resampler(torch.zeros(1, 4, 4, 3), torch.zeros(1, 4, 4, 2))
+
+
+@pytest.mark.parametrize("cls,kind", [("AppearanceFlowModel", "base"), ("AppFlowHighDimAngle", "highdim"),
+                                      ("AppFlowLowDimAngle", "lowdim"), ("AppearanceFlowTinghui", "tinghui")])
+@pytest.mark.parametrize("H", [128, 224])
+def test_variable_tables_match_reference_graph(cls, kind, H):
+    import dynamic_multiview_3d_b200 as pkg
+    from oracle import graph as G
+    m = getattr(pkg, cls)({"batch_size": 2, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": 19}, device="meta")
+    shapes = G.appflow_param_shapes(H, 19, kind)
+    assert list(shapes) == list(m.store.vars)
+    for k, (_, shp) in shapes.items():
+        assert tuple(shp) == m.store.vars[k].shape, k
+    assert tuple(m.flow_field.shape) == (2, H, H, 2) and tuple(m.gen.shape) == (2, H, H, 3)
+    dead = [v.name for v in m.store.vars.values() if not v.trainable]
+    assert dead == (["a0/Matrix", "a0/b", "a1/Matrix", "a1/b"] if kind == "highdim" else [])
+    # flat offsets are 64-element aligned and non-overlapping
+    offs = [(v.offset, v.numel) for v in m.store.vars.values()]
+    assert all(o % 64 == 0 for o, _ in offs)
+    assert all(o2 >= o1 + n1 for (o1, n1), (o2, _) in zip(offs, offs[1:]))
+
+
+def test_reference_conf_loads_unchanged(tmp_path):
+    from dynamic_multiview_3d_b200 import train
+    conf_py = tmp_path / "conf.py"
+    conf_py.write_text(
+        "import os\ncurrent_dir = os.path.dirname(os.path.realpath(__file__))\n"
+        "from highdim_angle import AppFlowHighDimAngle\nimport dyn_mult_view\n"
+        "configuration = {'experiment_name': 'x', 'data_dir': '/nope', 'output_dir': current_dir + '/modeldata',\n"
+        " 'current_dir': current_dir, 'num_iterations': 200000, 'batch_size': 64, 'learning_rate': 1e-4,\n"
+        " 'train_val_split': 0.95, 'model': AppFlowHighDimAngle}\n")
+    conf = train.load_conf(str(conf_py))
+    import dynamic_multiview_3d_b200 as pkg
+    assert conf["model"] is pkg.AppFlowHighDimAngle and conf["batch_size"] == 64
+    assert train.checkpoint_iteration("/x/y/model120000") == 120000
+
+
+def test_bucket_plan_is_reverse_contiguous():
+    from dynamic_multiview_3d_b200.data_parallel import plan_buckets
+    table, off = [], 0
+    for i, n in enumerate([64, 128, 1 << 20, 64, 3 << 20, 256]):
+        table.append(("v%d" % i, off, n))
+        off += n
+    b = plan_buckets(table, 1 << 20)
+    assert b[0][2][0] == "v5"                          # last-created variable first
+    assert b[0][1] == off and b[-1][0] == 0            # covers the whole buffer
+    assert all(x[0] == y[1] for x, y in zip(b, b[1:]))  # contiguous, descending
+    assert sum(len(x[2]) for x in b) == len(table)
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from dynamic_multiview_3d_b200.data_parallel import GradientAllReducer
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["MASTER_PORT"], rank=rank, world_size=world)
+sizes = [64, 192, 4096, 64, 8192, 128]
+table, off = [], 0
+for i, n in enumerate(sizes):
+    table.append(("v%%d" %% i, off, n)); off += n
+flat = torch.zeros(off)
+red = GradientAllReducer(flat, table, bucket_mb=4096 * 4 / (1 << 20), trainable={"v%%d" %% i for i in range(6) if i != 3})
+order = []
+for i in reversed(range(6)):                      # backward order
+    if i == 3: continue                            # a dead variable never reports
+    name, o, n = table[i]
+    flat[o:o + n] = float(rank + 1) * (i + 1)
+    red.on_grad_ready(name)
+    order.append(list(red.launched))
+red.finish()
+exp = torch.cat([torch.full((n,), float(sum(range(1, world + 1))) * (i + 1)) if i != 3 else torch.zeros(n) for i, (_, _, n) in enumerate(table)])
+assert torch.equal(flat, exp), (flat[:4], exp[:4])
+assert red.pending == red.expected and red.launched == []
+assert len(order[-1]) == len(red.buckets)
+print("rank", rank, "ok", len(red.buckets), "buckets")
+dist.destroy_process_group()
+"""
+
+
+def test_gradient_allreduce_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
+def test_synthetic_batches_are_deterministic_and_in_range():
+    from dynamic_multiview_3d_b200.synthetic import make_batch
+    a = make_batch(3, 64, "onehot19", seed=1234, rank=1, depth=True)
+    b = make_batch(3, 64, "onehot19", seed=1234, rank=1, depth=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    assert a["image0"].shape == (3, 64, 64, 3) and a["image0"].dtype == np.float32
+    assert 0.0 <= a["image0"].min() and a["image0"].max() <= 1.0
+    assert (a["disp"].sum(1) == 1).all() and a["disp"].shape == (3, 19)
+    assert a["depth0"].max() == 1.0 and 0.3 <= a["depth0"].min() <= 0.6
+    c = make_batch(2, 64, "disp2", views=4)
+    assert c["image0"].shape == (2, 4, 64, 64, 3) and c["disp"].shape == (2, 2)

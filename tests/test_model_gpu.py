@@ -1,0 +1,109 @@
+"""GPU parity tests of the whole appearance-flow graph against the oracle on identical weights
+and inputs, the train step, CUDA-graph capture, and the checkpoint surface."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _params_from(model):
+    return {k: v.master.detach().cpu().numpy().copy() for k, v in model.store.vars.items()}
+
+
+def _batch(B, H, V, seed=1234):
+    from dynamic_multiview_3d_b200.synthetic import make_batch
+    return make_batch(B, H, "onehot19" if V == 19 else "disp2", seed=seed)
+
+
+@pytest.mark.parametrize("cls,kind,H", [("AppearanceFlowModel", "base", 64), ("AppFlowHighDimAngle", "highdim", 32),
+                                        ("AppFlowLowDimAngle", "lowdim", 32), ("AppearanceFlowTinghui", "tinghui", 64)])
+@pytest.mark.parametrize("algo", ["simt", "auto"])
+def test_forward_parity_with_oracle(cls, kind, H, algo):
+    import dynamic_multiview_3d_b200 as pkg
+    B, V = 4, 19
+    model = getattr(pkg, cls)({"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "algo": algo})
+    b = _batch(B, H, V)
+    out = model.forward(torch.from_numpy(b["image0"]).cuda(), torch.from_numpy(b["disp"]).cuda())
+    ref = G.appearance_flow_forward(G.NumpyOps(), _params_from(model), b["image0"], b["disp"], kind)
+    flow, rflow = out["flow_field"].float().cpu().numpy(), ref["flow_field"]
+    rel = np.abs(flow - rflow).max() / np.abs(rflow).max()
+    assert rel < 1e-2, rel                                     # bf16 conv stack vs fp32 oracle (BASELINE tolerance)
+    gen, rgen = out["gen"].cpu().numpy(), ref["gen"]
+    assert np.abs(gen - rgen).max() < 2e-2
+    loss = float(model.build_loss(torch.from_numpy(b["image1"]).cuda()))
+    rloss = float(G.appearance_flow_loss(G.NumpyOps(), ref, b["image1"]))
+    assert loss == pytest.approx(rloss, rel=1e-2)
+    assert np.array_equal(model.warp_pts.cpu().numpy(), (flow + G.T.coords(H, H, B)).astype(np.float32))
+
+
+def test_gradients_match_torch_cpu_port():
+    """Parameter gradients of one step vs autograd through the torch-CPU port of the oracle graph."""
+    import dynamic_multiview_3d_b200 as pkg
+    B, H, V = 2, 32, 19
+    model = pkg.AppearanceFlowModel({"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V})
+    b = _batch(B, H, V)
+    model.forward(torch.from_numpy(b["image0"]).cuda(), torch.from_numpy(b["disp"]).cuda())
+    model.build_loss(torch.from_numpy(b["image1"]).cuda()).backward()
+    P = {k: torch.tensor(v, requires_grad=True) for k, v in _params_from(model).items()}
+    ops = G.TorchCpuOps()
+    ref = G.appearance_flow_forward(ops, P, b["image0"], b["disp"], "base")
+    G.appearance_flow_loss(ops, ref, b["image1"]).backward()
+    worst = 0.0
+    for k, v in model.store.vars.items():
+        g, r = v.grad.cpu().numpy(), P[k].grad.numpy()
+        cos = float((g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+        worst = max(worst, 1 - cos)
+        assert cos > 0.98, (k, cos)
+        assert np.linalg.norm(g - r) <= 0.15 * np.linalg.norm(r) + 1e-12, (k, np.linalg.norm(g - r) / np.linalg.norm(r))
+
+
+def test_train_step_decreases_loss_and_graph_replay_matches_eager():
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200.train import GraphedTrainStep
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "seed": 3}
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    eager = pkg.AppearanceFlowModel(conf)
+    le = [float(eager.train_step(*args)) for _ in range(8)]
+    assert le[-1] < le[0] and all(np.isfinite(le))
+    graphed = pkg.AppearanceFlowModel(conf)
+    step = GraphedTrainStep(graphed, warmup=3)
+    lg = [float(step(*args)) for _ in range(5)]           # first call: 3 eager warm-ups + capture (1 step) + replay
+    # steps 1..3 eager warm-up, step 4 during capture (not executed), replays are steps 4..8
+    assert lg[0] == pytest.approx(le[3], rel=1e-4) and lg[4] == pytest.approx(le[7], rel=1e-4)
+    assert step.launches_per_step > 50
+    assert graphed.optimizer.t == 8
+
+
+def test_l1_loss_mode_and_xy_grid():
+    import dynamic_multiview_3d_b200 as pkg
+    B, H, V = 2, 32, 2
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "loss": "l1", "grid_order": "xy"}
+    m = pkg.AppearanceFlowModel(conf)
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    l0 = float(m.train_step(*args))
+    ref = G.appearance_flow_forward(G.NumpyOps(), _params_from(m), b["image0"], b["disp"], "base")
+    assert np.isfinite(l0)
+    for _ in range(5):
+        l1 = float(m.train_step(*args))
+    assert l1 < l0
+
+
+def test_checkpoint_roundtrip():
+    import dynamic_multiview_3d_b200 as pkg
+    conf = {"batch_size": 2, "learning_rate": 1e-4, "image_size": 32, "viewpoint_dim": 19}
+    b = _batch(2, 32, 19)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    m1 = pkg.AppearanceFlowModel(conf)
+    for _ in range(2):
+        m1.train_step(*args)
+    sd = m1.state_dict()
+    assert "fc1/Matrix" in sd and "e0/w" in sd and "flow_field/w" in sd and "fc1/Matrix/Adam" in sd
+    m2 = pkg.AppearanceFlowModel(dict(conf, seed=7))
+    m2.load_state_dict(sd)
+    assert float(m1.train_step(*args)) == float(m2.train_step(*args))
