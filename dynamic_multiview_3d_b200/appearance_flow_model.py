@@ -114,6 +114,9 @@ class AppearanceFlowModel(object):
         """image0 [B,H,H,3] fp32 in [0,1], disp [B,V] fp32 -> dict(flow_field, gen); sets the
         reference's attribute names.  warp_pts is formed inside the sampler; read
         ``self.warp_pts`` to materialise it."""
+        # drop the previous step's tape before building the next one (see VariableStore.new_anchor)
+        self.flow_field = self.gen = self.loss = None
+        self.store.new_anchor()
         self.image0, self.disp = image0, disp
         with use_store(self.store):
             self.flow_field = self.buildModel(image0, F.to_bf16(disp))

@@ -16,6 +16,12 @@ from . import functional as F
 from .variables import current_store
 
 
+def _rec(store, var, y):
+    if store.record is not None:
+        store.record[var.name.rsplit("/", 1)[0]] = y
+    return y
+
+
 def euclidean_loss(input1, input2):
     """tf_utils.py:18-19  reduce_mean(reduce_sum((a-b)^2, 3))."""
     return F.reconstruction_loss(input1, input2, "l2")
@@ -71,7 +77,7 @@ def linear_msra(input_, output_size, name, act=None, algo=None):
     with store.scope(name):
         matrix = store.get("Matrix", [fan_in, output_size], "normal", math.sqrt(2.0 / float(fan_in)))
         b = store.get("b", [output_size], "zeros")
-    return F.linear(input_, matrix, b, act, algo)
+    return _rec(store, matrix, F.linear(input_, matrix, b, act, algo))
 
 
 def conv2d_msra(input_, output_dim, k_h, k_w, d_h, d_w, name, act=None, algo=None, out_dtype=torch.bfloat16):
@@ -83,7 +89,7 @@ def conv2d_msra(input_, output_dim, k_h, k_w, d_h, d_w, name, act=None, algo=Non
     with store.scope(name):
         w = store.get("w", [k_h, k_w, cin, output_dim], "truncated_normal", math.sqrt(2.0 / float(k_h * k_w * cin)))
         b = store.get("b", [output_dim], "zeros")
-    return F.conv2d(input_, w, b, d_h, act, algo, out_dtype)
+    return _rec(store, w, F.conv2d(input_, w, b, d_h, act, algo, out_dtype))
 
 
 def deconv2d_msra(input_, output_shape, k_h, k_w, d_h, d_w, name, act=None, algo=None, out_dtype=torch.bfloat16):
@@ -96,4 +102,4 @@ def deconv2d_msra(input_, output_shape, k_h, k_w, d_h, d_w, name, act=None, algo
     with store.scope(name):
         w = store.get("w", [k_h, k_w, int(output_shape[-1]), cin], "normal",
                       math.sqrt(2.0 / float(k_h * k_w * cin) * float(d_h) * float(d_w)))
-    return F.deconv2d(input_, w, (output_shape[1], output_shape[2]), d_h, act, algo, out_dtype)
+    return _rec(store, w, F.deconv2d(input_, w, (output_shape[1], output_shape[2]), d_h, act, algo, out_dtype))

@@ -43,9 +43,19 @@ class VariableStore:
         self.gen.manual_seed(seed)
         self.grad_ready_hook = None     # called with a Variable when its gradient has been written
         self.flat = {}
+        self.record = None              # dict: layer name -> activation, filled by tf_utils ops when set (tests)
         # dummy differentiable leaf: keeps the autograd tape alive for layers whose only
         # differentiable inputs are parameters (gradients of parameters bypass autograd)
-        self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
+        self.anchor = None
+        self.new_anchor()
+
+    def new_anchor(self):
+        """A fresh leaf per forward pass.  Autograd pins a leaf's AccumulateGrad node to the
+        stream that was current when the node was created and joins that stream at the end
+        of backward; a leaf that outlives a step would tie a CUDA-graph capture to the
+        (uncaptured) warm-up stream -- cudaErrorStreamCaptureIsolation."""
+        self.anchor = torch.empty(1, device=self.device, requires_grad=True)
+        return self.anchor
 
     # -- scopes -------------------------------------------------------------------------
     @contextlib.contextmanager

@@ -314,8 +314,9 @@ def adam_tf_step(theta, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     lr_t = adam_lr_t(lr, t, beta1, beta2)
     # TF's ApplyAdam functor form: m += (g - m)(1-b1); v += (g^2 - v)(1-b2);
     # var -= (m * lr_t) / (sqrt(v) + eps)
-    m = (m + (g - m) * f(1.0 - beta1)).astype(np.float32)
-    v = (v + (g * g - v) * f(1.0 - beta2)).astype(np.float32)
+    # (T(1) - beta) is evaluated in float32 by TF: 1 - 0.999f = 0.0010000467, not float32(0.001)
+    m = (m + (g - m) * (f(1.0) - f(beta1))).astype(np.float32)
+    v = (v + (g * g - v) * (f(1.0) - f(beta2))).astype(np.float32)
     theta = (theta - (m * lr_t) / (np.sqrt(v) + f(eps))).astype(np.float32)
     return theta, m, v
 
