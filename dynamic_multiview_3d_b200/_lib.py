@@ -24,18 +24,20 @@ SIGNATURES = {
     "dmv_arch": (C.c_char_p, []),
     "dmv_last_error": (_i, [C.c_char_p, _sz]),
     "dmv_launch_count": (_ll, []),
+    "dmv_tc_launch_count": (_ll, []),
     "dmv_sampler_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "dmv_sampler_bwd_workspace_size": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dmv_sampler_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp, _sz, _vp]),
     "dmv_loss_workspace_size": (_sz, [_ll]),
     "dmv_loss_fused_fwd_bwd": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_f), _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _vp, _sz, _vp]),
     "dmv_scale_by_device_scalar": (_i, [_vp, _vp, _ll, _vp]),
-    "dmv_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 10 + [_vp]),
-    "dmv_conv2d_dgrad": (_i, [_vp, _vp, _vp] + [_i] * 9 + [_vp]),
+    "dmv_conv_workspace_size": (_sz, [_i, _i, _i]),
+    "dmv_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
+    "dmv_conv2d_dgrad": (_i, [_vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_wgrad_workspace_size": (_sz, [_i, _i, _i, _ll]),
     "dmv_conv2d_wgrad": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
-    "dmv_deconv2d_fwd": (_i, [_vp, _vp, _vp, _i] + [_i] * 10 + [_vp]),
-    "dmv_deconv2d_dgrad": (_i, [_vp, _i, _vp, _vp] + [_i] * 9 + [_vp]),
+    "dmv_deconv2d_fwd": (_i, [_vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
+    "dmv_deconv2d_dgrad": (_i, [_vp, _i, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_deconv2d_wgrad": (_i, [_vp, _vp, _i, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dmv_linear_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -90,3 +92,7 @@ def call(name, *args):
 
 def launch_count():
     return int(load().dmv_launch_count())
+
+
+def tc_launch_count():
+    return int(load().dmv_tc_launch_count())

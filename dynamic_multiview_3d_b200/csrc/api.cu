@@ -7,6 +7,7 @@
 namespace dmv {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_tc_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -15,6 +16,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
+long long tc_launches() { return g_tc_launches.load(std::memory_order_relaxed); }
 }  // namespace dmv
 
 extern "C" {
@@ -27,4 +30,5 @@ int dmv_last_error(char* buf, size_t n) {
     return DMV_OK;
 }
 long long dmv_launch_count(void) { return dmv::g_launches.load(std::memory_order_relaxed); }
+long long dmv_tc_launch_count(void) { return dmv::tc_launches(); }
 }

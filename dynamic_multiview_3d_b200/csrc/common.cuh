@@ -13,6 +13,8 @@ namespace dmv {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void count_tc_launch();
+long long tc_launches();
 
 inline int fail(int code, const char* msg) {
     set_error("%s", msg);

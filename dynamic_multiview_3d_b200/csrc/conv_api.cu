@@ -18,25 +18,31 @@ size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels) {
     return a > b ? a : b;
 }
 
+size_t dmv_conv_workspace_size(int taps, int Cin, int Cout) {
+    if (taps <= 0 || Cin <= 0 || Cout <= 0) return 0;
+    return tc_pack_workspace(taps, Cin, Cout);
+}
+
 int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype, int B, int H, int W,
-                   int Cin, int Cout, int kh, int kw, int stride, int act, int algo, void* stream) {
+                   int Cin, int Cout, int kh, int kw, int stride, int act, void* workspace, size_t workspace_bytes, int algo,
+                   void* stream) {
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "conv2d_fwd: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, st);
+        int rc = tc_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, st);
 }
 
 int dmv_conv2d_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
-                     int algo, void* stream) {
+                     void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "conv2d_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, st);
+        int rc = tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, st);
@@ -55,24 +61,24 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, floa
 }
 
 int dmv_deconv2d_fwd(const void* x, const void* w, void* y, int y_dtype, int B, int Hout, int Wout, int Cin, int Cout, int kh,
-                     int kw, int stride, int act, int algo, void* stream) {
+                     int kw, int stride, int act, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "deconv2d_fwd: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, st);
+        int rc = tc_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, st);
 }
 
 int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout,
-                       int kh, int kw, int stride, int algo, void* stream) {
+                       int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "deconv2d_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, st);
+        int rc = tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, st);

@@ -21,16 +21,17 @@ int simt_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B,
                       int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t tc_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
+size_t tc_pack_workspace(int taps, int Cin, int Cout);
 int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin, int Cout,
-                int kh, int kw, int stride, int act, cudaStream_t st);
+                int kh, int kw, int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
-                  cudaStream_t st);
+                  void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_conv_wgrad(const void* x, int xdt, const void* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout, int kh,
                   int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hout, int Wout, int Cin, int Cout, int kh, int kw,
-                  int stride, int act, cudaStream_t st);
+                  int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout, int kh,
-                    int kw, int stride, cudaStream_t st);
+                    int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B, int Hout, int Wout, int Cin, int Cout, int kh,
                     int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, cudaStream_t st);

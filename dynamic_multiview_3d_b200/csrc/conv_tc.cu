@@ -1,18 +1,644 @@
-// tcgen05 / TMEM / TMA implicit-GEMM conv, deconv and linear kernels (sm_100a).
-// Stage 0: every entry reports DMV_E_UNSUPPORTED_SHAPE so DMV_ALGO_AUTO uses the SIMT path.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a.
+//
+// One persistent, warp-specialised kernel covers the "F" and "G" forms of conv_simt.cu
+// (conv fwd, conv dgrad, deconv fwd, deconv dgrad) as an implicit GEMM
+//     D[pixel, n] = sum_{tap} sum_{c} A_tap[pixel, c] * B[n, (tap, c)]
+// with M = a tile of <= 128 output pixels, N = output channels (padded to 16), K = taps x
+// channels.  Nothing is im2col'ed in memory:
+//   * A: for every (tap, channel chunk) ONE TMA box load of the input window shifted by the
+//     tap offset.  The input is described to TMA as a 5-D tensor (C', W', P, H', N); for
+//     stride-2 reads it is the parity view [N][H/2][2][W/2][2C] of the same NHWC buffer, so
+//     a strided tap is again a plain shifted box.  Out-of-bounds elements are zero-filled
+//     by TMA, which is exactly TF-SAME padding (asymmetric pads are just coordinates).
+//   * B: weights, K-major: either a packed [n][tap*C + c] copy (F form) or -- for the G
+//     form -- the reference HWIO layout itself read as a 3-D tensor (co, ci, tap).
+//   * stride-2 G forms (conv dgrad, deconv fwd) are split into the four output-parity
+//     classes; each class is a stride-1 problem with its own tap list, and all four are
+//     tiles of the same launch.
+// Both operands land in 128B/64B-swizzled shared memory, tcgen05.mma (M=128, kind::f16,
+// bf16 x bf16 -> fp32) accumulates into double-buffered TMEM, and four epilogue warps read
+// TMEM with tcgen05.ld, fuse bias + activation, and store NHWC rows.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "conv_impl.h"
 
+namespace {
+using namespace dmv;
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and
+// offsets in 16-byte units, version 1 (Blackwell), SBO = 8 rows, layout 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                                // LBO (unused for swizzled K-major)
+    d |= (uint64_t)((8u * row_bytes) >> 4) << 32;          // SBO: 8 rows
+    d |= (uint64_t)1 << 46;                                // version
+    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;       // swizzle mode
+    return d;
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 40;
+constexpr int kThreads = 192;
+
+struct TapClass {
+    int tap_begin, tap_count, k_elem_offset, py, px;
+};
+struct Tap {
+    short dh, dw, ph, pw;   // row/col shift in the (possibly parity-) view, parity plane, channel-plane
+    int id;                 // r*kw + s in the reference weight layout
+};
+struct IgemmParams {
+    int num_classes, tiles_per_class, tiles_w, tiles_h, groups;
+    int BW, BH, NB, rows;
+    int Jh, Jw, Nimg;
+    int kc_per_tap, c_plane;      // channel chunks per tap; channels of one parity plane (C of the source)
+    int n_real, n_pad;
+    int out_mul, out_H, out_W;
+    int act, out_f32, b_direct;
+    int stages;
+    TapClass cls[4];
+    Tap taps[kMaxTaps];
+    const float* bias;
+    void* out;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b,
+                                                             const __grid_constant__ IgemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int kRowBytes = KC * 2;
+    constexpr int kABytes = 128 * kRowBytes;
+    const int b_bytes = p.n_pad * kRowBytes;
+    const int stage_bytes = kABytes + b_bytes;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tfull_bar = empty_bar + p.stages;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * p.n_pad)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_tiles = p.num_classes * p.tiles_per_class;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = (uint32_t)(p.rows * kRowBytes + b_bytes);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ci = tile / p.tiles_per_class;
+                int t = tile - ci * p.tiles_per_class;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int g = t;
+                const TapClass& c = p.cls[ci];
+                for (int j = 0; j < c.tap_count; ++j) {
+                    const Tap& tp = p.taps[c.tap_begin + j];
+                    for (int ch = 0; ch < p.kc_per_tap; ++ch) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&full_bar[stage], tx);
+                        tma_load_5d(sa, &map_a, &full_bar[stage], tp.pw * p.c_plane + ch * KC, tw * p.BW + tp.dw, tp.ph,
+                                    th * p.BH + tp.dh, g * p.NB);
+                        if (p.b_direct)
+                            tma_load_3d(sa + kABytes, &map_b, &full_bar[stage], ch * KC, 0, tp.id);
+                        else
+                            tma_load_3d(sa + kABytes, &map_b, &full_bar[stage], c.k_elem_offset + (j * p.kc_per_tap + ch) * KC, 0, 0);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_pad, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TapClass& c = p.cls[tile / p.tiles_per_class];
+                const int kblocks = c.tap_count * p.kc_per_tap;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_pad);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_kmajor_desc(sa, kRowBytes);
+                    const uint64_t bdesc = make_kmajor_desc(sa + kABytes, kRowBytes);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)   // +32 bytes (2 x 16B units) per K=16 step inside the swizzle span
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);        // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                    // TMEM lanes 32*quarter .. +31
+        const int m = quarter * 32 + lane;               // row of the tile = output pixel
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int per_img = p.BH * p.BW;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ci = tile / p.tiles_per_class;
+            int t = tile - ci * p.tiles_per_class;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; t /= p.tiles_h;
+            const int g = t;
+            const TapClass& c = p.cls[ci];
+            const int nb = m / per_img, rem = m - nb * per_img;
+            const int bh = rem / p.BW, bw = rem - bh * p.BW;
+            const int n = g * p.NB + nb, jh = th * p.BH + bh, jw = tw * p.BW + bw;
+            const int oy = p.out_mul * jh + c.py, ox = p.out_mul * jw + c.px;
+            const bool ok = (m < p.rows) && (n < p.Nimg) && (jh < p.Jh) && (jw < p.Jw) && (oy < p.out_H) && (ox < p.out_W);
+            const long long opix = ((long long)n * p.out_H + oy) * p.out_W + ox;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
+            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (ok) {
+                    float f[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int col = c0 + k;
+                        float x = __uint_as_float(v[k]);
+                        if (p.bias && col < p.n_real) x += __ldg(p.bias + col);
+                        f[k] = apply_act(x, p.act);
+                    }
+                    if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out) + opix * p.n_real + c0;
+                        if (c0 + 16 <= p.n_real && (p.n_real & 3) == 0) {
+#pragma unroll
+                            for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(o + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+                        } else {
+                            for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = f[k];
+                        }
+                    } else {
+                        bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + c0;
+                        if (c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
+                            uint4 q0, q1;
+                            __nv_bfloat162 h;
+                            h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[2], f[3]); q0.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[4], f[5]); q0.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[6], f[7]); q0.w = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[8], f[9]); q1.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[10], f[11]); q1.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[12], f[13]); q1.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[14], f[15]); q1.w = *reinterpret_cast<uint32_t*>(&h);
+                            reinterpret_cast<uint4*>(o)[0] = q0;
+                            reinterpret_cast<uint4*>(o)[1] = q1;
+                        } else {
+                            for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// F-form weight packing: w[t][ci][co] (bf16) -> packed[co][t*Cin + ci]
+__global__ void pack_f_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int taps, int Cin, int Cout) {
+    const long long n = (long long)taps * Cin * Cout;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int co = (int)(i % Cout);
+        const long long r = i / Cout;      // t*Cin + ci
+        out[(long long)co * taps * Cin + r] = w[i];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, int row_bytes) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(DMV_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    // the driver call needs a current context on THIS host thread (autograd runs backward on its
+    // own threads, where only the other runtime instance may have bound one)
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(0);
+        ctx_bound = true;
+    }
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+        return DMV_E_CUDA;
+    }
+    return DMV_OK;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Pick the output-tile box (BW x BH x NB <= 128 rows) that wastes the fewest MMA rows.
+void choose_tile(int Jh, int Jw, int N, int& BW, int& BH, int& NB) {
+    if (Jh * Jw <= 64) {
+        BW = Jw; BH = Jh;
+        NB = 128 / (Jh * Jw);
+        if (NB > N) NB = N;
+        if (NB > 256) NB = 256;
+        return;
+    }
+    NB = 1;
+    double best = -1.0;
+    BW = 1; BH = 1;
+    for (int bw = 1; bw <= Jw && bw <= 128; ++bw) {
+        int bh = 128 / bw;
+        if (bh > Jh) bh = Jh;
+        if (bh < 1) continue;
+        const long long tiles = (long long)ceil_div(Jw, bw) * ceil_div(Jh, bh);
+        const double eff = (double)Jh * Jw / ((double)tiles * 128.0);
+        // prefer wider boxes on ties (longer contiguous TMA rows)
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > BW)) { best = eff; BW = bw; BH = bh; }
+    }
+}
+
+struct Problem {
+    // source (A) tensor: NHWC bf16 [N][Hs][Ws][Cs], read through a parity view when src_stride == 2
+    const void* src; int N, Hs, Ws, Cs, src_stride;
+    // weights
+    const void* w_hwio; int kh, kw, w_ci, w_co;   // reference layout [kh][kw][w_ci][w_co]
+    bool g_form;                                   // contraction over w_co (G) or w_ci (F)
+    // output
+    void* out; int out_f32, out_H, out_W, n_real, out_mul;
+    int Jh, Jw;                                    // per-class tiled index space
+    const float* bias; int act;
+};
+
+int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_bytes, cudaStream_t st) {
+    const int Cc = q.Cs;                            // contraction channels per tap
+    const int KC = (Cc % 64 == 0) ? 64 : 32;
+    if (Cc % 32 != 0) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: contraction channels must be a multiple of 32");
+    if (q.n_real > 256) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: more than 256 output channels");
+    if (((uintptr_t)q.src & 15) || ((uintptr_t)q.w_hwio & 15) || ((uintptr_t)q.out & 15))
+        return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: buffers must be 16-byte aligned");
+    p.n_real = q.n_real;
+    p.n_pad = ceil_div(q.n_real, 16) * 16;
+    p.kc_per_tap = Cc / KC;
+    p.c_plane = Cc;
+    p.Jh = q.Jh; p.Jw = q.Jw; p.Nimg = q.N;
+    choose_tile(q.Jh, q.Jw, q.N, p.BW, p.BH, p.NB);
+    p.rows = p.BW * p.BH * p.NB;
+    p.tiles_w = ceil_div(q.Jw, p.BW);
+    p.tiles_h = ceil_div(q.Jh, p.BH);
+    p.groups = ceil_div(q.N, p.NB);
+    p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
+    p.out_mul = q.out_mul; p.out_H = q.out_H; p.out_W = q.out_W;
+    p.act = q.act; p.out_f32 = q.out_f32; p.bias = q.bias; p.out = q.out;
+    p.b_direct = q.g_form ? 1 : 0;
+
+    const int row_bytes = KC * 2;
+    // ---- A map: 5-D (C', W', P, H', N)
+    CUtensorMap map_a, map_b;
+    {
+        const int s = q.src_stride;
+        if (s == 2 && ((q.Hs & 1) || (q.Ws & 1))) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: stride-2 source needs even H and W");
+        cuuint64_t dims[5] = {(cuuint64_t)(s * q.Cs), (cuuint64_t)(q.Ws / s), (cuuint64_t)s, (cuuint64_t)(q.Hs / s), (cuuint64_t)q.N};
+        const cuuint64_t pix = (cuuint64_t)q.Cs * 2;
+        cuuint64_t strides[4] = {(cuuint64_t)s * pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)s * q.Ws * pix, (cuuint64_t)q.Hs * q.Ws * pix};
+        cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)p.BW, 1u, (cuuint32_t)p.BH, (cuuint32_t)p.NB};
+        int rc = encode_map(&map_a, q.src, 5, dims, strides, box, row_bytes);
+        if (rc) return rc;
+    }
+    // ---- B map: 3-D.  G form reads HWIO directly as (co, ci, tap); F form reads the packed copy as (K, n, 1)
+    const int taps_total = q.kh * q.kw;
+    if (q.g_form) {
+        cuuint64_t dims[3] = {(cuuint64_t)q.w_co, (cuuint64_t)q.w_ci, (cuuint64_t)taps_total};
+        cuuint64_t strides[2] = {(cuuint64_t)q.w_co * 2, (cuuint64_t)q.w_ci * q.w_co * 2};
+        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.n_pad, 1u};
+        int rc = encode_map(&map_b, q.w_hwio, 3, dims, strides, box, row_bytes);
+        if (rc) return rc;
+    } else {
+        const size_t need = (size_t)taps_total * q.w_ci * q.w_co * 2;
+        if (!workspace || ws_bytes < need) return fail(DMV_E_WORKSPACE, "tc: workspace too small for packed weights");
+        long long blocks = ceil_div_ll((long long)taps_total * q.w_ci * q.w_co, 256);
+        if (blocks > 2048) blocks = 2048;
+        pack_f_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)q.w_hwio, (bf16*)workspace, taps_total, q.w_ci, q.w_co);
+        int rc = check_launch("tc pack weights");
+        if (rc) return rc;
+        const cuuint64_t ktot = (cuuint64_t)taps_total * q.w_ci;
+        cuuint64_t dims[3] = {ktot, (cuuint64_t)q.w_co, 1};
+        cuuint64_t strides[2] = {ktot * 2, ktot * 2 * (cuuint64_t)q.w_co};
+        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.n_pad, 1u};
+        rc = encode_map(&map_b, workspace, 3, dims, strides, box, row_bytes);
+        if (rc) return rc;
+    }
+    // ---- shared memory / grid
+    const int stage_bytes = 128 * row_bytes + p.n_pad * row_bytes;
+    int stages = (160 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+    const int total_tiles = p.num_classes * p.tiles_per_class;
+    int grid = num_sms();
+    if (grid > total_tiles) grid = total_tiles;
+    cudaError_t e;
+    if (KC == 64) {
+        e = cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) igemm_kernel<64><<<grid, kThreads, smem, st>>>(map_a, map_b, p);
+    } else {
+        e = cudaFuncSetAttribute(igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) igemm_kernel<32><<<grid, kThreads, smem, st>>>(map_a, map_b, p);
+    }
+    if (e != cudaSuccess) {
+        set_error("tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return DMV_E_CUDA;
+    }
+    count_tc_launch();
+    return check_launch("igemm_tc");
+}
+
+// taps of the F form (conv-fwd-like): A pixel = out*stride + (r - pt, s - pl)
+int build_f(IgemmParams& p, int kh, int kw, int stride, int pt, int pl) {
+    if (kh * kw > kMaxTaps) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: too many taps");
+    p.num_classes = 1;
+    p.cls[0] = TapClass{0, kh * kw, 0, 0, 0};
+    for (int r = 0; r < kh; ++r)
+        for (int s = 0; s < kw; ++s) {
+            Tap& t = p.taps[r * kw + s];
+            const int dy = r - pt, dx = s - pl;
+            if (stride == 1) {
+                t.dh = (short)dy; t.dw = (short)dx; t.ph = 0; t.pw = 0;
+            } else {
+                t.ph = (short)(((dy % 2) + 2) % 2); t.dh = (short)((dy - t.ph) / 2);
+                t.pw = (short)(((dx % 2) + 2) % 2); t.dw = (short)((dx - t.pw) / 2);
+            }
+            t.id = r * kw + s;
+        }
+    return DMV_OK;
+}
+
+// taps of the G form (conv-dgrad-like): small pixel = (big + pad - tap) / stride, split by output parity
+int build_g(IgemmParams& p, int kh, int kw, int stride, int pt, int pl, int w_co) {
+    int n = 0;
+    p.num_classes = stride * stride;
+    if (stride > 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: stride > 2");
+    for (int py = 0; py < stride; ++py)
+        for (int px = 0; px < stride; ++px) {
+            TapClass& c = p.cls[py * stride + px];
+            c.tap_begin = n; c.py = py; c.px = px; c.k_elem_offset = 0;
+            for (int r = 0; r < kh; ++r) {
+                if ((py + pt - r) % stride) continue;
+                for (int s = 0; s < kw; ++s) {
+                    if ((px + pl - s) % stride) continue;
+                    if (n >= kMaxTaps) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: too many taps");
+                    Tap& t = p.taps[n++];
+                    t.dh = (short)((py + pt - r) / stride); t.dw = (short)((px + pl - s) / stride);
+                    t.ph = 0; t.pw = 0; t.id = r * kw + s;
+                }
+            }
+            c.tap_count = n - c.tap_begin;
+            if (c.tap_count == 0) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: empty parity class");
+        }
+    (void)w_co;
+    return DMV_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// entry points used by conv_api.cu
+// ----------------------------------------------------------------------------------------------
 namespace dmv {
-static int unsupported(const char* what) { return fail(DMV_E_UNSUPPORTED_SHAPE, what); }
+
 size_t tc_wgrad_workspace(int, int, int, long long) { return 0; }
-int tc_conv_fwd(const void*, int, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t) { return unsupported("tc_conv_fwd: shape not covered"); }
-int tc_conv_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t) { return unsupported("tc_conv_dgrad: shape not covered"); }
-int tc_conv_wgrad(const void*, int, const void*, float*, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_conv_wgrad: shape not covered"); }
-int tc_deconv_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t) { return unsupported("tc_deconv_fwd: shape not covered"); }
-int tc_deconv_dgrad(const void*, int, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t) { return unsupported("tc_deconv_dgrad: shape not covered"); }
-int tc_deconv_wgrad(const void*, const void*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_deconv_wgrad: shape not covered"); }
-int tc_linear_fwd(const void*, const void*, const float*, void*, int, int, int, int, cudaStream_t) { return unsupported("tc_linear_fwd: shape not covered"); }
-int tc_linear_dgrad(const void*, const void*, void*, int, int, int, cudaStream_t) { return unsupported("tc_linear_dgrad: shape not covered"); }
-int tc_linear_wgrad(const void*, const void*, float*, float*, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_linear_wgrad: shape not covered"); }
+
+size_t tc_pack_workspace(int taps, int Cin, int Cout) { return (size_t)taps * Cin * Cout * 2 + 256; }
+
+// conv fwd: F form, A = x
+int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin, int Cout,
+                int kh, int kw, int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (xdt != DMV_DT_BF16) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_conv_fwd: bf16 input only");
+    if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_conv_fwd: stride");
+    const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = build_f(p, kh, kw, stride, ph.before, pw.before);
+    if (rc) return rc;
+    Problem q;
+    q.src = x; q.N = B; q.Hs = H; q.Ws = W; q.Cs = Cin; q.src_stride = stride;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = false;
+    q.out = y; q.out_f32 = (ydt == DMV_DT_F32); q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cout; q.out_mul = 1;
+    q.Jh = ph.out; q.Jw = pw.out; q.bias = bias; q.act = act;
+    return launch_igemm(q, p, ws, ws_bytes, st);
+}
+
+// conv dgrad: G form, A = dy (small side), output = dx (big side, Cin channels)
+int tc_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_conv_dgrad: stride");
+    const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = build_g(p, kh, kw, stride, ph.before, pw.before, Cout);
+    if (rc) return rc;
+    Problem q;
+    q.src = dy; q.N = B; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cout; q.src_stride = 1;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = true;
+    q.out = dx; q.out_f32 = 0; q.out_H = H; q.out_W = W; q.n_real = Cin; q.out_mul = stride;
+    q.Jh = ceil_div(H, stride); q.Jw = ceil_div(W, stride); q.bias = nullptr; q.act = DMV_ACT_NONE;
+    return launch_igemm(q, p, ws, ws_bytes, st);
+}
+
+// deconv fwd: G form with the deconv's weights w[kh][kw][Cout_t][Cin_t] (ci-role = Cout_t, co-role = Cin_t)
+int tc_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hout, int Wout, int Cin, int Cout, int kh, int kw,
+                  int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_deconv_fwd: stride");
+    const SamePad ph = same_pad(Hout, kh, stride), pw = same_pad(Wout, kw, stride);
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = build_g(p, kh, kw, stride, ph.before, pw.before, Cin);
+    if (rc) return rc;
+    Problem q;
+    q.src = x; q.N = B; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cin; q.src_stride = 1;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = true;
+    q.out = y; q.out_f32 = (ydt == DMV_DT_F32); q.out_H = Hout; q.out_W = Wout; q.n_real = Cout; q.out_mul = stride;
+    q.Jh = ceil_div(Hout, stride); q.Jw = ceil_div(Wout, stride); q.bias = nullptr; q.act = act;
+    return launch_igemm(q, p, ws, ws_bytes, st);
+}
+
+// deconv dgrad: F form over dy (big side, Cout_t channels) with w[kh][kw][Cout_t][Cin_t]
+int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout, int kh, int kw,
+                    int stride, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (dydt != DMV_DT_BF16) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_deconv_dgrad: bf16 gradient only");
+    if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_deconv_dgrad: stride");
+    const SamePad ph = same_pad(Hout, kh, stride), pw = same_pad(Wout, kw, stride);
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = build_f(p, kh, kw, stride, ph.before, pw.before);
+    if (rc) return rc;
+    Problem q;
+    q.src = dy; q.N = B; q.Hs = Hout; q.Ws = Wout; q.Cs = Cout; q.src_stride = stride;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = false;
+    q.out = dx; q.out_f32 = 0; q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cin; q.out_mul = 1;
+    q.Jh = ph.out; q.Jw = pw.out; q.bias = nullptr; q.act = DMV_ACT_NONE;
+    return launch_igemm(q, p, ws, ws_bytes, st);
+}
+
+static int unsupported(const char* what) { return fail(DMV_E_UNSUPPORTED_SHAPE, what); }
+int tc_conv_wgrad(const void*, int, const void*, float*, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_conv_wgrad: not covered yet"); }
+int tc_deconv_wgrad(const void*, const void*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_deconv_wgrad: not covered yet"); }
+int tc_linear_fwd(const void*, const void*, const float*, void*, int, int, int, int, cudaStream_t) { return unsupported("tc_linear_fwd: not covered yet"); }
+int tc_linear_dgrad(const void*, const void*, void*, int, int, int, cudaStream_t) { return unsupported("tc_linear_dgrad: not covered yet"); }
+int tc_linear_wgrad(const void*, const void*, float*, float*, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_linear_wgrad: not covered yet"); }
 }  // namespace dmv

@@ -139,8 +139,9 @@ class _Conv2d(torch.autograd.Function):
         assert wcin == Cin, (wvar.name, wvar.shape, x.shape)
         y = torch.empty((B, same_out(H, stride), same_out(W, stride), Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
+        ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
         call("dmv_conv2d_fwd", _p(x), _dt(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
-             B, H, W, Cin, Cout, kh, kw, stride, ACT[act], algo, _stream(x))
+             B, H, W, Cin, Cout, kh, kw, stride, ACT[act], _p(ws), ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
         ctx.cfg = (wvar, bvar, stride, act, algo)
         return y
@@ -166,7 +167,8 @@ class _Conv2d(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), B, H, W, Cin, Cout, kh, kw, stride, algo, st)
+            ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+            call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
             if x.dtype != torch.bfloat16:
                 dxf = torch.empty(x.shape, dtype=x.dtype, device=x.device)
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
@@ -197,8 +199,9 @@ class _Deconv2d(torch.autograd.Function):
         assert same_out(Ho, stride) == Hin and same_out(Wo, stride) == Win, "output_shape inconsistent with input"
         y = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
-        call("dmv_deconv2d_fwd", _p(x), _p(wvar.half), _p(y), _dt(y), B, Ho, Wo, Cin, Cout, kh, kw, stride, ACT[act], algo,
-             _stream(x))
+        ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+        call("dmv_deconv2d_fwd", _p(x), _p(wvar.half), _p(y), _dt(y), B, Ho, Wo, Cin, Cout, kh, kw, stride, ACT[act], _p(ws),
+             ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
         ctx.cfg = (wvar, stride, act, algo)
         return y
@@ -220,7 +223,9 @@ class _Deconv2d(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            call("dmv_deconv2d_dgrad", _p(dpre), _dt(dpre), _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, algo, st)
+            ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+            call("dmv_deconv2d_dgrad", _p(dpre), _dt(dpre), _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
+                 ws.numel(), algo, st)
         pixels = B * x.shape[1] * x.shape[2]
         nws = _lib.load().dmv_wgrad_workspace_size(kh * kw, Cout, Cin, pixels)
         ws = workspace(nws, x.device)

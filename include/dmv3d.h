@@ -65,6 +65,7 @@ int dmv_version(void);                      /* MAJOR*10000 + MINOR*100 + PATCH *
 const char* dmv_arch(void);                 /* "sm_100a" */
 int dmv_last_error(char* buf, size_t n);    /* copies the thread's last error text */
 long long dmv_launch_count(void);           /* kernels launched by this library so far */
+long long dmv_tc_launch_count(void);        /* of which tcgen05 tensor-core kernels */
 
 /* ---- bilinear sampler --------------------------------------------------------------- *
  * replaces tf.contrib.resampler.resampler -- tf_utils.py:40-42 (resample_layer) and
@@ -124,13 +125,18 @@ int dmv_scale_by_device_scalar(float* x, const float* scalar, long long n, void*
  * `act` is fused into the forward epilogue; backward entry points take the gradient wrt
  * the PRE-activation (dmv_act_bwd produces it from the post-activation output).          */
 
+/* Forward / dgrad scratch (the tensor-core path repacks the layer's weights into it):
+ * dmv_conv_workspace_size(kh*kw, Cin, Cout) bytes; may be NULL with DMV_ALGO_SIMT.        */
+size_t dmv_conv_workspace_size(int taps, int Cin, int Cout);
 /* replaces tf.nn.conv2d(...,'SAME') + b  -- conv2d_msra, tf_utils.py:70-84 */
 int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w_bf16, const float* bias, void* y,
                    int y_dtype, int B, int H, int W, int Cin, int Cout, int kh, int kw,
-                   int stride, int act, int algo, void* stream);
+                   int stride, int act, void* workspace, size_t workspace_bytes, int algo,
+                   void* stream);
 /* replaces Conv2DBackpropInput (implicit, appearance_flow_model.py:77) */
 int dmv_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int B, int H, int W,
-                     int Cin, int Cout, int kh, int kw, int stride, int algo, void* stream);
+                     int Cin, int Cout, int kh, int kw, int stride, void* workspace,
+                     size_t workspace_bytes, int algo, void* stream);
 /* replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 [kh,kw,Cin,Cout], db f32 [Cout] or NULL.
  * Deterministic split-K (fixed-order second pass).  workspace: dmv_wgrad_workspace_size.   */
 size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels);
@@ -142,11 +148,11 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy_bf16, float* dw,
  * tf_utils.py:87-98 (no bias).  x [B,Hin,Win,Cin] -> y [B,Hout,Wout,Cout], where
  * Hin == ceil(Hout/stride).                                                               */
 int dmv_deconv2d_fwd(const void* x_bf16, const void* w_bf16, void* y, int y_dtype, int B, int Hout,
-                     int Wout, int Cin, int Cout, int kh, int kw, int stride, int act, int algo,
-                     void* stream);
+                     int Wout, int Cin, int Cout, int kh, int kw, int stride, int act,
+                     void* workspace, size_t workspace_bytes, int algo, void* stream);
 int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w_bf16, void* dx_bf16, int B,
                        int Hout, int Wout, int Cin, int Cout, int kh, int kw, int stride,
-                       int algo, void* stream);
+                       void* workspace, size_t workspace_bytes, int algo, void* stream);
 int dmv_deconv2d_wgrad(const void* x_bf16, const void* dy, int dy_dtype, float* dw, int B, int Hout,
                        int Wout, int Cin, int Cout, int kh, int kw, int stride, void* workspace,
                        size_t workspace_bytes, int algo, void* stream);

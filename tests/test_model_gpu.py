@@ -49,7 +49,7 @@ def test_forward_parity_with_oracle(cls, kind, H, algo):
     assert max(early) < 1e-2, worst
     rel = np.linalg.norm(flow - rflow) / np.linalg.norm(rflow)
     assert rel < 2e-2, rel
-    assert np.abs(model.warp_pts.cpu().numpy() - ref["warp_pts"]).max() < 1e-2
+    assert np.abs(model.warp_pts.cpu().numpy() - ref["warp_pts"]).max() < 1e-3 * H      # pixels, relative to the image side
     gen, rgen = out["gen"].detach().cpu().numpy(), ref["gen"]
     assert np.abs(gen - rgen).max() < 2e-2
     loss = float(model.build_loss(torch.from_numpy(b["image1"]).cuda()).detach())

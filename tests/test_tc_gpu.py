@@ -1,0 +1,136 @@
+"""GPU tests of the tcgen05/TMEM/TMA implicit-GEMM path: it must actually run (tensor-core
+launch counter), agree with the oracle on small cases and with the SIMT kernels at the
+BASELINE layer sizes (224^2 graph, batch 8)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _store():
+    from dynamic_multiview_3d_b200.variables import VariableStore
+    return VariableStore(torch.device("cuda:0"))
+
+
+def _var(store, name, arr):
+    v = store.get(name, arr.shape, "zeros")
+    v.master.copy_(torch.from_numpy(np.ascontiguousarray(arr)).cuda())
+    store._cast(v.master, v.half, v.numel)
+    return v
+
+
+def bf16_round(x):
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+SMALL = [  # kind, k, s, H(big side), cin, cout, B
+    ("conv", 5, 1, 16, 32, 32, 3), ("conv", 5, 2, 16, 32, 64, 3), ("conv", 3, 1, 7, 256, 256, 5), ("conv", 3, 2, 14, 128, 256, 3),
+    ("conv", 3, 1, 14, 128, 128, 2), ("conv", 5, 1, 28, 64, 64, 2), ("conv", 3, 2, 28, 64, 128, 2), ("conv", 5, 1, 24, 32, 64, 1),
+    ("deconv", 3, 2, 14, 256, 128, 3), ("deconv", 3, 2, 28, 128, 64, 2), ("deconv", 5, 2, 16, 64, 32, 3), ("deconv", 5, 2, 32, 32, 2, 2),
+    ("deconv", 3, 1, 16, 32, 2, 2),
+]
+
+
+@pytest.mark.parametrize("kind,k,s,H,cin,cout,B", SMALL)
+def test_tc_small_vs_oracle(kind, k, s, H, cin, cout, B):
+    from dynamic_multiview_3d_b200 import _lib, functional as F
+    rng = np.random.default_rng(k * 1000 + s * 100 + cin + cout + H)
+    st = _store()
+    n0 = _lib.tc_launch_count()
+    if kind == "conv":
+        x = bf16_round(rng.standard_normal((B, H, H, cin)))
+        w = bf16_round(rng.standard_normal((k, k, cin, cout)) * T.conv_stddev(k, k, cin))
+        b = rng.standard_normal(cout).astype(np.float32)
+        y = T.conv2d_same(x, w, b, s, s)
+        gy = bf16_round(rng.standard_normal(y.shape))
+        gx, gw, gb = T.conv2d_same_grads(x, w, gy, s, s)
+        wv, bv = _var(st, "w", w), _var(st, "b", b)
+        xt = torch.from_numpy(x).cuda().to(torch.bfloat16).requires_grad_(True)
+        yo = F.conv2d(xt, wv, bv, s, None, "auto", torch.float32)
+        assert _lib.tc_launch_count() == n0 + 1, "forward did not take the tensor-core path"
+        assert _rel(yo.detach().cpu().numpy(), y) < 1e-4
+        yb = F.conv2d(xt, wv, bv, s, "lrelu", "auto")
+        assert _rel(yb.detach().float().cpu().numpy(), T.lrelu(y)) < 1e-2
+        yo2 = F.conv2d(xt, wv, bv, s, None, "auto")
+        n1 = _lib.tc_launch_count()
+        yo2.backward(torch.from_numpy(gy).cuda().to(torch.bfloat16))
+        assert _lib.tc_launch_count() == n1 + 1, "dgrad did not take the tensor-core path"
+    else:
+        h = -(-H // s)
+        x = bf16_round(rng.standard_normal((B, h, h, cin)))
+        w = bf16_round(rng.standard_normal((k, k, cout, cin)) * T.deconv_stddev(k, k, cin, s, s))
+        y = T.conv2d_transpose_same(x, w, (B, H, H, cout), s, s)
+        gy = bf16_round(rng.standard_normal(y.shape))
+        gx, gw = T.conv2d_transpose_same_grads(x, w, gy, s, s)
+        wv = _var(st, "w", w)
+        xt = torch.from_numpy(x).cuda().to(torch.bfloat16).requires_grad_(True)
+        yo = F.deconv2d(xt, wv, (H, H), s, None, "auto", torch.float32)
+        assert _lib.tc_launch_count() == n0 + 1, "forward did not take the tensor-core path"
+        assert _rel(yo.detach().cpu().numpy(), y) < 1e-4
+        yo2 = F.deconv2d(xt, wv, (H, H), s, None, "auto")
+        n1 = _lib.tc_launch_count()
+        yo2.backward(torch.from_numpy(gy).cuda().to(torch.bfloat16))
+        if cout % 32 == 0:
+            assert _lib.tc_launch_count() == n1 + 1, "dgrad did not take the tensor-core path"
+    assert _rel(xt.grad.float().cpu().numpy(), gx) < 1e-2
+    assert _rel(wv.grad.cpu().numpy(), gw) < 2e-4
+
+
+FULL = [  # the 224^2 graph's tensor-core layers (appearance_flow_model.py:89-125), batch 8
+    ("conv", 5, 1, 112, 32, 32), ("conv", 5, 2, 112, 32, 32), ("conv", 5, 1, 56, 32, 32), ("conv", 5, 2, 56, 32, 64),
+    ("conv", 5, 1, 28, 64, 64), ("conv", 3, 2, 28, 64, 128), ("conv", 3, 1, 14, 128, 128), ("conv", 3, 2, 14, 128, 256),
+    ("conv", 3, 1, 7, 256, 256), ("conv", 5, 1, 56, 32, 64),
+    ("deconv", 3, 2, 14, 256, 128), ("deconv", 3, 2, 28, 128, 64), ("deconv", 5, 2, 56, 64, 32), ("deconv", 5, 2, 112, 64, 32),
+    ("deconv", 5, 2, 224, 32, 2),
+]
+
+
+@pytest.mark.parametrize("kind,k,s,H,cin,cout", FULL)
+def test_tc_full_size_vs_simt(kind, k, s, H, cin, cout):
+    """BASELINE layer sizes: the oracle is too slow here, so the tensor-core result is compared with the
+    (oracle-verified) SIMT kernels on the same bf16 inputs -- both accumulate in fp32."""
+    from dynamic_multiview_3d_b200 import _lib, functional as F
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(k + s + H + cin)
+    st = _store()
+    if kind == "conv":
+        x = torch.randn((B, H, H, cin), device="cuda", generator=g).to(torch.bfloat16)
+        wv = _var(st, "w", (np.random.default_rng(1).standard_normal((k, k, cin, cout)) * T.conv_stddev(k, k, cin)).astype(np.float32))
+        bv = _var(st, "b", np.random.default_rng(2).standard_normal(cout).astype(np.float32))
+        outs, grads = {}, {}
+        for algo in ("simt", "auto"):
+            xt = x.clone().requires_grad_(True)
+            n0 = _lib.tc_launch_count()
+            y = F.conv2d(xt, wv, bv, s, "lrelu", algo, torch.float32)
+            if algo == "auto":
+                assert _lib.tc_launch_count() == n0 + 1
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+            yb = F.conv2d(xt, wv, bv, s, None, algo)
+            yb.backward(gy.to(torch.bfloat16))
+            outs[algo], grads[algo] = y.detach(), xt.grad.float()
+    else:
+        h = -(-H // s)
+        x = torch.randn((B, h, h, cin), device="cuda", generator=g).to(torch.bfloat16)
+        wv = _var(st, "w", (np.random.default_rng(1).standard_normal((k, k, cout, cin)) * T.deconv_stddev(k, k, cin, s, s)).astype(np.float32))
+        outs, grads = {}, {}
+        for algo in ("simt", "auto"):
+            xt = x.clone().requires_grad_(True)
+            n0 = _lib.tc_launch_count()
+            y = F.deconv2d(xt, wv, (H, H), s, "lrelu" if cout > 2 else None, algo, torch.float32)
+            if algo == "auto":
+                assert _lib.tc_launch_count() == n0 + 1
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+            yb = F.deconv2d(xt, wv, (H, H), s, None, algo)
+            yb.backward(gy.to(torch.bfloat16))
+            outs[algo], grads[algo] = y.detach(), xt.grad.float()
+    d = (outs["auto"] - outs["simt"]).abs().max() / outs["simt"].abs().max()
+    assert float(d) < 1e-4, float(d)
+    dg = (grads["auto"] - grads["simt"]).abs().max() / grads["simt"].abs().max()
+    assert float(dg) < 1e-2, float(dg)           # bf16 outputs: one rounding apart at most
