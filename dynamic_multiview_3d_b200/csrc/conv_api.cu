@@ -15,7 +15,9 @@ size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels) {
     if (taps <= 0 || Cin <= 0 || Cout <= 0 || pixels <= 0) return 0;
     size_t a = simt_wgrad_workspace(taps, Cin, Cout, pixels);
     size_t b = tc_wgrad_workspace(taps, Cin, Cout, pixels);
-    return a > b ? a : b;
+    size_t c = thin_wgrad_eligible(taps, Cin, Cout) ? thin_wgrad_workspace(taps, Cin) : 0;
+    if (b > a) a = b;
+    return c > a ? c : a;
 }
 
 size_t dmv_conv_workspace_size(int taps, int Cin, int Cout) {
@@ -53,8 +55,20 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, floa
     DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "conv2d_wgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (algo == DMV_ALGO_AUTO && thin_wgrad_eligible(kh * kw, Cin, Cout)) {   // e0: 3-channel image side
+        int rc = thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc == DMV_OK && db) {
+            const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+            rc = simt_bias_grad(dy, db, (long long)B * ph.out * pw.out, Cout, workspace, workspace_bytes, st);
+        }
+        return rc;
+    }
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_conv_wgrad(x, x_dtype, dy, dw, db, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        int rc = tc_conv_wgrad(x, x_dtype, dy, dw, nullptr, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc == DMV_OK && db) {
+            const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+            rc = simt_bias_grad(dy, db, (long long)B * ph.out * pw.out, Cout, workspace, workspace_bytes, st);
+        }
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_conv_wgrad(x, x_dtype, dy, dw, db, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
@@ -89,6 +103,8 @@ int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, i
     DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "deconv2d_wgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (algo == DMV_ALGO_AUTO && thin_wgrad_eligible(kh * kw, Cout, Cin))      // flow head: 2-channel output side
+        return thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, kh, kw, stride, workspace, workspace_bytes, st);
     if (algo != DMV_ALGO_SIMT) {
         int rc = tc_deconv_wgrad(x, dy, dy_dtype, dw, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
@@ -126,7 +142,8 @@ int dmv_linear_wgrad(const void* x, const void* dy, float* dw, float* db, int M,
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_linear_wgrad(x, dy, dw, db, M, K, N, workspace, workspace_bytes, st);
+        int rc = tc_linear_wgrad(x, dy, dw, nullptr, M, K, N, workspace, workspace_bytes, st);
+        if (rc == DMV_OK && db) rc = simt_bias_grad(dy, db, M, N, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_conv_wgrad(x, DMV_DT_BF16, dy, dw, db, M, 1, 1, K, N, 1, 1, 1, workspace, workspace_bytes, st);

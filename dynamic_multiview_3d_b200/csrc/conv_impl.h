@@ -7,6 +7,7 @@
 
 namespace dmv {
 size_t simt_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
+int simt_bias_grad(const void* dy_bf16, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 int simt_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin,
                   int Cout, int kh, int kw, int stride, int act, cudaStream_t st);
 int simt_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
@@ -19,6 +20,11 @@ int simt_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, 
                       int kw, int stride, cudaStream_t st);
 int simt_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B, int Hout, int Wout, int Cin, int Cout, int kh,
                       int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
+
+size_t thin_wgrad_workspace(int taps, int Ct);
+bool thin_wgrad_eligible(int taps, int Ct, int Cw);
+int thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride,
+               void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t tc_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
 size_t tc_pack_workspace(int taps, int Cin, int Cout);

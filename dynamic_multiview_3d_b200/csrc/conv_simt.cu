@@ -306,6 +306,10 @@ int run_g(const void* s, const void* w, void* b, const ConvGeom& g, int act, cud
 // (called by the public dispatchers in conv_api.cu)
 namespace dmv {
 
+int simt_bias_grad(const void* dy_bf16, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return run_colsum<bf16>((const bf16*)dy_bf16, db, pixels, C, ws, ws_bytes, st);
+}
+
 size_t simt_wgrad_workspace(int taps, int Cin, int Cout, long long pixels) {
     const SplitPlan p = plan_split(taps, Cin, Cout, pixels);
     size_t a = (size_t)p.splits * taps * Cin * Cout * sizeof(float);

@@ -19,104 +19,12 @@
 // bf16 x bf16 -> fp32) accumulates into double-buffered TMEM, and four epilogue warps read
 // TMEM with tcgen05.ld, fuse bias + activation, and store NHWC rows.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "conv_impl.h"
 
 namespace {
 using namespace dmv;
-typedef __nv_bfloat16 bf16;
-
-// ----------------------------------------------------------------------------------------------
-// PTX wrappers
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and
-// offsets in 16-byte units, version 1 (Blackwell), SBO = 8 rows, layout 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                                // LBO (unused for swizzled K-major)
-    d |= (uint64_t)((8u * row_bytes) >> 4) << 32;          // SBO: 8 rows
-    d |= (uint64_t)1 << 46;                                // version
-    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;       // swizzle mode
-    return d;
-}
+using namespace dmv::tc;
 
 // ----------------------------------------------------------------------------------------------
 // kernel
@@ -136,9 +44,12 @@ struct IgemmParams {
     int BW, BH, NB, rows;
     int Jh, Jw, Nimg;
     int kc_per_tap, c_plane;      // channel chunks per tap; channels of one parity plane (C of the source)
-    int n_real, n_pad;
+    int n_real, n_pad;            // total output channels; UMMA N of one N tile (multiple of 16)
+    int n_tiles;                  // N tiles (n_pad columns each)
     int out_mul, out_H, out_W;
-    int act, out_f32, b_direct;
+    int act, out_f32;
+    int b_mode;                   // 0: packed K-major [n][K]; 1: reference HWIO read as (co, ci, tap), K-major;
+                                  // 2: MN-major [K][n] (linear forward: Matrix[K,N] as stored)
     int stages;
     TapClass cls[4];
     Tap taps[kMaxTaps];
@@ -153,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int kRowBytes = KC * 2;
     constexpr int kABytes = 128 * kRowBytes;
-    const int b_bytes = p.n_pad * kRowBytes;
+    const int b_bytes = p.n_pad * kRowBytes;     // mode 2: (n_pad/64) boxes of KC rows x 128 B -- the same size
     const int stage_bytes = kABytes + b_bytes;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -184,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int total_tiles = p.num_classes * p.tiles_per_class;
+    const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -193,8 +104,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             uint32_t phase = 0;
             const uint32_t tx = (uint32_t)(p.rows * kRowBytes + b_bytes);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ci = tile / p.tiles_per_class;
-                int t = tile - ci * p.tiles_per_class;
+                const int nt = tile % p.n_tiles;
+                const int sp = tile / p.n_tiles;
+                const int ci = sp / p.tiles_per_class;
+                int t = sp - ci * p.tiles_per_class;
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int g = t;
@@ -207,10 +120,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         mbar_expect_tx(&full_bar[stage], tx);
                         tma_load_5d(sa, &map_a, &full_bar[stage], tp.pw * p.c_plane + ch * KC, tw * p.BW + tp.dw, tp.ph,
                                     th * p.BH + tp.dh, g * p.NB);
-                        if (p.b_direct)
-                            tma_load_3d(sa + kABytes, &map_b, &full_bar[stage], ch * KC, 0, tp.id);
-                        else
-                            tma_load_3d(sa + kABytes, &map_b, &full_bar[stage], c.k_elem_offset + (j * p.kc_per_tap + ch) * KC, 0, 0);
+                        if (p.b_mode == 1) {
+                            tma_load_3d(sa + kABytes, &map_b, &full_bar[stage], ch * KC, nt * p.n_pad, tp.id);
+                        } else if (p.b_mode == 0) {
+                            tma_load_3d(sa + kABytes, &map_b, &full_bar[stage], c.k_elem_offset + (j * p.kc_per_tap + ch) * KC,
+                                        nt * p.n_pad, 0);
+                        } else {
+                            for (int jb = 0; jb < p.n_pad / 64; ++jb)
+                                tma_load_3d(sa + kABytes + jb * (KC * 128), &map_b, &full_bar[stage], nt * p.n_pad + jb * 64,
+                                            (j * p.kc_per_tap + ch) * KC, 0);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -220,13 +139,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_pad, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (p.b_mode == 2 ? (1u << 16) : 0u) |
+                                   ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TapClass& c = p.cls[tile / p.tiles_per_class];
+                const TapClass& c = p.cls[(tile / p.n_tiles) / p.tiles_per_class];
                 const int kblocks = c.tap_count * p.kc_per_tap;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -236,10 +156,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t adesc = make_kmajor_desc(sa, kRowBytes);
-                    const uint64_t bdesc = make_kmajor_desc(sa + kABytes, kRowBytes);
+                    // K-major B: +32 bytes per K=16 step inside the swizzle span; MN-major B: +16 rows of 128 B
+                    const uint64_t bdesc = p.b_mode == 2 ? make_mnmajor_desc(sa + kABytes, 128, KC * 128) : make_kmajor_desc(sa + kABytes, kRowBytes);
+                    const uint64_t bstep = p.b_mode == 2 ? 128u : 2u;
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k)   // +32 bytes (2 x 16B units) per K=16 step inside the swizzle span
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < KC / 16; ++k)
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + bstep * (uint64_t)k, idesc, (kb | k) ? 1u : 0u);
                     tc_commit(&empty_bar[stage]);        // frees the smem slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -255,12 +177,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         uint32_t acc_phase = 0;
         const int per_img = p.BH * p.BW;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int ci = tile / p.tiles_per_class;
-            int t = tile - ci * p.tiles_per_class;
+            const int nt = tile % p.n_tiles;
+            const int sp = tile / p.n_tiles;
+            const int ci = sp / p.tiles_per_class;
+            int t = sp - ci * p.tiles_per_class;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; t /= p.tiles_h;
             const int g = t;
             const TapClass& c = p.cls[ci];
+            const int ncol0 = nt * p.n_pad;
             const int nb = m / per_img, rem = m - nb * per_img;
             const int bh = rem / p.BW, bw = rem - bh * p.BW;
             const int n = g * p.NB + nb, jh = th * p.BH + bh, jw = tw * p.BW + bw;
@@ -278,22 +203,22 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     float f[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
-                        const int col = c0 + k;
+                        const int col = ncol0 + c0 + k;
                         float x = __uint_as_float(v[k]);
                         if (p.bias && col < p.n_real) x += __ldg(p.bias + col);
                         f[k] = apply_act(x, p.act);
                     }
                     if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out) + opix * p.n_real + c0;
-                        if (c0 + 16 <= p.n_real && (p.n_real & 3) == 0) {
+                        float* o = reinterpret_cast<float*>(p.out) + opix * p.n_real + ncol0 + c0;
+                        if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 3) == 0) {
 #pragma unroll
                             for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(o + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
                         } else {
-                            for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = f[k];
+                            for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = f[k];
                         }
                     } else {
-                        bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + c0;
-                        if (c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
+                        bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + ncol0 + c0;
+                        if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
                             uint4 q0, q1;
                             __nv_bfloat162 h;
                             h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
@@ -307,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                             reinterpret_cast<uint4*>(o)[0] = q0;
                             reinterpret_cast<uint4*>(o)[1] = q1;
                         } else {
-                            for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
+                            for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
                         }
                     }
                 }
@@ -340,55 +265,6 @@ __global__ void pack_f_kernel(const bf16* __restrict__ w, bf16* __restrict__ out
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, int row_bytes) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return fail(DMV_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    // the driver call needs a current context on THIS host thread (autograd runs backward on its
-    // own threads, where only the other runtime instance may have bound one)
-    static thread_local bool ctx_bound = false;
-    if (!ctx_bound) {
-        cudaFree(0);
-        ctx_bound = true;
-    }
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
-                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
-        return DMV_E_CUDA;
-    }
-    return DMV_OK;
-}
-
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 // Pick the output-tile box (BW x BH x NB <= 128 rows) that wastes the fewest MMA rows.
 void choose_tile(int Jh, int Jw, int N, int& BW, int& BH, int& NB) {
     if (Jh * Jw <= 64) {
@@ -418,6 +294,8 @@ struct Problem {
     // weights
     const void* w_hwio; int kh, kw, w_ci, w_co;   // reference layout [kh][kw][w_ci][w_co]
     bool g_form;                                   // contraction over w_co (G) or w_ci (F)
+    int n_tile;                                    // 0: one N tile covering all output channels
+    int b_mode_override;                           // -1: by form; 2: MN-major Matrix[K,N] (linear forward)
     // output
     void* out; int out_f32, out_H, out_W, n_real, out_mul;
     int Jh, Jw;                                    // per-class tiled index space
@@ -428,11 +306,12 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     const int Cc = q.Cs;                            // contraction channels per tap
     const int KC = (Cc % 64 == 0) ? 64 : 32;
     if (Cc % 32 != 0) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: contraction channels must be a multiple of 32");
-    if (q.n_real > 256) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: more than 256 output channels");
+    if (q.n_tile == 0 && q.n_real > 256) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: more than 256 output channels");
     if (((uintptr_t)q.src & 15) || ((uintptr_t)q.w_hwio & 15) || ((uintptr_t)q.out & 15))
         return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: buffers must be 16-byte aligned");
     p.n_real = q.n_real;
-    p.n_pad = ceil_div(q.n_real, 16) * 16;
+    p.n_pad = q.n_tile ? q.n_tile : ceil_div(q.n_real, 16) * 16;
+    p.n_tiles = ceil_div(q.n_real, p.n_pad);
     p.kc_per_tap = Cc / KC;
     p.c_plane = Cc;
     p.Jh = q.Jh; p.Jw = q.Jw; p.Nimg = q.N;
@@ -444,7 +323,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
     p.out_mul = q.out_mul; p.out_H = q.out_H; p.out_W = q.out_W;
     p.act = q.act; p.out_f32 = q.out_f32; p.bias = q.bias; p.out = q.out;
-    p.b_direct = q.g_form ? 1 : 0;
+    p.b_mode = q.b_mode_override >= 0 ? q.b_mode_override : (q.g_form ? 1 : 0);
 
     const int row_bytes = KC * 2;
     // ---- A map: 5-D (C', W', P, H', N)
@@ -461,7 +340,15 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     }
     // ---- B map: 3-D.  G form reads HWIO directly as (co, ci, tap); F form reads the packed copy as (K, n, 1)
     const int taps_total = q.kh * q.kw;
-    if (q.g_form) {
+    if (p.b_mode == 2) {
+        // Matrix[K][N] as stored: N contiguous.  Boxes of 64 columns x KC rows, 128-byte swizzle.
+        if (p.n_pad % 64) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: MN-major B needs N tiles of 64");
+        cuuint64_t dims[3] = {(cuuint64_t)q.w_co, (cuuint64_t)q.w_ci, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)q.w_co * 2, (cuuint64_t)q.w_ci * q.w_co * 2};
+        cuuint32_t box[3] = {64u, (cuuint32_t)KC, 1u};
+        int rc = encode_map(&map_b, q.w_hwio, 3, dims, strides, box, 128);
+        if (rc) return rc;
+    } else if (q.g_form) {
         cuuint64_t dims[3] = {(cuuint64_t)q.w_co, (cuuint64_t)q.w_ci, (cuuint64_t)taps_total};
         cuuint64_t strides[2] = {(cuuint64_t)q.w_co * 2, (cuuint64_t)q.w_ci * q.w_co * 2};
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.n_pad, 1u};
@@ -489,7 +376,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
-    const int total_tiles = p.num_classes * p.tiles_per_class;
+    const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles;
     int grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
     cudaError_t e;
@@ -561,7 +448,6 @@ int build_g(IgemmParams& p, int kh, int kw, int stride, int pt, int pl, int w_co
 // ----------------------------------------------------------------------------------------------
 namespace dmv {
 
-size_t tc_wgrad_workspace(int, int, int, long long) { return 0; }
 
 size_t tc_pack_workspace(int taps, int Cin, int Cout) { return (size_t)taps * Cin * Cout * 2 + 256; }
 
@@ -577,7 +463,7 @@ int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* 
     if (rc) return rc;
     Problem q;
     q.src = x; q.N = B; q.Hs = H; q.Ws = W; q.Cs = Cin; q.src_stride = stride;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = false;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = false; q.n_tile = 0; q.b_mode_override = -1;
     q.out = y; q.out_f32 = (ydt == DMV_DT_F32); q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cout; q.out_mul = 1;
     q.Jh = ph.out; q.Jw = pw.out; q.bias = bias; q.act = act;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -594,7 +480,7 @@ int tc_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, 
     if (rc) return rc;
     Problem q;
     q.src = dy; q.N = B; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cout; q.src_stride = 1;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = true;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = true; q.n_tile = 0; q.b_mode_override = -1;
     q.out = dx; q.out_f32 = 0; q.out_H = H; q.out_W = W; q.n_real = Cin; q.out_mul = stride;
     q.Jh = ceil_div(H, stride); q.Jw = ceil_div(W, stride); q.bias = nullptr; q.act = DMV_ACT_NONE;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -611,7 +497,7 @@ int tc_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hou
     if (rc) return rc;
     Problem q;
     q.src = x; q.N = B; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cin; q.src_stride = 1;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = true;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = true; q.n_tile = 0; q.b_mode_override = -1;
     q.out = y; q.out_f32 = (ydt == DMV_DT_F32); q.out_H = Hout; q.out_W = Wout; q.n_real = Cout; q.out_mul = stride;
     q.Jh = ceil_div(Hout, stride); q.Jw = ceil_div(Wout, stride); q.bias = nullptr; q.act = act;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -629,16 +515,42 @@ int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, in
     if (rc) return rc;
     Problem q;
     q.src = dy; q.N = B; q.Hs = Hout; q.Ws = Wout; q.Cs = Cout; q.src_stride = stride;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = false;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = false; q.n_tile = 0; q.b_mode_override = -1;
     q.out = dx; q.out_f32 = 0; q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cin; q.out_mul = 1;
     q.Jh = ph.out; q.Jw = pw.out; q.bias = nullptr; q.act = DMV_ACT_NONE;
     return launch_igemm(q, p, ws, ws_bytes, st);
 }
 
-static int unsupported(const char* what) { return fail(DMV_E_UNSUPPORTED_SHAPE, what); }
-int tc_conv_wgrad(const void*, int, const void*, float*, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_conv_wgrad: not covered yet"); }
-int tc_deconv_wgrad(const void*, const void*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_deconv_wgrad: not covered yet"); }
-int tc_linear_fwd(const void*, const void*, const float*, void*, int, int, int, int, cudaStream_t) { return unsupported("tc_linear_fwd: not covered yet"); }
-int tc_linear_dgrad(const void*, const void*, void*, int, int, int, cudaStream_t) { return unsupported("tc_linear_dgrad: not covered yet"); }
-int tc_linear_wgrad(const void*, const void*, float*, float*, int, int, int, void*, size_t, cudaStream_t) { return unsupported("tc_linear_wgrad: not covered yet"); }
+
+// linear forward: Y[M,N] = X[M,K] Matrix[K,N] + b.  A = X (K-major rows), B = Matrix as stored (MN-major),
+// N tiles of 64 columns so that the weight stream (the whole cost at M = 64) is spread over >= 64 CTAs.
+int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, cudaStream_t st) {
+    if (K % 32 || N % 8) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_linear_fwd: need K % 32 == 0 and N % 8 == 0");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = build_f(p, 1, 1, 1, 0, 0);
+    if (rc) return rc;
+    Problem q;
+    q.src = x; q.N = M; q.Hs = 1; q.Ws = 1; q.Cs = K; q.src_stride = 1;
+    q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = false; q.n_tile = 64; q.b_mode_override = 2;
+    q.out = y; q.out_f32 = 0; q.out_H = 1; q.out_W = 1; q.n_real = N; q.out_mul = 1;
+    q.Jh = 1; q.Jw = 1; q.bias = bias; q.act = act;
+    return launch_igemm(q, p, nullptr, 0, st);
+}
+
+// linear dgrad: dX[M,K] = dY[M,N] Matrix[K,N]^T.  A = dY rows, B = Matrix rows (contraction over N is contiguous:
+// K-major), output columns = K in tiles of 64.
+int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, cudaStream_t st) {
+    if (N % 32 || K % 8) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_linear_dgrad: need N % 32 == 0 and K % 8 == 0");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = build_g(p, 1, 1, 1, 0, 0, N);
+    if (rc) return rc;
+    Problem q;
+    q.src = dy; q.N = M; q.Hs = 1; q.Ws = 1; q.Cs = N; q.src_stride = 1;
+    q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = true; q.n_tile = 64; q.b_mode_override = -1;
+    q.out = dx; q.out_f32 = 0; q.out_H = 1; q.out_W = 1; q.n_real = K; q.out_mul = 1;
+    q.Jh = 1; q.Jw = 1; q.bias = nullptr; q.act = DMV_ACT_NONE;
+    return launch_igemm(q, p, nullptr, 0, st);
+}
 }  // namespace dmv

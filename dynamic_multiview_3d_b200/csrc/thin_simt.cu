@@ -1,0 +1,151 @@
+// CUDA-core kernels for the two "thin" layers of the graph, whose channel count on the
+// image side (3 for e0, 2 for the flow head) is far below tensor-core and TMA granularity
+// ("treat as bandwidth kernels").
+//
+// thin wgrad:  dW[(tap, ct), cw] = sum_{pixels} Thin[n, oh*st + r - pt, ow*st + s - pl, ct] * Wide[n, oh, ow, cw]
+//   (conv e0: Thin = fp32 image, Wide = dY;  deconv flow head: Thin = fp32 flow gradient, Wide = x)
+// One WARP owns the complete [rows x 32] output in registers: lane = (row group, column
+// group) holds R x 8 accumulators and streams pixels, loading its 8 wide channels with one
+// 16-byte load and its R thin values through L1.  Warps/CTAs take interleaved pixels; CTA
+// partials are summed in CTA order by the shared split-K reduce (deterministic).
+#include "common.cuh"
+#include "conv_impl.h"
+
+namespace {
+using namespace dmv;
+typedef __nv_bfloat16 bf16;
+
+struct ThinGeom {
+    int N, Hb, Wb, Ct, Hs, Ws, kh, kw, st, pt, pl, rows;   // rows = kh*kw*Ct
+};
+
+template <typename TT, int R>
+__global__ void __launch_bounds__(256, 2) thin_wgrad_kernel(const TT* __restrict__ thin, const bf16* __restrict__ wide,
+                                                          float* __restrict__ part, ThinGeom g, long long pixels_per_cta) {
+    __shared__ float red[8][32][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rg = lane >> 2, cg = lane & 3;
+    // per-lane row table: element offset of the tap/channel from the window origin, and (dy+64, dx+64, valid) packed
+    int r_off[R], r_pk[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int row = rg * R + i;
+        const bool ok = row < g.rows;
+        const int tap = ok ? row / g.Ct : 0;
+        const int c = ok ? row - tap * g.Ct : 0;
+        const int dy = tap / g.kw - g.pt, dx = tap % g.kw - g.pl;
+        r_off[i] = (dy * g.Wb + dx) * g.Ct + c;
+        r_pk[i] = (dy + 64) | ((dx + 64) << 8) | (ok ? (1 << 16) : 0);
+    }
+    float acc[R][8];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+
+    const long long total = (long long)g.N * g.Hs * g.Ws;
+    const long long p0 = (long long)blockIdx.x * pixels_per_cta;
+    const long long p1 = min(total, p0 + pixels_per_cta);
+    for (long long p = p0 + warp; p < p1; p += 8) {
+        const int ow = (int)(p % g.Ws);
+        const int oh = (int)((p / g.Ws) % g.Hs);
+        const int n = (int)(p / ((long long)g.Ws * g.Hs));
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wide + p * 32 + cg * 8));
+        float wf[8];
+        {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&wv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 t = __bfloat1622float2(h[k]);
+                wf[2 * k] = t.x;
+                wf[2 * k + 1] = t.y;
+            }
+        }
+        const int by = oh * g.st, bx = ow * g.st;
+        const TT* base = thin + (((long long)n * g.Hb + by) * g.Wb + bx) * g.Ct;
+        const bool interior = (by - g.pt >= 0) && (bx - g.pl >= 0) && (by + g.kh - 1 - g.pt < g.Hb) && (bx + g.kw - 1 - g.pl < g.Wb);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            float tv = 0.f;
+            if (r_pk[i] >> 16) {
+                const int y = by + (r_pk[i] & 255) - 64, x = bx + ((r_pk[i] >> 8) & 255) - 64;
+                if (interior || (y >= 0 && y < g.Hb && x >= 0 && x < g.Wb)) tv = load_as_float(base + r_off[i]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(tv, wf[k], acc[i][k]);
+        }
+    }
+    // fixed-order reduction over the 8 warps, row by row
+    float* out = part + (long long)blockIdx.x * g.rows * 32;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[warp][lane][k] = acc[i][k];
+        __syncthreads();
+        if (warp == 0) {
+            const int row = rg * R + i;
+            if (row < g.rows) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) s += red[w][lane][k];
+                    out[(long long)row * 32 + cg * 8 + k] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void thin_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int parts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int z = 0; z < parts; ++z) s += part[(long long)z * n + i];
+    out[i] = s;
+}
+
+template <typename TT>
+int run_thin(const TT* thin, const bf16* wide, float* dw, const ThinGeom& g, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const long long total = (long long)g.N * g.Hs * g.Ws;
+    int ctas = 148 * 4;
+    if (ctas > (int)ceil_div_ll(total, 64)) ctas = (int)ceil_div_ll(total, 64);
+    if (ctas < 1) ctas = 1;
+    const long long per = ceil_div_ll(total, ctas);
+    ctas = (int)ceil_div_ll(total, per);
+    const size_t need = (size_t)ctas * g.rows * 32 * sizeof(float);
+    if (!ws || ws_bytes < need) return fail(DMV_E_WORKSPACE, "thin wgrad: workspace too small");
+    float* part = reinterpret_cast<float*>(ws);
+    const int R = ceil_div(g.rows, 8);
+    if (R <= 7) thin_wgrad_kernel<TT, 7><<<ctas, 256, 0, st>>>(thin, wide, part, g, per);
+    else if (R <= 10) thin_wgrad_kernel<TT, 10><<<ctas, 256, 0, st>>>(thin, wide, part, g, per);
+    else return fail(DMV_E_UNSUPPORTED_SHAPE, "thin wgrad: too many rows");
+    int rc = check_launch("thin_wgrad");
+    if (rc) return rc;
+    const int n = g.rows * 32;
+    thin_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(part, dw, n, ctas);
+    return check_launch("thin_wgrad reduce");
+}
+}  // namespace
+
+namespace dmv {
+
+size_t thin_wgrad_workspace(int taps, int Ct) { return (size_t)148 * 4 * taps * Ct * 32 * sizeof(float) + 256; }
+
+bool thin_wgrad_eligible(int taps, int Ct, int Cw) { return Cw == 32 && Ct <= 4 && taps * Ct <= 80; }
+
+// thin_dtype: DMV_DT_F32 or DMV_DT_BF16
+int thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride,
+               void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!thin_wgrad_eligible(kh * kw, Ct, 32)) return fail(DMV_E_UNSUPPORTED_SHAPE, "thin wgrad: shape not covered");
+    if ((uintptr_t)wide_bf16 & 15) return fail(DMV_E_UNSUPPORTED_SHAPE, "thin wgrad: wide tensor must be 16-byte aligned");
+    const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
+    ThinGeom g;
+    g.N = N; g.Hb = Hb; g.Wb = Wb; g.Ct = Ct; g.Hs = ph.out; g.Ws = pw.out; g.kh = kh; g.kw = kw; g.st = stride;
+    g.pt = ph.before; g.pl = pw.before; g.rows = kh * kw * Ct;
+    if (thin_dtype == DMV_DT_F32) return run_thin<float>((const float*)thin, (const bf16*)wide_bf16, dw, g, ws, ws_bytes, st);
+    return run_thin<bf16>((const bf16*)thin, (const bf16*)wide_bf16, dw, g, ws, ws_bytes, st);
+}
+
+}  // namespace dmv

@@ -61,7 +61,7 @@ def test_tc_small_vs_oracle(kind, k, s, H, cin, cout, B):
         yo2 = F.conv2d(xt, wv, bv, s, None, "auto")
         n1 = _lib.tc_launch_count()
         yo2.backward(torch.from_numpy(gy).cuda().to(torch.bfloat16))
-        assert _lib.tc_launch_count() == n1 + 1, "dgrad did not take the tensor-core path"
+        assert _lib.tc_launch_count() == n1 + 2, "dgrad / wgrad did not take the tensor-core path"
     else:
         h = -(-H // s)
         x = bf16_round(rng.standard_normal((B, h, h, cin)))
@@ -78,7 +78,7 @@ def test_tc_small_vs_oracle(kind, k, s, H, cin, cout, B):
         n1 = _lib.tc_launch_count()
         yo2.backward(torch.from_numpy(gy).cuda().to(torch.bfloat16))
         if cout % 32 == 0:
-            assert _lib.tc_launch_count() == n1 + 1, "dgrad did not take the tensor-core path"
+            assert _lib.tc_launch_count() == n1 + 2, "dgrad / wgrad did not take the tensor-core path"
     assert _rel(xt.grad.float().cpu().numpy(), gx) < 1e-2
     assert _rel(wv.grad.cpu().numpy(), gw) < 2e-4
 
@@ -100,6 +100,7 @@ def test_tc_full_size_vs_simt(kind, k, s, H, cin, cout):
     B = 8
     g = torch.Generator(device="cuda").manual_seed(k + s + H + cin)
     st = _store()
+    wgs = {}
     if kind == "conv":
         x = torch.randn((B, H, H, cin), device="cuda", generator=g).to(torch.bfloat16)
         wv = _var(st, "w", (np.random.default_rng(1).standard_normal((k, k, cin, cout)) * T.conv_stddev(k, k, cin)).astype(np.float32))
@@ -115,6 +116,7 @@ def test_tc_full_size_vs_simt(kind, k, s, H, cin, cout):
             yb = F.conv2d(xt, wv, bv, s, None, algo)
             yb.backward(gy.to(torch.bfloat16))
             outs[algo], grads[algo] = y.detach(), xt.grad.float()
+            wgs[algo] = wv.grad.clone()
     else:
         h = -(-H // s)
         x = torch.randn((B, h, h, cin), device="cuda", generator=g).to(torch.bfloat16)
@@ -130,7 +132,58 @@ def test_tc_full_size_vs_simt(kind, k, s, H, cin, cout):
             yb = F.deconv2d(xt, wv, (H, H), s, None, algo)
             yb.backward(gy.to(torch.bfloat16))
             outs[algo], grads[algo] = y.detach(), xt.grad.float()
+            wgs[algo] = wv.grad.clone()
+    dw = (wgs["auto"] - wgs["simt"]).abs().max() / wgs["simt"].abs().max()
+    assert float(dw) < 1e-3, float(dw)           # fp32 sums over up to 100k pixels in different orders
     d = (outs["auto"] - outs["simt"]).abs().max() / outs["simt"].abs().max()
     assert float(d) < 1e-4, float(d)
     dg = (grads["auto"] - grads["simt"]).abs().max() / grads["simt"].abs().max()
     assert float(dg) < 1e-2, float(dg)           # bf16 outputs: one rounding apart at most
+
+
+@pytest.mark.parametrize("M,K,N", [(64, 12544, 4096), (64, 4160, 4096), (64, 4096, 12544), (64, 64, 64), (8, 4096, 256), (3, 64, 64)])
+def test_tc_linear_wgrad(M, K, N):
+    from dynamic_multiview_3d_b200 import _lib, functional as F
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    x = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    gy = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16)
+    st = _store()
+    mv = _var(st, "Matrix", np.zeros((K, N), np.float32))
+    bv = _var(st, "b", np.zeros((N,), np.float32))
+    n0 = _lib.tc_launch_count()
+    xt = x.clone().requires_grad_(True)
+    F.linear(xt, mv, bv, None, "auto").backward(gy)
+    assert _lib.tc_launch_count() > n0, "linear wgrad did not take the tensor-core path"
+    ref = x.float().t() @ gy.float()
+    d = (mv.grad - ref).abs().max() / ref.abs().max()
+    assert float(d) < 1e-5, float(d)
+    assert float((bv.grad - gy.float().sum(0)).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("M,K,N", [(64, 12544, 4096), (64, 4160, 4096), (64, 4096, 12544), (64, 64, 64), (8, 4096, 256), (3, 64, 64),
+                                   (130, 96, 72)])
+def test_tc_linear_fwd_dgrad(M, K, N):
+    from dynamic_multiview_3d_b200 import _lib, functional as F
+    rng = np.random.default_rng(M + K + N)
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    x = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    gy = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16)
+    w = (rng.standard_normal((K, N)) * T.linear_stddev(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    st = _store()
+    mv, bv = _var(st, "Matrix", w), _var(st, "b", b)
+    wh = mv.half.float()
+    n0 = _lib.tc_launch_count()
+    xt = x.clone().requires_grad_(True)
+    y = F.linear(xt, mv, bv, "lrelu", "auto")
+    assert _lib.tc_launch_count() == n0 + 1, "linear forward did not take the tensor-core path"
+    pre = x.float() @ wh + torch.from_numpy(b).cuda()
+    ref = 0.6 * pre + 0.4 * pre.abs()
+    assert float((y.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    y2 = F.linear(xt, mv, bv, None, "auto")
+    n1 = _lib.tc_launch_count()
+    y2.backward(gy)
+    if N % 32 == 0 and K % 32 == 0:
+        assert _lib.tc_launch_count() >= n1 + 2, "linear dgrad / wgrad did not take the tensor-core path"
+    gref = gy.float() @ wh.t()
+    assert float((xt.grad.float() - gref).abs().max() / gref.abs().max()) < 1e-2
