@@ -371,13 +371,16 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     }
     // ---- shared memory / grid
     const int stage_bytes = 128 * row_bytes + p.n_pad * row_bytes;
-    int stages = (160 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
+    // The pipeline is latency-bound (one TMA box per tap): keep as many bytes in flight per SM as
+    // possible.  Narrow layers (N <= 64) run two CTAs per SM, each with half of the shared memory.
+    const bool two_per_sm = p.n_pad <= 64;
+    int stages = ((two_per_sm ? 106 : 200) * 1024) / stage_bytes;
+    if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
     const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles;
-    int grid = num_sms();
+    int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > total_tiles) grid = total_tiles;
     cudaError_t e;
     if (KC == 64) {
