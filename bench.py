@@ -44,40 +44,69 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 10 ms (nvidia-smi fallback)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.stop_flag, self.smax = index, [], set(), False, None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
 
     def run(self):
         while not self.stop_flag:
+            self.sample()
+            time.sleep(0.01 if self.nv else 0.2)
+
+    def sample(self):
+        if self.nv:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.2)
+            return
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            f = [x.strip() for x in out.split(",")]
+            self.sm.append(float(f[0]))
+            self.smax = float(f[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def summary(self):
         self.stop_flag = True
-
-        def num(s):
-            try:
-                return float(s)
-            except ValueError:
-                return None
-        sm = sorted(x for x in (num(r[0]) for r in self.rows if r) if x is not None)
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        smax = num(self.rows[0][1]) if self.rows else None
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def reference_arm(args, rank):
@@ -265,9 +294,10 @@ def main():
     e2e = world * BATCH / (ms_e2e * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        # the remaining work (per-kernel profile, microbenchmarks, CPU baseline) is rank 0's alone.  Wait for it on
+        # the rendezvous store -- not on an NCCL barrier -- and leave without tearing the communicator down: a
+        # process group whose collectives were captured into a live CUDA graph can block in destroy_process_group.
+        finish(world, rank)
         return 0
 
     # ---------------- per-kernel profile of one eager step -> dominant kernel + roofline
@@ -332,11 +362,28 @@ def main():
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sampler": micro, "top_kernels": top,
             "step_tflops_per_gpu": round(step_tflops, 2), "final_loss": last}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish(world, rank)
     return 0
 
 
+def finish(world, rank):
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch.distributed as dist
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("dmv_bench_done", "1")
+            else:
+                store.wait(["dmv_bench_done"])
+        except Exception:
+            pass
+        os._exit(0)
+
+
 if __name__ == "__main__":
+    import signal
+    signal.signal(signal.SIGALRM, lambda *a: os._exit(3))    # never sit on a GPU box: hard stop after 20 minutes
+    signal.alarm(1200)
     sys.exit(main())

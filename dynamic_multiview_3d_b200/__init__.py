@@ -7,6 +7,7 @@ Host-side mirror of the reference's operator and model interfaces for the path
 from . import _lib, functional, tf_utils  # noqa: F401
 from .appearance_flow_model import (AppearanceFlowModel, AppearanceFlowTinghui, AppFlowHighDimAngle,  # noqa: F401
                                     AppFlowLowDimAngle)
+from .main_model import Base_Prediction_Model  # noqa: F401
 from .optimizer import TFAdam  # noqa: F401
 from .variables import VariableStore, use_store  # noqa: F401
 

@@ -31,10 +31,10 @@ SIGNATURES = {
     "dmv_loss_workspace_size": (_sz, [_ll]),
     "dmv_loss_fused_fwd_bwd": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_f), _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _vp, _sz, _vp]),
     "dmv_scale_by_device_scalar": (_i, [_vp, _vp, _ll, _vp]),
-    "dmv_conv_workspace_size": (_sz, [_i, _i, _i]),
+    "dmv_conv_workspace_size": (_sz, [_i] * 8),
     "dmv_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
     "dmv_conv2d_dgrad": (_i, [_vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
-    "dmv_wgrad_workspace_size": (_sz, [_i, _i, _i, _ll]),
+    "dmv_wgrad_workspace_size": (_sz, [_i] * 8),
     "dmv_conv2d_wgrad": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_deconv2d_fwd": (_i, [_vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
     "dmv_deconv2d_dgrad": (_i, [_vp, _i, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),

@@ -11,18 +11,36 @@ using namespace dmv;
 
 extern "C" {
 
-size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels) {
-    if (taps <= 0 || Cin <= 0 || Cout <= 0 || pixels <= 0) return 0;
-    size_t a = simt_wgrad_workspace(taps, Cin, Cout, pixels);
-    size_t b = tc_wgrad_workspace(taps, Cin, Cout, pixels);
-    size_t c = thin_wgrad_eligible(taps, Cin, Cout) ? thin_wgrad_workspace(taps, Cin) : 0;
+// layers with fewer than 8 channels on the image side (e0: 3, flow head: 2) go through a patch matrix
+static bool thin_side(int c) { return c < 8; }
+
+size_t dmv_wgrad_workspace_size(int B, int H, int W, int Cbig, int Csmall, int kh, int kw, int stride) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cbig <= 0 || Csmall <= 0 || kh <= 0 || kw <= 0 || stride <= 0) return 0;
+    const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+    const long long pixels = (long long)B * ph.out * pw.out;
+    const int taps = kh * kw;
+    size_t a = simt_wgrad_workspace(taps, Cbig, Csmall, pixels);
+    size_t b = tc_wgrad_workspace(taps, Cbig, Csmall, pixels);
     if (b > a) a = b;
-    return c > a ? c : a;
+    if (thin_side(Cbig)) {
+        size_t c = tc_thin_workspace(B, H, W, Cbig, Csmall, kh, kw, stride);
+        if (c > a) a = c;
+        if (thin_wgrad_eligible(taps, Cbig, Csmall)) {
+            c = thin_wgrad_workspace(taps, Cbig);
+            if (c > a) a = c;
+        }
+    }
+    return a + 256;
 }
 
-size_t dmv_conv_workspace_size(int taps, int Cin, int Cout) {
-    if (taps <= 0 || Cin <= 0 || Cout <= 0) return 0;
-    return tc_pack_workspace(taps, Cin, Cout);
+size_t dmv_conv_workspace_size(int B, int H, int W, int Cbig, int Csmall, int kh, int kw, int stride) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cbig <= 0 || Csmall <= 0 || kh <= 0 || kw <= 0 || stride <= 0) return 0;
+    size_t a = tc_pack_workspace(kh * kw, Cbig, Csmall);
+    if (thin_side(Cbig)) {
+        size_t c = tc_thin_workspace(B, H, W, Cbig, Csmall, kh, kw, stride);
+        if (c > a) a = c;
+    }
+    return a + 256;
 }
 
 int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype, int B, int H, int W,
@@ -31,6 +49,10 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias,
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "conv2d_fwd: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT && thin_side(Cin)) {
+        int rc = tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
+    }
     if (algo != DMV_ALGO_SIMT) {
         int rc = tc_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
@@ -55,14 +77,19 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, floa
     DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "conv2d_wgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo == DMV_ALGO_AUTO && thin_wgrad_eligible(kh * kw, Cin, Cout)) {   // e0: 3-channel image side
-        int rc = thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+    if (algo != DMV_ALGO_SIMT && thin_side(Cin)) {   // e0: 3-channel image side
+        int rc = tc_thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc == DMV_E_UNSUPPORTED_SHAPE || rc == DMV_E_WORKSPACE) {
+            if (!thin_wgrad_eligible(kh * kw, Cin, Cout)) goto generic;
+            rc = thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+        }
         if (rc == DMV_OK && db) {
             const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
             rc = simt_bias_grad(dy, db, (long long)B * ph.out * pw.out, Cout, workspace, workspace_bytes, st);
         }
         return rc;
     }
+generic:
     if (algo != DMV_ALGO_SIMT) {
         int rc = tc_conv_wgrad(x, x_dtype, dy, dw, nullptr, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc == DMV_OK && db) {
@@ -91,6 +118,11 @@ int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, in
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "deconv2d_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {   // flow head: dx = conv of the 2-channel gradient with w[r,s,c,ci]
+        int rc = tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
+                             workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
+    }
     if (algo != DMV_ALGO_SIMT) {
         int rc = tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
@@ -103,8 +135,12 @@ int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, i
     DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "deconv2d_wgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo == DMV_ALGO_AUTO && thin_wgrad_eligible(kh * kw, Cout, Cin))      // flow head: 2-channel output side
-        return thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+    if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {      // flow head: 2-channel output side
+        int rc = tc_thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
+        if (thin_wgrad_eligible(kh * kw, Cout, Cin))
+            return thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+    }
     if (algo != DMV_ALGO_SIMT) {
         int rc = tc_deconv_wgrad(x, dy, dy_dtype, dw, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;

@@ -22,6 +22,16 @@ int simt_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B,
                       int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t thin_wgrad_workspace(int taps, int Ct);
+int thin_patch_cols(int taps, int Ct);
+int thin_im2col(const void* thin, int thin_dtype, void* P, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride, cudaStream_t st);
+int thin_pack_weights(const void* w_bf16, void* packed, int rows, int Cw, int Kp, cudaStream_t st);
+int copy_f32(const float* src, float* dst, int n, cudaStream_t st);
+// thin-channel layers on tensor cores through an explicit patch matrix (conv_tc.cu / wgrad_tc.cu)
+size_t tc_thin_workspace(int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw, int stride);
+int tc_thin_fwd(const void* thin, int thin_dtype, const void* w_bf16, const float* bias, void* out, int out_dtype, int N, int Hb, int Wb,
+                int Ct, int Cw, int kh, int kw, int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw,
+                  int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 bool thin_wgrad_eligible(int taps, int Ct, int Cw);
 int thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride,
                void* ws, size_t ws_bytes, cudaStream_t st);

@@ -19,6 +19,8 @@
 // bf16 x bf16 -> fp32) accumulates into double-buffered TMEM, and four epilogue warps read
 // TMEM with tcgen05.ld, fuse bias + activation, and store NHWC rows.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "conv_impl.h"
 
@@ -51,6 +53,7 @@ struct IgemmParams {
     int b_mode;                   // 0: packed K-major [n][K]; 1: reference HWIO read as (co, ci, tap), K-major;
                                   // 2: MN-major [K][n] (linear forward: Matrix[K,N] as stored)
     int stages;
+    int halo_pitch, halo_h, min_dh, min_dw;   // halo kernel: window rows x pitch pixels, origin offset of the window
     TapClass cls[4];
     Tap taps[kMaxTaps];
     const float* bias;
@@ -251,6 +254,182 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Halo variant for stride-1 layers whose weights fit in shared memory next to the input windows
+// (the four largest layers of the graph and their dgrads).  Instead of one TMA box per tap, the CTA
+// loads the (16 + kh - 1) x (8 + kw - 1) input window of an 8 x 16 output tile ONCE; the A operand of
+// tap (r, s) is the same shared-memory tile addressed through a descriptor that starts (r * pitch + s)
+// pixel rows further and strides one window row per 8-row core group.  This works because the
+// shared-memory swizzle is a pure function of the address (established with tools/probe), and it cuts
+// the L2 -> SM traffic of a 5x5 layer by ~13x.  All kh*kw weight tiles are loaded once per CTA.
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_b,
+                                                            const __grid_constant__ IgemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int kRowBytes = KC * 2;
+    const TapClass& c = p.cls[0];
+    const int ntaps = c.tap_count;
+    const int wtile_bytes = p.n_pad * kRowBytes;
+    const int a_bytes = p.halo_h * p.halo_pitch * kRowBytes;
+    const int a_stage = (a_bytes + 1023) & ~1023;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + (size_t)ntaps * wtile_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_a + (size_t)p.stages * a_stage);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tfull_bar = empty_bar + p.stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * p.n_pad)) tmem_cols <<= 1;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_tiles = p.tiles_per_class;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)(ntaps * wtile_bytes));
+            for (int j = 0; j < ntaps; ++j) {
+                if (p.b_mode == 1) tma_load_3d(s_w + (size_t)j * wtile_bytes, &map_b, w_bar, 0, 0, p.taps[c.tap_begin + j].id);
+                else tma_load_3d(s_w + (size_t)j * wtile_bytes, &map_b, w_bar, c.k_elem_offset + j * KC, 0, 0);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
+                tma_load_5d(s_a + (size_t)stage * a_stage, &map_a, &full_bar[stage], 0, tw * 8 + p.min_dw, 0, th * 16 + p.min_dh, t);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            // descriptor template for A: SBO = one window row (pitch pixels)
+            uint64_t a_tmpl = 0;
+            a_tmpl |= (uint64_t)1 << 16;
+            a_tmpl |= (uint64_t)((uint32_t)(p.halo_pitch * kRowBytes) >> 4) << 32;
+            a_tmpl |= (uint64_t)1 << 46;
+            a_tmpl |= (uint64_t)(kRowBytes == 128 ? 2 : 4) << 61;
+            mbar_wait(w_bar, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t w_addr = smem_u32(s_w);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_pad);
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s_a + (size_t)stage * a_stage);
+                for (int j = 0; j < ntaps; ++j) {
+                    const Tap& tp = p.taps[c.tap_begin + j];
+                    const uint32_t off = (uint32_t)(((tp.dh - p.min_dh) * p.halo_pitch + (tp.dw - p.min_dw)) * kRowBytes);
+                    const uint64_t adesc = a_tmpl | (uint64_t)(((a_addr + off) & 0x3FFFF) >> 4);
+                    const uint64_t bdesc = make_kmajor_desc(w_addr + (uint32_t)(j * wtile_bytes), kRowBytes);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | k) ? 1u : 0u);
+                }
+                tc_commit(&empty_bar[stage]);
+                tc_commit(&tfull_bar[acc]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const int bh = m >> 3, bw = m & 7;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; t /= p.tiles_h;
+            const int n = t, oy = th * 16 + bh, ox = tw * 8 + bw;
+            const bool ok = (oy < p.out_H) && (ox < p.out_W);
+            const long long opix = ((long long)n * p.out_H + oy) * p.out_W + ox;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
+            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (ok) {
+                    float f[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        float x = __uint_as_float(v[k]);
+                        if (p.bias && c0 + k < p.n_real) x += __ldg(p.bias + c0 + k);
+                        f[k] = apply_act(x, p.act);
+                    }
+                    if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out) + opix * p.n_real + c0;
+                        for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = f[k];
+                    } else {
+                        bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + c0;
+                        if (c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
+                            uint4 q0, q1;
+                            __nv_bfloat162 h;
+                            h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[2], f[3]); q0.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[4], f[5]); q0.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[6], f[7]); q0.w = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[8], f[9]); q1.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[10], f[11]); q1.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[12], f[13]); q1.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(f[14], f[15]); q1.w = *reinterpret_cast<uint32_t*>(&h);
+                            reinterpret_cast<uint4*>(o)[0] = q0;
+                            reinterpret_cast<uint4*>(o)[1] = q1;
+                        } else {
+                            for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // F-form weight packing: w[t][ci][co] (bf16) -> packed[co][t*Cin + ci]
 __global__ void pack_f_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int taps, int Cin, int Cout) {
     const long long n = (long long)taps * Cin * Cout;
@@ -323,9 +502,40 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
     p.out_mul = q.out_mul; p.out_H = q.out_H; p.out_W = q.out_W;
     p.act = q.act; p.out_f32 = q.out_f32; p.bias = q.bias; p.out = q.out;
-    p.b_mode = q.b_mode_override >= 0 ? q.b_mode_override : (q.g_form ? 1 : 0);
+    const bool prepacked = q.b_mode_override == 3;      // w_hwio already holds the packed [n][K] K-major matrix
+    p.b_mode = prepacked ? 0 : (q.b_mode_override >= 0 ? q.b_mode_override : (q.g_form ? 1 : 0));
 
     const int row_bytes = KC * 2;
+    // ---- halo eligibility: stride-1 source, one channel chunk, one tap class, one N tile, weights resident
+    bool halo_ok = false;
+    int halo_stages = 0;
+    size_t halo_smem = 0;
+    if (q.src_stride == 1 && p.num_classes == 1 && p.kc_per_tap == 1 && p.n_tiles == 1 && p.b_mode != 2 && q.out_mul == 1 &&
+        q.Jh * q.Jw >= 256 && !getenv("DMV_NO_HALO")) {
+        int dh0 = 1 << 20, dh1 = -(1 << 20), dw0 = 1 << 20, dw1 = -(1 << 20);
+        for (int j = 0; j < p.cls[0].tap_count; ++j) {
+            const Tap& t = p.taps[p.cls[0].tap_begin + j];
+            dh0 = t.dh < dh0 ? t.dh : dh0; dh1 = t.dh > dh1 ? t.dh : dh1;
+            dw0 = t.dw < dw0 ? t.dw : dw0; dw1 = t.dw > dw1 ? t.dw : dw1;
+        }
+        p.min_dh = dh0; p.min_dw = dw0;
+        p.halo_h = 16 + (dh1 - dh0);
+        p.halo_pitch = 8 + (dw1 - dw0);
+        const size_t wbytes = (size_t)p.cls[0].tap_count * p.n_pad * row_bytes;
+        const size_t a_stage = ((size_t)p.halo_h * p.halo_pitch * row_bytes + 1023) & ~(size_t)1023;
+        if (p.halo_pitch <= 256 && p.halo_h <= 256 && wbytes + 2 * a_stage <= 200 * 1024) {
+            halo_stages = (int)((200 * 1024 - wbytes) / a_stage);
+            if (halo_stages > 6) halo_stages = 6;
+            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8) * sizeof(uint64_t) + 16 + 1024;
+            halo_ok = true;
+            // the halo kernel tiles the image 8 wide x 16 tall, one image per tile
+            p.BW = 8; p.BH = 16; p.NB = 1; p.rows = 128;
+            p.tiles_w = ceil_div(q.Jw, 8);
+            p.tiles_h = ceil_div(q.Jh, 16);
+            p.groups = q.N;
+            p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
+        }
+    }
     // ---- A map: 5-D (C', W', P, H', N)
     CUtensorMap map_a, map_b;
     {
@@ -354,6 +564,13 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.n_pad, 1u};
         int rc = encode_map(&map_b, q.w_hwio, 3, dims, strides, box, row_bytes);
         if (rc) return rc;
+    } else if (prepacked) {
+        const cuuint64_t ktot = (cuuint64_t)q.w_ci;
+        cuuint64_t dims[3] = {ktot, (cuuint64_t)q.w_co, 1};
+        cuuint64_t strides[2] = {ktot * 2, ktot * 2 * (cuuint64_t)q.w_co};
+        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.n_pad, 1u};
+        int rc = encode_map(&map_b, q.w_hwio, 3, dims, strides, box, row_bytes);
+        if (rc) return rc;
     } else {
         const size_t need = (size_t)taps_total * q.w_ci * q.w_co * 2;
         if (!workspace || ws_bytes < need) return fail(DMV_E_WORKSPACE, "tc: workspace too small for packed weights");
@@ -368,6 +585,33 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.n_pad, 1u};
         rc = encode_map(&map_b, workspace, 3, dims, strides, box, row_bytes);
         if (rc) return rc;
+    }
+    // ---- halo variant (see halo_kernel)
+    if (halo_ok) {
+        CUtensorMap map_h;
+        cuuint64_t dims[5] = {(cuuint64_t)q.Cs, (cuuint64_t)q.Ws, 1, (cuuint64_t)q.Hs, (cuuint64_t)q.N};
+        const cuuint64_t pix = (cuuint64_t)q.Cs * 2;
+        cuuint64_t strides[4] = {pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Hs * q.Ws * pix};
+        cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)p.halo_pitch, 1u, (cuuint32_t)p.halo_h, 1u};
+        int rc = encode_map(&map_h, q.src, 5, dims, strides, box, row_bytes);
+        if (rc) return rc;
+        p.stages = halo_stages;
+        int grid = num_sms();
+        if (grid > p.tiles_per_class) grid = p.tiles_per_class;
+        cudaError_t e;
+        if (KC == 64) {
+            e = cudaFuncSetAttribute(halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem);
+            if (e == cudaSuccess) halo_kernel<64><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);
+        } else {
+            e = cudaFuncSetAttribute(halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem);
+            if (e == cudaSuccess) halo_kernel<32><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);
+        }
+        if (e != cudaSuccess) {
+            set_error("tc halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return DMV_E_CUDA;
+        }
+        count_tc_launch();
+        return check_launch("halo_tc");
     }
     // ---- shared memory / grid
     const int stage_bytes = 128 * row_bytes + p.n_pad * row_bytes;
@@ -556,4 +800,45 @@ int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N
     q.Jh = 1; q.Jw = 1; q.bias = nullptr; q.act = DMV_ACT_NONE;
     return launch_igemm(q, p, nullptr, 0, st);
 }
+
+// ---- thin-channel layers (3-channel image side of e0, 2-channel side of the flow head) -------------------
+// The patch matrix P[pixel][Kp] (bf16, k = (tap, ct), zero padded to a multiple of 32) is written once by a gather
+// kernel; the layer is then a 1x1 convolution over P on the tensor cores.
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t tc_thin_workspace(int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw, int stride) {
+    const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
+    const int Kp = thin_patch_cols(kh * kw, Ct);
+    const size_t P = align256((size_t)N * ph.out * pw.out * Kp * 2);
+    const size_t packed = align256((size_t)Cw * Kp * 2);
+    const size_t dwt = align256((size_t)Kp * Cw * 4);
+    const size_t parts = tc_wgrad_workspace(1, Kp, Cw, (long long)N * ph.out * pw.out);
+    return P + packed + dwt + parts + 1024;
+}
+
+int tc_thin_fwd(const void* thin, int thin_dtype, const void* w, const float* bias, void* out, int out_dtype, int N, int Hb, int Wb, int Ct,
+                int Cw, int kh, int kw, int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (Cw % 8 || Cw > 256) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_thin_fwd: output channels");
+    const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
+    const int rows = kh * kw * Ct, Kp = thin_patch_cols(kh * kw, Ct);
+    const size_t Pb = align256((size_t)N * ph.out * pw.out * Kp * 2), Wb_ = align256((size_t)Cw * Kp * 2);
+    if (!ws || ws_bytes < Pb + Wb_ || ((uintptr_t)ws & 255)) return fail(DMV_E_WORKSPACE, "tc_thin_fwd: workspace too small or unaligned");
+    uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+    int rc = thin_im2col(thin, thin_dtype, base, N, Hb, Wb, Ct, kh, kw, stride, st);
+    if (rc) return rc;
+    rc = thin_pack_weights(w, base + Pb, rows, Cw, Kp, st);
+    if (rc) return rc;
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    rc = build_f(p, 1, 1, 1, 0, 0);
+    if (rc) return rc;
+    Problem q;
+    q.src = base; q.N = N; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Kp; q.src_stride = 1;
+    q.w_hwio = base + Pb; q.kh = 1; q.kw = 1; q.w_ci = Kp; q.w_co = Cw; q.g_form = false; q.n_tile = 0; q.b_mode_override = 3;
+    q.out = out; q.out_f32 = (out_dtype == DMV_DT_F32); q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cw; q.out_mul = 1;
+    q.Jh = ph.out; q.Jw = pw.out; q.bias = bias; q.act = act;
+    return launch_igemm(q, p, nullptr, 0, st);
+}
+
 }  // namespace dmv
+

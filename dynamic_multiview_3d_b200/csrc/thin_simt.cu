@@ -106,6 +106,55 @@ __global__ void thin_reduce_kernel(const float* __restrict__ part, float* __rest
     out[i] = s;
 }
 
+// Patch matrix of a thin tensor: P[pixel][k], k = (tap, ct) in reference weight order, zero padded to Kp columns.
+// One thread writes 8 consecutive bf16 (16 bytes).
+template <typename TT>
+__global__ void thin_im2col_kernel(const TT* __restrict__ thin, bf16* __restrict__ P, ThinGeom g, int Kp) {
+    const int groups = Kp / 8;
+    const long long total = (long long)g.N * g.Hs * g.Ws * groups;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int gq = (int)(i % groups);
+        const long long p = i / groups;
+        const int ow = (int)(p % g.Ws);
+        const int oh = (int)((p / g.Ws) % g.Hs);
+        const int n = (int)(p / ((long long)g.Ws * g.Hs));
+        const int by = oh * g.st - g.pt, bx = ow * g.st - g.pl;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int row = gq * 8 + k;
+            v[k] = 0.f;
+            if (row < g.rows) {
+                const int tap = row / g.Ct, c = row - tap * g.Ct;
+                const int y = by + tap / g.kw, x = bx + tap % g.kw;
+                if (y >= 0 && y < g.Hb && x >= 0 && x < g.Wb) v[k] = load_as_float(thin + (((long long)n * g.Hb + y) * g.Wb + x) * g.Ct + c);
+            }
+        }
+        uint4 q;
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(v[0], v[1]); q.x = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(v[2], v[3]); q.y = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(v[4], v[5]); q.z = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(v[6], v[7]); q.w = *reinterpret_cast<uint32_t*>(&h);
+        *reinterpret_cast<uint4*>(P + p * Kp + gq * 8) = q;
+    }
+}
+
+// weights w[rows][Cw] (reference order) -> packed[Cw][Kp] K-major, zero padded
+__global__ void thin_pack_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int rows, int Cw, int Kp) {
+    const int n = Cw * Kp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int k = i % Kp, co = i / Kp;
+        out[i] = k < rows ? w[(long long)k * Cw + co] : __float2bfloat16_rn(0.f);
+    }
+}
+
+__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
 template <typename TT>
 int run_thin(const TT* thin, const bf16* wide, float* dw, const ThinGeom& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     const long long total = (long long)g.N * g.Hs * g.Ws;
@@ -130,6 +179,31 @@ int run_thin(const TT* thin, const bf16* wide, float* dw, const ThinGeom& g, voi
 }  // namespace
 
 namespace dmv {
+
+int thin_patch_cols(int taps, int Ct) { return ceil_div(taps * Ct, 32) * 32; }
+
+int thin_im2col(const void* thin, int thin_dtype, void* P, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride, cudaStream_t st) {
+    const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
+    ThinGeom g;
+    g.N = N; g.Hb = Hb; g.Wb = Wb; g.Ct = Ct; g.Hs = ph.out; g.Ws = pw.out; g.kh = kh; g.kw = kw; g.st = stride;
+    g.pt = ph.before; g.pl = pw.before; g.rows = kh * kw * Ct;
+    const int Kp = thin_patch_cols(kh * kw, Ct);
+    long long blocks = ceil_div_ll((long long)N * g.Hs * g.Ws * (Kp / 8), 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (thin_dtype == DMV_DT_F32) thin_im2col_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)thin, (bf16*)P, g, Kp);
+    else thin_im2col_kernel<bf16><<<(int)blocks, 256, 0, st>>>((const bf16*)thin, (bf16*)P, g, Kp);
+    return check_launch("thin_im2col");
+}
+
+int thin_pack_weights(const void* w_bf16, void* packed, int rows, int Cw, int Kp, cudaStream_t st) {
+    thin_pack_kernel<<<ceil_div(Cw * Kp, 256), 256, 0, st>>>((const bf16*)w_bf16, (bf16*)packed, rows, Cw, Kp);
+    return check_launch("thin_pack");
+}
+
+int copy_f32(const float* src, float* dst, int n, cudaStream_t st) {
+    copy_rows_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, dst, n);
+    return check_launch("copy_f32");
+}
 
 size_t thin_wgrad_workspace(int taps, int Ct) { return (size_t)148 * 4 * taps * Ct * 32 * sizeof(float) + 256; }
 

@@ -377,4 +377,28 @@ int tc_linear_wgrad(const void* x, const void* dy, float* dw, float* db, int M, 
     return run_wgrad(q, ws, ws_bytes, st);
 }
 
+
+int tc_thin_wgrad(const void* thin, int thin_dtype, const void* wide, float* dw, int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw,
+                  int stride, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
+    const int rows = kh * kw * Ct, Kp = thin_patch_cols(kh * kw, Ct);
+    if (!wgrad_eligible(Kp, Cw, 1)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_thin_wgrad: channel counts not covered");
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t Pb = al((size_t)N * ph.out * pw.out * Kp * 2), Db = al((size_t)Kp * Cw * 4);
+    const size_t parts = tc_wgrad_workspace(1, Kp, Cw, (long long)N * ph.out * pw.out);
+    if (!ws || ws_bytes < Pb + Db + parts || ((uintptr_t)ws & 255)) return fail(DMV_E_WORKSPACE, "tc_thin_wgrad: workspace too small or unaligned");
+    uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+    int rc = thin_im2col(thin, thin_dtype, base, N, Hb, Wb, Ct, kh, kw, stride, st);
+    if (rc) return rc;
+    float* dwt = reinterpret_cast<float*>(base + Pb);
+    WProblem q;
+    q.big = base; q.N = N; q.Hb = ph.out; q.Wb = pw.out; q.Cb = Kp; q.stride = 1;
+    q.small = wide; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cw;
+    q.kh = 1; q.kw = 1; q.pt = 0; q.pl = 0; q.dw = dwt;
+    rc = run_wgrad(q, base + Pb + Db, ws_bytes - Pb - Db, st);
+    if (rc) return rc;
+    return copy_f32(dwt, dw, rows * Cw, st);      // drop the zero-padded rows
+}
+
 }  // namespace dmv
+

@@ -139,7 +139,7 @@ class _Conv2d(torch.autograd.Function):
         assert wcin == Cin, (wvar.name, wvar.shape, x.shape)
         y = torch.empty((B, same_out(H, stride), same_out(W, stride), Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
-        ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+        ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), x.device)
         call("dmv_conv2d_fwd", _p(x), _dt(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
              B, H, W, Cin, Cout, kh, kw, stride, ACT[act], _p(ws), ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
@@ -167,14 +167,14 @@ class _Conv2d(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+            ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), x.device)
             call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
             if x.dtype != torch.bfloat16:
                 dxf = torch.empty(x.shape, dtype=x.dtype, device=x.device)
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
                 dx = dxf
         pixels = B * y.shape[1] * y.shape[2]
-        nws = _lib.load().dmv_wgrad_workspace_size(kh * kw, Cin, Cout, pixels)
+        nws = _lib.load().dmv_wgrad_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
         ws = workspace(nws, x.device)
         call("dmv_conv2d_wgrad", _p(x), _dt(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if bvar is not None else None,
              B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
@@ -199,7 +199,7 @@ class _Deconv2d(torch.autograd.Function):
         assert same_out(Ho, stride) == Hin and same_out(Wo, stride) == Win, "output_shape inconsistent with input"
         y = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
-        ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+        ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
         call("dmv_deconv2d_fwd", _p(x), _p(wvar.half), _p(y), _dt(y), B, Ho, Wo, Cin, Cout, kh, kw, stride, ACT[act], _p(ws),
              ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
@@ -223,11 +223,11 @@ class _Deconv2d(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            ws = workspace(_lib.load().dmv_conv_workspace_size(kh * kw, Cin, Cout), x.device)
+            ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
             call("dmv_deconv2d_dgrad", _p(dpre), _dt(dpre), _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
                  ws.numel(), algo, st)
         pixels = B * x.shape[1] * x.shape[2]
-        nws = _lib.load().dmv_wgrad_workspace_size(kh * kw, Cout, Cin, pixels)
+        nws = _lib.load().dmv_wgrad_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
         ws = workspace(nws, x.device)
         call("dmv_deconv2d_wgrad", _p(x), _p(dpre), _dt(dpre), _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
              ws.numel(), algo, st)
@@ -271,7 +271,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx = torch.empty_like(x)
             call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, algo, st)
-        nws = _lib.load().dmv_wgrad_workspace_size(1, K, N, M)
+        nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
         ws = workspace(nws, x.device)
         call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if bvar is not None else None, M, K, N,
              _p(ws), ws.numel(), algo, st)

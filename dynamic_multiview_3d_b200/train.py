@@ -118,7 +118,8 @@ def main(argv=None):
         conf["num_iterations"] = args.num_iterations
     from .appearance_flow_model import AppearanceFlowModel
     from .synthetic import make_batch
-    Model = conf.get("model", AppearanceFlowModel)
+    from .main_model import Base_Prediction_Model
+    Model = conf.get("model", Base_Prediction_Model if ("use_color" in conf or "use_depth" in conf) else AppearanceFlowModel)
     model = Model(conf, load_tfrec=True, build_loss=not args.visualize)
     out_dir = conf.get("output_dir", ".")
     os.makedirs(out_dir, exist_ok=True)

@@ -125,9 +125,15 @@ int dmv_scale_by_device_scalar(float* x, const float* scalar, long long n, void*
  * `act` is fused into the forward epilogue; backward entry points take the gradient wrt
  * the PRE-activation (dmv_act_bwd produces it from the post-activation output).          */
 
-/* Forward / dgrad scratch (the tensor-core path repacks the layer's weights into it):
- * dmv_conv_workspace_size(kh*kw, Cin, Cout) bytes; may be NULL with DMV_ALGO_SIMT.        */
-size_t dmv_conv_workspace_size(int taps, int Cin, int Cout);
+/* Scratch sizes.  Geometry is always that of the SAME conv the layer is (or is the gradient
+ * of): BIG side [B,H,W,Cbig] (conv input / deconv output), small side ceil(H/stride) with
+ * Csmall channels (conv output / deconv input).
+ *   dmv_conv_workspace_size : forward and dgrad entry points (weight repacking; the patch
+ *                             matrix of layers with < 8 big-side channels); NULL allowed
+ *                             with DMV_ALGO_SIMT
+ *   dmv_wgrad_workspace_size: wgrad entry points (deterministic split-K partials)
+ * For linear layers use B = M, H = W = 1, kh = kw = stride = 1, Cbig = K, Csmall = N.      */
+size_t dmv_conv_workspace_size(int B, int H, int W, int Cbig, int Csmall, int kh, int kw, int stride);
 /* replaces tf.nn.conv2d(...,'SAME') + b  -- conv2d_msra, tf_utils.py:70-84 */
 int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w_bf16, const float* bias, void* y,
                    int y_dtype, int B, int H, int W, int Cin, int Cout, int kh, int kw,
@@ -139,7 +145,7 @@ int dmv_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int
                      size_t workspace_bytes, int algo, void* stream);
 /* replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 [kh,kw,Cin,Cout], db f32 [Cout] or NULL.
  * Deterministic split-K (fixed-order second pass).  workspace: dmv_wgrad_workspace_size.   */
-size_t dmv_wgrad_workspace_size(int taps, int Cin, int Cout, long long pixels);
+size_t dmv_wgrad_workspace_size(int B, int H, int W, int Cbig, int Csmall, int kh, int kw, int stride);
 int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy_bf16, float* dw, float* db, int B,
                      int H, int W, int Cin, int Cout, int kh, int kw, int stride,
                      void* workspace, size_t workspace_bytes, int algo, void* stream);

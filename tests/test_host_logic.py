@@ -43,7 +43,8 @@ def test_error_reporting_without_gpu():
     with pytest.raises(_lib.DmvError):
         _lib.check(rc, "dmv_sampler_fwd")
     assert lib.dmv_sampler_bwd_workspace_size(64, 224, 224, 3, 224, 224) == 64 * 49 * 16
-    assert lib.dmv_wgrad_workspace_size(25, 32, 32, 802816) > 0
+    assert lib.dmv_wgrad_workspace_size(64, 112, 112, 32, 32, 5, 5, 1) > 0
+    assert lib.dmv_conv_workspace_size(64, 224, 224, 3, 32, 5, 5, 2) >= 64 * 112 * 112 * 96 * 2
 
 
 def test_cpu_tensors_are_rejected():
@@ -70,6 +71,22 @@ def test_variable_tables_match_reference_graph(cls, kind, H):
     offs = [(v.offset, v.numel) for v in m.store.vars.values()]
     assert all(o % 64 == 0 for o, _ in offs)
     assert all(o2 >= o1 + n1 for (o1, n1), (o2, _) in zip(offs, offs[1:]))
+
+
+@pytest.mark.parametrize("head", ["tanh", "flow"])
+def test_colordepth_variable_table(head):
+    """Base_Prediction_Model (main_model.py) at 224^2: same variables and shapes as the oracle's restatement."""
+    import dynamic_multiview_3d_b200 as pkg
+    from oracle import graph as G
+    conf = {"batch_size": 2, "learning_rate": 1e-4, "image_size": 224, "viewpoint_dim": 2, "use_color": "", "use_depth": "",
+            "depth_lr_factor": 0.1, "head": head}
+    m = pkg.Base_Prediction_Model(conf, device="meta")
+    shapes = G.colordepth_param_shapes(224, 2, conf)
+    assert set(shapes) == set(m.store.vars)
+    for k, (_, shp) in shapes.items():
+        assert tuple(shp) == m.store.vars[k].shape, k
+    assert tuple(m.gen_image1.shape) == (2, 224, 224, 3) and tuple(m.gen_dimage1.shape) == (2, 224, 224, 1)
+    assert list(m.store.vars)[:2] == ["pre_image0/e0/w", "pre_image0/e0/b"] and m.store.vars["d3_0/w"].shape == (5, 5, 64, 128)
 
 
 def test_reference_conf_loads_unchanged(tmp_path):

@@ -133,3 +133,30 @@ def test_checkpoint_roundtrip():
     m2 = pkg.AppearanceFlowModel(dict(conf, seed=7))
     m2.load_state_dict(sd)
     assert float(m1.train_step(*args)) == float(m2.train_step(*args))
+
+
+@pytest.mark.parametrize("head,mode", [("tanh", "l2"), ("tanh", "l1"), ("flow", "l2")])
+def test_colordepth_model_parity_and_training(head, mode):
+    """Base_Prediction_Model (BASELINE config 4): forward + loss vs the oracle's restatement of main_model.py, then
+    a few train steps."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200.synthetic import make_batch
+    B, H, V = 4, 64, 2
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "use_color": "", "use_depth": "",
+            "depth_lr_factor": 0.1, "head": head, "loss": mode}
+    model = pkg.Base_Prediction_Model(conf)
+    b = make_batch(B, H, "disp2", depth=True)
+    t = {k: torch.from_numpy(v).cuda() for k, v in b.items()}
+    out = model.forward(t["image0"], t["depth0"], t["disp"])
+    ref = G.colordepth_forward(G.NumpyOps(), _params_from(model), conf, b["image0"], b["depth0"], b["disp"])
+    for k in ("gen_image1", "gen_dimage1"):
+        a, r = out[k].detach().cpu().numpy(), ref[k]
+        assert np.abs(a - r).max() < 3e-2, (k, np.abs(a - r).max())
+        assert np.linalg.norm(a - r) / np.linalg.norm(r) < 2e-2, k
+    loss = float(model.build_loss(t["image1"], t["depth1"]).detach())
+    rloss = float(G.colordepth_loss(G.NumpyOps(), ref, conf, b["image1"], b["depth1"], mode))
+    assert loss == pytest.approx(rloss, rel=2e-2)
+    l0 = float(model.train_step(t["image0"], t["depth0"], t["image1"], t["depth1"], t["disp"]))
+    for _ in range(6):
+        l1 = float(model.train_step(t["image0"], t["depth0"], t["image1"], t["depth1"], t["disp"]))
+    assert np.isfinite(l1) and l1 < l0
