@@ -44,6 +44,8 @@ SIGNATURES = {
     "dmv_linear_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _i, _vp]),
     "dmv_act_fwd": (_i, [_vp, _vp, _i, _ll, _i, _vp]),
     "dmv_act_bwd": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),
+    "dmv_act_bwd_bias_workspace_size": (_sz, [_ll, _i]),
+    "dmv_act_bwd_bias": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _sz, _vp]),
     "dmv_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "dmv_cast_bf16_to_f32": (_i, [_vp, _vp, _ll, _vp]),
     "dmv_adam_tick": (_i, [_vp, _f, _f, _f, _vp]),

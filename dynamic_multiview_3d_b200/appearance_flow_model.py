@@ -136,7 +136,7 @@ class AppearanceFlowModel(object):
         The mean runs over the GLOBAL batch under data parallelism."""
         self.image1 = image1
         n = image1.shape[0] * image1.shape[1] * image1.shape[2] * self.world_size
-        self.loss = F.reconstruction_loss(self.gen, image1, self.loss_mode, inv_count=1.0 / n)
+        self.loss = F.reconstruction_loss(self.gen, image1, self.loss_mode, inv_count=1.0 / n, unit_upstream=True)
         return self.loss
 
     def train_step(self, image0, image1, disp):

@@ -11,6 +11,14 @@ using namespace dmv;
 
 extern "C" {
 
+size_t dmv_act_bwd_bias_workspace_size(long long rows, int C) { return rows > 0 && C > 0 ? act_bwd_bias_workspace(rows, C) : 0; }
+
+int dmv_act_bwd_bias(const void* dy_bf16, const void* y_bf16, void* dpre_bf16, float* db, long long rows, int C, int act, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    DMV_REQUIRE(dy_bf16 && y_bf16 && dpre_bf16 && db && rows > 0 && C > 0, DMV_E_INVALID_ARG, "act_bwd_bias: bad argument");
+    return act_bwd_bias(dy_bf16, y_bf16, dpre_bf16, db, rows, C, act, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 // layers with fewer than 8 channels on the image side (e0: 3, flow head: 2) go through a patch matrix
 static bool thin_side(int c) { return c < 8; }
 

@@ -7,6 +7,9 @@
 
 namespace dmv {
 size_t simt_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
+size_t act_bwd_bias_workspace(long long rows, int C);
+int act_bwd_bias(const void* dy, const void* y, void* dpre, float* db, long long rows, int C, int act, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
 int simt_bias_grad(const void* dy_bf16, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 int simt_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin,
                   int Cout, int kh, int kw, int stride, int act, cudaStream_t st);

@@ -223,6 +223,61 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ Y, fl
     }
 }
 
+// dpre = dy * act'(y) fused with the bias gradient db[c] = sum_rows dpre[row][c]  (bf16 [rows][C], C % 8 == 0).
+// Regime A (C/8 divides 256): a CTA owns a contiguous row range, thread = (row lane, 8-channel group); partial
+// sums per CTA, summed in CTA order by splitk_reduce_kernel.  Regime B (wide FC outputs, few rows): one thread
+// per channel group walks all rows and writes db directly.
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dpre,
+                                                            float* __restrict__ part, long long rows, int C8, long long rows_per_cta, int act,
+                                                            int direct) {
+    __shared__ float red[256][9];
+    float sum[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+    int cg, rl, rstep;
+    long long r0, r1;
+    if (direct) {
+        cg = blockIdx.x * 256 + threadIdx.x; rl = 0; rstep = 1; r0 = 0; r1 = (cg < C8) ? rows : 0;
+    } else {
+        cg = threadIdx.x % C8; rl = threadIdx.x / C8; rstep = 256 / C8;
+        r0 = (long long)blockIdx.x * rows_per_cta; r1 = min(rows, r0 + rows_per_cta);
+    }
+    for (long long r = r0 + rl; r < r1; r += rstep) {
+        const long long i = r * C8 + cg;
+        const uint4 a = __ldg(dy + i), b = __ldg(y + i);
+        uint4 o;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fa = __bfloat1622float2(pa[k]), fb = __bfloat1622float2(pb[k]);
+            po[k] = __floats2bfloat162_rn(fa.x * act_grad_from_output(fb.x, act), fa.y * act_grad_from_output(fb.y, act));
+            const float2 q = __bfloat1622float2(po[k]);     // the bias gradient sums exactly what wgrad/dgrad will read
+            sum[2 * k] += q.x;
+            sum[2 * k + 1] += q.y;
+        }
+        dpre[i] = o;
+    }
+    if (direct) {
+        if (cg < C8)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) part[cg * 8 + k] = sum[k];
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = sum[k];
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float t = 0.f;
+            for (int j = 0; j < rstep; ++j) t += red[j * C8 + cg][k];
+            part[(long long)blockIdx.x * C8 * 8 + cg * 8 + k] = t;
+        }
+    }
+}
+
 int make_geom(ConvGeom& g, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride) {
     DMV_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0, DMV_E_INVALID_ARG,
                 "conv: non-positive dimension");
@@ -305,6 +360,34 @@ int run_g(const void* s, const void* w, void* b, const ConvGeom& g, int act, cud
 // ------------------------------------------------------------------ SIMT entry points
 // (called by the public dispatchers in conv_api.cu)
 namespace dmv {
+
+size_t act_bwd_bias_workspace(long long rows, int C) {
+    (void)rows;
+    return (size_t)148 * 4 * C * sizeof(float) + 256;
+}
+
+int act_bwd_bias(const void* dy, const void* y, void* dpre, float* db, long long rows, int C, int act, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+    if (C % 8 || (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dpre) & 15)) return fail(DMV_E_UNSUPPORTED_SHAPE, "act_bwd_bias: need C % 8 == 0, 16-byte alignment");
+    const int C8 = C / 8;
+    if (C8 <= 256 && (256 % C8) == 0) {
+        long long ctas = 148 * 4;
+        const long long min_rows = 256 / C8 * 4;
+        if (ctas > ceil_div_ll(rows, min_rows)) ctas = ceil_div_ll(rows, min_rows);
+        if (ctas < 1) ctas = 1;
+        const long long per = ceil_div_ll(rows, ctas);
+        ctas = ceil_div_ll(rows, per);
+        if (!ws || ws_bytes < (size_t)ctas * C * sizeof(float)) return fail(DMV_E_WORKSPACE, "act_bwd_bias: workspace too small");
+        float* part = reinterpret_cast<float*>(ws);
+        act_bwd_bias_kernel<<<(int)ctas, 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dpre, part, rows, C8, per, act, 0);
+        int rc = check_launch("act_bwd_bias");
+        if (rc) return rc;
+        splitk_reduce_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, db, C, (int)ctas);
+        return check_launch("act_bwd_bias reduce");
+    }
+    act_bwd_bias_kernel<<<ceil_div(C8, 256), 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dpre, db, rows, C8, rows, act, 1);
+    return check_launch("act_bwd_bias");
+}
 
 int simt_bias_grad(const void* dy_bf16, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
     return run_colsum<bf16>((const bf16*)dy_bf16, db, pixels, C, ws, ws_bytes, st);

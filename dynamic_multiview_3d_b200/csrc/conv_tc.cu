@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     uint64_t* tfull_bar = empty_bar + p.stages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* w_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint64_t* s_bdesc = w_bar + 1;                 // [ntaps] weight-tile descriptors
+    uint32_t* s_aoff = reinterpret_cast<uint32_t*>(s_bdesc + kMaxTaps);   // [ntaps] tap offsets (16-byte units)
+    uint32_t* tmem_slot = s_aoff + kMaxTaps;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_cols = 32;
@@ -299,6 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
         }
         mbar_init(w_bar, 1);
         fence_barrier_init();
+    }
+    if (threadIdx.x < ntaps) {      // MMA operand descriptors, computed once
+        const Tap& tp = p.taps[c.tap_begin + threadIdx.x];
+        s_aoff[threadIdx.x] = (uint32_t)(((tp.dh - p.min_dh) * p.halo_pitch + (tp.dw - p.min_dw)) * kRowBytes) >> 4;
+        s_bdesc[threadIdx.x] = make_kmajor_desc(smem_u32(s_w) + (uint32_t)(threadIdx.x * wtile_bytes), kRowBytes);
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
@@ -341,19 +348,18 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            const uint32_t w_addr = smem_u32(s_w);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_pad);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(s_a + (size_t)stage * a_stage);
+                // the issue loop is single-threaded: keep it to one add and one shared load per tap
+                const uint64_t a_base = a_tmpl | (uint64_t)((smem_u32(s_a + (size_t)stage * a_stage) & 0x3FFFF) >> 4);
+#pragma unroll 5
                 for (int j = 0; j < ntaps; ++j) {
-                    const Tap& tp = p.taps[c.tap_begin + j];
-                    const uint32_t off = (uint32_t)(((tp.dh - p.min_dh) * p.halo_pitch + (tp.dw - p.min_dw)) * kRowBytes);
-                    const uint64_t adesc = a_tmpl | (uint64_t)(((a_addr + off) & 0x3FFFF) >> 4);
-                    const uint64_t bdesc = make_kmajor_desc(w_addr + (uint32_t)(j * wtile_bytes), kRowBytes);
+                    const uint64_t adesc = a_base + (uint64_t)s_aoff[j];
+                    const uint64_t bdesc = s_bdesc[j];
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | k) ? 1u : 0u);
@@ -526,7 +532,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         if (p.halo_pitch <= 256 && p.halo_h <= 256 && wbytes + 2 * a_stage <= 200 * 1024) {
             halo_stages = (int)((200 * 1024 - wbytes) / a_stage);
             if (halo_stages > 6) halo_stages = 6;
-            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8) * sizeof(uint64_t) + 16 + 1024;
+            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8 + kMaxTaps) * sizeof(uint64_t) + kMaxTaps * 4 + 16 + 1024;
             halo_ok = true;
             // the halo kernel tiles the image 8 wide x 16 tall, one image per tile
             p.BW = 8; p.BH = 16; p.NB = 1; p.rows = 128;

@@ -115,6 +115,55 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(LossParams p) {
     }
 }
 
+// Plain (single view, unmasked) loss over the flat [pixels*C] arrays: float4 loads/stores, channel = index % C.
+__global__ void __launch_bounds__(kThreads) loss_flat_kernel(LossParams p) {
+    const long long n4 = (p.pixels * p.C) >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(p.gen);
+    const float4* t4 = reinterpret_cast<const float4*>(p.target);
+    float4* o4 = reinterpret_cast<float4*>(p.grad_gen);
+    double local = 0.0;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        const float4 a = __ldg(g4 + i), b = __ldg(t4 + i);
+        int c = (int)((i * 4) % p.C);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        float gv[4], acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float w = p.w[c];
+            const float d = av[k] - bv[k];
+            float g;
+            if (p.mode == DMV_LOSS_L2) { acc += w * d * d; g = 2.0f * d; }
+            else { acc += w * fabsf(d); g = (d > 0.f) ? 1.0f : (d < 0.f ? -1.0f : 0.0f); }
+            gv[k] = g * w * p.inv_count;
+            if (++c == p.C) c = 0;
+        }
+        if (o4) o4[i] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        local += (double)acc;
+    }
+    __shared__ double s_red[kThreads / 32];
+    __shared__ bool s_last;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) t += s_red[w];
+        p.partials[blockIdx.x] = t;
+        __threadfence();
+        const unsigned done = atomicAdd(p.counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) t += ((volatile double*)p.partials)[i];
+        *p.loss_out = (float)(t * (double)p.inv_count);
+        *p.counter = 0;
+    }
+}
+
 __global__ void scale_kernel(float* x, const float* s, long long n) {
     const float k = __ldg(s);
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -152,6 +201,15 @@ int dmv_loss_fused_fwd_bwd(const float* gen, const float* logits, int V, const f
     long long blocks = dmv::ceil_div_ll(pixels, kThreads);
     if (blocks > kMaxBlocks) blocks = kMaxBlocks;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool flat = V == 1 && !mask && !fused_out && ((pixels * C) % 4 == 0) &&
+                      ((((uintptr_t)gen | (uintptr_t)target | (uintptr_t)grad_gen) & 15) == 0);
+    if (flat) {
+        long long fb = dmv::ceil_div_ll(pixels * C / 4, kThreads * 4);
+        if (fb > kMaxBlocks) fb = kMaxBlocks;
+        if (fb < 1) fb = 1;
+        loss_flat_kernel<<<(int)fb, kThreads, 0, st>>>(p);
+        return dmv::check_launch("loss_flat");
+    }
     switch (C) {
         case 1: loss_kernel<1><<<(int)blocks, kThreads, 0, st>>>(p); break;
         case 3: loss_kernel<3><<<(int)blocks, kThreads, 0, st>>>(p); break;

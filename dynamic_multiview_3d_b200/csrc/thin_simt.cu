@@ -107,29 +107,46 @@ __global__ void thin_reduce_kernel(const float* __restrict__ part, float* __rest
 }
 
 // Patch matrix of a thin tensor: P[pixel][k], k = (tap, ct) in reference weight order, zero padded to Kp columns.
-// One thread writes 8 consecutive bf16 (16 bytes).
+// One CTA builds the patches of ONE output row: the kh input rows it touches are staged in shared memory
+// (coalesced, zero padded left/right/top/bottom exactly like TF-SAME), then every thread assembles 16-byte
+// chunks of P through a per-column offset table.  HBM-bound: reads the thin tensor once, writes P once.
 template <typename TT>
-__global__ void thin_im2col_kernel(const TT* __restrict__ thin, bf16* __restrict__ P, ThinGeom g, int Kp) {
+__global__ void __launch_bounds__(256) thin_im2col_kernel(const TT* __restrict__ thin, bf16* __restrict__ P, ThinGeom g, int Kp) {
+    extern __shared__ float s_rows[];             // [kh][pitch] then int koff[Kp]
+    const int pr = max((g.Ws - 1) * g.st + g.kw - g.Wb - g.pl, 0);
+    const int pitch = (g.pl + g.Wb + pr) * g.Ct;
+    int* koff = reinterpret_cast<int*>(s_rows + g.kh * pitch);
+    const int oh = blockIdx.x % g.Hs, n = blockIdx.x / g.Hs;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        int off = -1;
+        if (k < g.rows) {
+            const int tap = k / g.Ct, c = k - tap * g.Ct;
+            off = (tap / g.kw) * pitch + (tap % g.kw) * g.Ct + c;
+        }
+        koff[k] = off;
+    }
+    const int row_elems = g.Wb * g.Ct;
+    for (int r = 0; r < g.kh; ++r) {
+        const int y = oh * g.st + r - g.pt;
+        float* dst = s_rows + r * pitch;
+        const bool in = (y >= 0 && y < g.Hb);
+        const TT* src = thin + ((long long)n * g.Hb + (in ? y : 0)) * row_elems;
+        for (int e = threadIdx.x; e < pitch; e += blockDim.x) {
+            const int j = e - g.pl * g.Ct;
+            dst[e] = (in && j >= 0 && j < row_elems) ? load_as_float(src + j) : 0.f;
+        }
+    }
+    __syncthreads();
     const int groups = Kp / 8;
-    const long long total = (long long)g.N * g.Hs * g.Ws * groups;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int gq = (int)(i % groups);
-        const long long p = i / groups;
-        const int ow = (int)(p % g.Ws);
-        const int oh = (int)((p / g.Ws) % g.Hs);
-        const int n = (int)(p / ((long long)g.Ws * g.Hs));
-        const int by = oh * g.st - g.pt, bx = ow * g.st - g.pl;
+    bf16* out = P + ((long long)n * g.Hs + oh) * g.Ws * Kp;
+    for (int i = threadIdx.x; i < g.Ws * groups; i += blockDim.x) {
+        const int ow = i / groups, gq = i - ow * groups;
+        const int base = ow * g.st * g.Ct;
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int row = gq * 8 + k;
-            v[k] = 0.f;
-            if (row < g.rows) {
-                const int tap = row / g.Ct, c = row - tap * g.Ct;
-                const int y = by + tap / g.kw, x = bx + tap % g.kw;
-                if (y >= 0 && y < g.Hb && x >= 0 && x < g.Wb) v[k] = load_as_float(thin + (((long long)n * g.Hb + y) * g.Wb + x) * g.Ct + c);
-            }
+            const int off = koff[gq * 8 + k];
+            v[k] = off >= 0 ? s_rows[base + off] : 0.f;
         }
         uint4 q;
         __nv_bfloat162 h;
@@ -137,7 +154,7 @@ __global__ void thin_im2col_kernel(const TT* __restrict__ thin, bf16* __restrict
         h = __floats2bfloat162_rn(v[2], v[3]); q.y = *reinterpret_cast<uint32_t*>(&h);
         h = __floats2bfloat162_rn(v[4], v[5]); q.z = *reinterpret_cast<uint32_t*>(&h);
         h = __floats2bfloat162_rn(v[6], v[7]); q.w = *reinterpret_cast<uint32_t*>(&h);
-        *reinterpret_cast<uint4*>(P + p * Kp + gq * 8) = q;
+        *reinterpret_cast<uint4*>(out + (long long)i * 8) = q;
     }
 }
 
@@ -188,10 +205,17 @@ int thin_im2col(const void* thin, int thin_dtype, void* P, int N, int Hb, int Wb
     g.N = N; g.Hb = Hb; g.Wb = Wb; g.Ct = Ct; g.Hs = ph.out; g.Ws = pw.out; g.kh = kh; g.kw = kw; g.st = stride;
     g.pt = ph.before; g.pl = pw.before; g.rows = kh * kw * Ct;
     const int Kp = thin_patch_cols(kh * kw, Ct);
-    long long blocks = ceil_div_ll((long long)N * g.Hs * g.Ws * (Kp / 8), 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    if (thin_dtype == DMV_DT_F32) thin_im2col_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)thin, (bf16*)P, g, Kp);
-    else thin_im2col_kernel<bf16><<<(int)blocks, 256, 0, st>>>((const bf16*)thin, (bf16*)P, g, Kp);
+    const int prr = (g.Ws - 1) * stride + kw - Wb - g.pl;
+    const size_t smem = (size_t)kh * (g.pl + Wb + (prr > 0 ? prr : 0)) * Ct * sizeof(float) + (size_t)Kp * sizeof(int);
+    if (smem > 200 * 1024) return fail(DMV_E_UNSUPPORTED_SHAPE, "thin_im2col: input rows do not fit shared memory");
+    const int blocks = N * g.Hs;
+    if (thin_dtype == DMV_DT_F32) {
+        cudaFuncSetAttribute(thin_im2col_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        thin_im2col_kernel<float><<<blocks, 256, smem, st>>>((const float*)thin, (bf16*)P, g, Kp);
+    } else {
+        cudaFuncSetAttribute(thin_im2col_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        thin_im2col_kernel<bf16><<<blocks, 256, smem, st>>>((const bf16*)thin, (bf16*)P, g, Kp);
+    }
     return check_launch("thin_im2col");
 }
 

@@ -237,7 +237,7 @@ size_t plan_wgrad(const WProblem& q, WgradParams& p) {
     p.img_groups = ceil_div(q.N, p.NB);
     p.chunks = p.tiles_w * p.tiles_h * p.img_groups;
     const int base_ctas = p.groups * p.n_tiles;
-    int slices = ceil_div(2 * num_sms(), base_ctas);
+    int slices = ceil_div(num_sms(), base_ctas);
     if (slices > p.chunks) slices = p.chunks;
     if (slices < 1) slices = 1;
     p.chunks_per_slice = ceil_div(p.chunks, slices);
@@ -337,7 +337,7 @@ size_t tc_wgrad_workspace(int taps, int Cin, int Cout, long long pixels) {
     int tpg = 512 / n_tile;
     if (tpg > m_tiles) tpg = m_tiles;
     const int base = ceil_div(m_tiles, tpg) * n_tiles;
-    long long slices = ceil_div(2 * num_sms(), base);
+    long long slices = ceil_div(num_sms(), base);
     const long long max_chunks = ceil_div_ll(pixels, 16);
     if (slices > max_chunks) slices = max_chunks;
     if (slices <= 1) return 0;

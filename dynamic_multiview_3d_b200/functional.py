@@ -155,7 +155,14 @@ class _Conv2d(torch.autograd.Function):
         st = _stream(x)
         _tag[0] = wvar.name
         dy = dy.contiguous()
-        if dy.dtype != torch.bfloat16 or ACT[act]:
+        bias_done = False
+        if bvar is not None and ACT[act] and y.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and Cout % 8 == 0:
+            dpre = torch.empty_like(y)
+            rows = y.numel() // Cout
+            ws = workspace(_lib.load().dmv_act_bwd_bias_workspace_size(rows, Cout), x.device)
+            call("dmv_act_bwd_bias", _p(dy), _p(y), _p(dpre), _p(bvar.grad), rows, Cout, ACT[act], _p(ws), ws.numel(), st)
+            bias_done = True
+        elif dy.dtype != torch.bfloat16 or ACT[act]:
             dpre = torch.empty(y.shape, dtype=y.dtype, device=y.device)
             call("dmv_act_bwd", _p(dy), _p(y), _p(dpre), _dt(y), y.numel(), ACT[act], st)
             if dpre.dtype != torch.bfloat16:
@@ -176,7 +183,7 @@ class _Conv2d(torch.autograd.Function):
         pixels = B * y.shape[1] * y.shape[2]
         nws = _lib.load().dmv_wgrad_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
         ws = workspace(nws, x.device)
-        call("dmv_conv2d_wgrad", _p(x), _dt(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if bvar is not None else None,
+        call("dmv_conv2d_wgrad", _p(x), _dt(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None,
              B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
         store = wvar.store
         if bvar is not None:
@@ -262,7 +269,13 @@ class _Linear(torch.autograd.Function):
         st = _stream(x)
         _tag[0] = wvar.name
         dy = dy.contiguous()
-        if ACT[act]:
+        bias_done = False
+        if bvar is not None and ACT[act] and N % 8 == 0:
+            dpre = torch.empty_like(y)
+            ws = workspace(_lib.load().dmv_act_bwd_bias_workspace_size(M, N), x.device)
+            call("dmv_act_bwd_bias", _p(dy), _p(y), _p(dpre), _p(bvar.grad), M, N, ACT[act], _p(ws), ws.numel(), st)
+            bias_done = True
+        elif ACT[act]:
             dpre = torch.empty_like(y)
             call("dmv_act_bwd", _p(dy), _p(y), _p(dpre), DT_BF16, y.numel(), ACT[act], st)
         else:
@@ -273,7 +286,7 @@ class _Linear(torch.autograd.Function):
             call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
         ws = workspace(nws, x.device)
-        call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if bvar is not None else None, M, K, N,
+        call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,
              _p(ws), ws.numel(), algo, st)
         if bvar is not None:
             wvar.store.notify_grad(bvar)
@@ -388,7 +401,7 @@ def resampler_debug(data, wf, flags=0):
 # ----------------------------------------------------------------------------- losses
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gen, logits, target, mask, weights, mode, inv_count, want_fused):
+    def forward(ctx, gen, logits, target, mask, weights, mode, inv_count, want_fused, unit_upstream=False):
         _need_cuda(gen, target)
         gen = gen.contiguous()
         target = target.contiguous()
@@ -412,6 +425,7 @@ class _FusedLoss(torch.autograd.Function):
         call("dmv_loss_fused_fwd_bwd", _p(gen), _p(logits), V, _p(target), _p(mask), w, LOSS[mode], float(inv_count), _p(loss),
              _p(gg), _p(gl), _p(fused), pixels, Cc, _p(ws), ws.numel(), _stream(gen))
         ctx.grads = (gg, gl)
+        ctx.unit_upstream = unit_upstream
         ctx.mark_non_differentiable(*([fused] if fused is not None else []))
         if fused is not None:
             return loss, fused
@@ -420,6 +434,8 @@ class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, *unused):
         gg, gl = ctx.grads
+        if ctx.unit_upstream:       # the caller guarantees d(total)/d(this loss) == 1: nothing to chain
+            return gg, gl, None, None, None, None, None, None, None
         st = _stream(gloss)
         _tag[0] = "loss"
         gloss = gloss.contiguous().to(torch.float32)
@@ -428,7 +444,7 @@ class _FusedLoss(torch.autograd.Function):
             call("dmv_scale_by_device_scalar", _p(gg), _p(gloss), gg.numel(), st)
         if gl is not None:
             call("dmv_scale_by_device_scalar", _p(gl), _p(gloss), gl.numel(), st)
-        return gg, gl, None, None, None, None, None, None
+        return gg, gl, None, None, None, None, None, None, None
 
 
 _loss_wss = {}
@@ -445,13 +461,15 @@ def _loss_ws(device, nbytes):
     return ws
 
 
-def reconstruction_loss(gen, target, mode="l2", weights=None, inv_count=None, mask=None):
-    """mean_{b,h,w} sum_c w_c * (d^2 | |d|), d = (gen - target) * mask; gradient fused in."""
+def reconstruction_loss(gen, target, mode="l2", weights=None, inv_count=None, mask=None, unit_upstream=False):
+    """mean_{b,h,w} sum_c w_c * (d^2 | |d|), d = (gen - target) * mask; gradient fused in.
+    unit_upstream=True: the loss enters the optimised objective with coefficient 1 (fold other coefficients
+    into ``weights``), so backward skips the pass that chains the upstream scalar."""
     Cc = gen.shape[-1]
     weights = [1.0] * Cc if weights is None else list(weights)
     if inv_count is None:
         inv_count = 1.0 / (target.numel() // Cc)
-    return _FusedLoss.apply(gen, None, target, mask, tuple(weights), mode, inv_count, False)
+    return _FusedLoss.apply(gen, None, target, mask, tuple(weights), mode, inv_count, False, unit_upstream)
 
 
 def fused_views_loss(gens, logits, target, mode="l2", weights=None, inv_count=None, mask=None, want_fused=True):

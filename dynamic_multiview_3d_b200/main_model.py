@@ -141,10 +141,10 @@ class Base_Prediction_Model(object):
         n = image1.shape[0] * image1.shape[1] * image1.shape[2] * self.world_size
         loss = None
         if self.use_color:
-            loss = F.reconstruction_loss(self.gen_image1, image1, self.loss_mode, inv_count=1.0 / n)
+            loss = F.reconstruction_loss(self.gen_image1, image1, self.loss_mode, inv_count=1.0 / n, unit_upstream=True)
         if self.use_depth:
             f = float(self.conf["depth_lr_factor"])
-            ld = F.reconstruction_loss(self.gen_dimage1, dimage1, self.loss_mode, weights=[f], inv_count=1.0 / n)
+            ld = F.reconstruction_loss(self.gen_dimage1, dimage1, self.loss_mode, weights=[f], inv_count=1.0 / n, unit_upstream=True)
             loss = ld if loss is None else loss + ld
         self.image1, self.dimage1, self.loss = image1, dimage1, loss
         return loss

@@ -178,6 +178,11 @@ int dmv_linear_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, float* 
 int dmv_act_fwd(const void* x, void* y, int dtype, long long n, int act, void* stream);
 int dmv_act_bwd(const void* dy, const void* y, void* dpre, int dtype, long long n, int act,
                 void* stream);
+/* dmv_act_bwd fused with the bias gradient (BiasAddGrad): db[c] = sum_rows dpre[row][c], bf16 [rows][C],
+ * C % 8 == 0; deterministic.  The wgrad entry points may then be called with db = NULL.          */
+size_t dmv_act_bwd_bias_workspace_size(long long rows, int C);
+int dmv_act_bwd_bias(const void* dy_bf16, const void* y_bf16, void* dpre_bf16, float* db, long long rows,
+                     int C, int act, void* workspace, size_t workspace_bytes, void* stream);
 int dmv_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int dmv_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, void* stream);
 
