@@ -127,7 +127,7 @@ def reference_arm(args, rank):
             "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def sampler_microbench(torch, pk, iters=20):
@@ -211,6 +211,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version banner)
+    # is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args, rank)
         return 0
@@ -361,9 +367,22 @@ def main():
             "gpu_launches": int(launches * K), "launches_per_step": int(launches),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sampler": micro, "top_kernels": top,
             "step_tflops_per_gpu": round(step_tflops, 2), "final_loss": last}
-    print(json.dumps(line), flush=True)
+    emit(line)
     finish(world, rank)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def finish(world, rank):

@@ -44,6 +44,10 @@ size_t dmv_wgrad_workspace_size(int B, int H, int W, int Cbig, int Csmall, int k
 size_t dmv_conv_workspace_size(int B, int H, int W, int Cbig, int Csmall, int kh, int kw, int stride) {
     if (B <= 0 || H <= 0 || W <= 0 || Cbig <= 0 || Csmall <= 0 || kh <= 0 || kw <= 0 || stride <= 0) return 0;
     size_t a = tc_pack_workspace(kh * kw, Cbig, Csmall);
+    if (H == 1 && W == 1 && kh == 1 && kw == 1) {           // linear layer: split-K partials
+        size_t c = tc_linear_workspace(B, Cbig, Csmall);
+        if (c > a) a = c;
+    }
     if (thin_side(Cbig)) {
         size_t c = tc_thin_workspace(B, H, W, Cbig, Csmall, kh, kw, stride);
         if (c > a) a = c;
@@ -157,24 +161,25 @@ int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, i
 }
 
 // linear == 1x1 conv over M "pixels"
-int dmv_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, int algo,
-                   void* stream) {
+int dmv_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, void* workspace,
+                   size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "linear_fwd: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_linear_fwd(x, w, bias, y, M, K, N, act, st);
+        int rc = tc_linear_fwd(x, w, bias, y, M, K, N, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_conv_fwd(x, DMV_DT_BF16, w, bias, y, DMV_DT_BF16, M, 1, 1, K, N, 1, 1, 1, act, st);
 }
 
-int dmv_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, int algo, void* stream) {
+int dmv_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, void* workspace, size_t workspace_bytes, int algo,
+                     void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "linear_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
     if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_linear_dgrad(dy, w, dx, M, K, N, st);
+        int rc = tc_linear_dgrad(dy, w, dx, M, K, N, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
     }
     return simt_conv_dgrad(dy, w, dx, M, 1, 1, K, N, 1, 1, 1, st);

@@ -53,8 +53,10 @@ int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, in
                     int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_deconv_wgrad(const void* x, const void* dy, int dydt, float* dw, int B, int Hout, int Wout, int Cin, int Cout, int kh,
                     int kw, int stride, void* ws, size_t ws_bytes, cudaStream_t st);
-int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, cudaStream_t st);
-int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, cudaStream_t st);
+size_t tc_linear_workspace(int M, int K, int N);
+int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_linear_wgrad(const void* x, const void* dy, float* dw, float* db, int M, int K, int N, void* ws, size_t ws_bytes,
                     cudaStream_t st);
 }  // namespace dmv

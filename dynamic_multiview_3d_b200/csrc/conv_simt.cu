@@ -224,27 +224,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ Y, fl
 }
 
 // dpre = dy * act'(y) fused with the bias gradient db[c] = sum_rows dpre[row][c]  (bf16 [rows][C], C % 8 == 0).
-// Regime A (C/8 divides 256): a CTA owns a contiguous row range, thread = (row lane, 8-channel group); partial
-// sums per CTA, summed in CTA order by splitk_reduce_kernel.  Regime B (wide FC outputs, few rows): one thread
-// per channel group walks all rows and writes db directly.
+// CTA = (CGB column groups of 8 channels) x (256/CGB row lanes) over a contiguous row range; grid.x tiles the
+// columns, grid.y the rows.  Four rows are in flight per thread.  CTA partials are summed in grid.y order by
+// splitk_reduce_kernel (deterministic).
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dpre,
-                                                            float* __restrict__ part, long long rows, int C8, long long rows_per_cta, int act,
-                                                            int direct) {
+                                                            float* __restrict__ part, long long rows, int C8, int cgb, long long rows_per_cta,
+                                                            int act) {
     __shared__ float red[256][9];
     float sum[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) sum[k] = 0.f;
-    int cg, rl, rstep;
-    long long r0, r1;
-    if (direct) {
-        cg = blockIdx.x * 256 + threadIdx.x; rl = 0; rstep = 1; r0 = 0; r1 = (cg < C8) ? rows : 0;
-    } else {
-        cg = threadIdx.x % C8; rl = threadIdx.x / C8; rstep = 256 / C8;
-        r0 = (long long)blockIdx.x * rows_per_cta; r1 = min(rows, r0 + rows_per_cta);
-    }
-    for (long long r = r0 + rl; r < r1; r += rstep) {
-        const long long i = r * C8 + cg;
-        const uint4 a = __ldg(dy + i), b = __ldg(y + i);
+    const int cl = threadIdx.x % cgb, rl = threadIdx.x / cgb, rstep = 256 / cgb;
+    const int cg = blockIdx.x * cgb + cl;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    auto one = [&](const uint4& a, const uint4& b) {
         uint4 o;
         const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
         const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
@@ -257,24 +250,44 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const uint4* __restri
             sum[2 * k] += q.x;
             sum[2 * k + 1] += q.y;
         }
-        dpre[i] = o;
-    }
-    if (direct) {
-        if (cg < C8)
+        return o;
+    };
+    long long r = r0 + rl;
+    for (; r + 3LL * rstep < r1; r += 4LL * rstep) {
+        uint4 a[4], b[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) part[cg * 8 + k] = sum[k];
-        return;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = sum[k];
-    __syncthreads();
-    if (rl == 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float t = 0.f;
-            for (int j = 0; j < rstep; ++j) t += red[j * C8 + cg][k];
-            part[(long long)blockIdx.x * C8 * 8 + cg * 8 + k] = t;
+        for (int u = 0; u < 4; ++u) {
+            const long long i = (r + (long long)u * rstep) * C8 + cg;
+            a[u] = __ldg(dy + i);
+            b[u] = __ldg(y + i);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dpre[(r + (long long)u * rstep) * C8 + cg] = one(a[u], b[u]);
+    }
+    for (; r < r1; r += rstep) {
+        const long long i = r * C8 + cg;
+        dpre[i] = one(__ldg(dy + i), __ldg(y + i));
+    }
+    // reduce over the row lanes: shuffles inside the warp (lanes sharing a column group are cgb apart),
+    // then across the 8 warps through shared memory, in a fixed order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int off = cgb; off < 32; off <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], off);
+    const int slots = cgb < 32 ? cgb : 32;
+    if (lane < slots)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[warp * 32 + lane][k] = sum[k];
+    __syncthreads();
+    for (int t = threadIdx.x; t < cgb * 8; t += 256) {
+        const int c = t >> 3, k = t & 7;
+        float acc = 0.f;
+        if (cgb <= 32) {
+            for (int w = 0; w < 8; ++w) acc += red[w * 32 + c][k];
+        } else {                                  // cgb == 64: even warps hold columns 0..31, odd warps 32..63
+            for (int w = (c >> 5); w < 8; w += 2) acc += red[w * 32 + (c & 31)][k];
+        }
+        part[((long long)blockIdx.y * C8 + blockIdx.x * cgb + c) * 8 + k] = acc;
     }
 }
 
@@ -363,30 +376,31 @@ namespace dmv {
 
 size_t act_bwd_bias_workspace(long long rows, int C) {
     (void)rows;
-    return (size_t)148 * 4 * C * sizeof(float) + 256;
+    return (size_t)148 * 6 * C * sizeof(float) + 256;
 }
 
 int act_bwd_bias(const void* dy, const void* y, void* dpre, float* db, long long rows, int C, int act, void* ws, size_t ws_bytes,
                  cudaStream_t st) {
     if (C % 8 || (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dpre) & 15)) return fail(DMV_E_UNSUPPORTED_SHAPE, "act_bwd_bias: need C % 8 == 0, 16-byte alignment");
     const int C8 = C / 8;
-    if (C8 <= 256 && (256 % C8) == 0) {
-        long long ctas = 148 * 4;
-        const long long min_rows = 256 / C8 * 4;
-        if (ctas > ceil_div_ll(rows, min_rows)) ctas = ceil_div_ll(rows, min_rows);
-        if (ctas < 1) ctas = 1;
-        const long long per = ceil_div_ll(rows, ctas);
-        ctas = ceil_div_ll(rows, per);
-        if (!ws || ws_bytes < (size_t)ctas * C * sizeof(float)) return fail(DMV_E_WORKSPACE, "act_bwd_bias: workspace too small");
-        float* part = reinterpret_cast<float*>(ws);
-        act_bwd_bias_kernel<<<(int)ctas, 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dpre, part, rows, C8, per, act, 0);
-        int rc = check_launch("act_bwd_bias");
-        if (rc) return rc;
-        splitk_reduce_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, db, C, (int)ctas);
-        return check_launch("act_bwd_bias reduce");
-    }
-    act_bwd_bias_kernel<<<ceil_div(C8, 256), 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dpre, db, rows, C8, rows, act, 1);
-    return check_launch("act_bwd_bias");
+    int cgb = 64;
+    while (cgb > 1 && (C8 % cgb)) cgb >>= 1;          // largest power of two <= 64 dividing C/8
+    const int col_blocks = C8 / cgb;
+    const int rstep = 256 / cgb;
+    long long row_ctas = ceil_div_ll(148 * 6, col_blocks);
+    const long long max_by_rows = ceil_div_ll(rows, (long long)rstep * 4);
+    if (row_ctas > max_by_rows) row_ctas = max_by_rows;
+    if (row_ctas < 1) row_ctas = 1;
+    const long long per = ceil_div_ll(rows, row_ctas);
+    row_ctas = ceil_div_ll(rows, per);
+    if (!ws || ws_bytes < (size_t)row_ctas * C * sizeof(float)) return fail(DMV_E_WORKSPACE, "act_bwd_bias: workspace too small");
+    float* part = reinterpret_cast<float*>(ws);
+    dim3 grid(col_blocks, (unsigned)row_ctas);
+    act_bwd_bias_kernel<<<grid, 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dpre, part, rows, C8, cgb, per, act);
+    int rc = check_launch("act_bwd_bias");
+    if (rc) return rc;
+    splitk_reduce_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, db, C, (int)row_ctas);
+    return check_launch("act_bwd_bias reduce");
 }
 
 int simt_bias_grad(const void* dy_bf16, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -53,6 +53,8 @@ struct IgemmParams {
     int b_mode;                   // 0: packed K-major [n][K]; 1: reference HWIO read as (co, ci, tap), K-major;
                                   // 2: MN-major [K][n] (linear forward: Matrix[K,N] as stored)
     int stages;
+    int k_splits;                 // linear layers: the contraction is cut into k_splits ranges (fp32 partials + finish kernel)
+    long long split_stride;       // elements between the partial outputs of consecutive splits
     int halo_pitch, halo_h, min_dh, min_dw;   // halo kernel: window rows x pitch pixels, origin offset of the window
     TapClass cls[4];
     Tap taps[kMaxTaps];
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles;
+    const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles * p.k_splits;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -108,16 +110,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             const uint32_t tx = (uint32_t)(p.rows * kRowBytes + b_bytes);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
-                const int sp = tile / p.n_tiles;
+                const int ks = (tile / p.n_tiles) % p.k_splits;
+                const int sp = tile / (p.n_tiles * p.k_splits);
                 const int ci = sp / p.tiles_per_class;
                 int t = sp - ci * p.tiles_per_class;
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int g = t;
                 const TapClass& c = p.cls[ci];
+                const int per_split = (p.kc_per_tap + p.k_splits - 1) / p.k_splits;      // k_splits > 1 only with one tap
+                const int ch0 = p.k_splits > 1 ? ks * per_split : 0;
+                const int ch1 = p.k_splits > 1 ? min(p.kc_per_tap, ch0 + per_split) : p.kc_per_tap;
                 for (int j = 0; j < c.tap_count; ++j) {
                     const Tap& tp = p.taps[c.tap_begin + j];
-                    for (int ch = 0; ch < p.kc_per_tap; ++ch) {
+                    for (int ch = ch0; ch < ch1; ++ch) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full_bar[stage], tx);
@@ -149,8 +155,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TapClass& c = p.cls[(tile / p.n_tiles) / p.tiles_per_class];
-                const int kblocks = c.tap_count * p.kc_per_tap;
+                const TapClass& c = p.cls[(tile / (p.n_tiles * p.k_splits)) / p.tiles_per_class];
+                int kblocks = c.tap_count * p.kc_per_tap;
+                if (p.k_splits > 1) {
+                    const int ks = (tile / p.n_tiles) % p.k_splits;
+                    const int per_split = (p.kc_per_tap + p.k_splits - 1) / p.k_splits;
+                    kblocks = min(p.kc_per_tap, (ks + 1) * per_split) - ks * per_split;
+                }
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_pad);
@@ -181,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int per_img = p.BH * p.BW;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
-            const int sp = tile / p.n_tiles;
+            const int ks = (tile / p.n_tiles) % p.k_splits;
+            const int sp = tile / (p.n_tiles * p.k_splits);
             const int ci = sp / p.tiles_per_class;
             int t = sp - ci * p.tiles_per_class;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         f[k] = apply_act(x, p.act);
                     }
                     if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out) + opix * p.n_real + ncol0 + c0;
+                        float* o = reinterpret_cast<float*>(p.out) + (long long)ks * p.split_stride + opix * p.n_real + ncol0 + c0;
                         if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 3) == 0) {
 #pragma unroll
                             for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(o + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
@@ -436,6 +448,18 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     }
 }
 
+// split-K finish: y[m][n] = act( sum_ks part[ks][m][n] + bias[n] ) in bf16, splits added in order
+__global__ void splitk_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias, bf16* __restrict__ y, long long mn, int N,
+                                     int splits, int act) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += stride) {
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[(long long)z * mn + i];
+        if (bias) s += __ldg(bias + (int)(i % N));
+        y[i] = __float2bfloat16_rn(apply_act(s, act));
+    }
+}
+
 // F-form weight packing: w[t][ci][co] (bf16) -> packed[co][t*Cin + ci]
 __global__ void pack_f_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int taps, int Cin, int Cout) {
     const long long n = (long long)taps * Cin * Cout;
@@ -479,6 +503,7 @@ struct Problem {
     // weights
     const void* w_hwio; int kh, kw, w_ci, w_co;   // reference layout [kh][kw][w_ci][w_co]
     bool g_form;                                   // contraction over w_co (G) or w_ci (F)
+    int k_splits;                                  // > 1: split the contraction (linear layers); needs workspace for partials
     int n_tile;                                    // 0: one N tile covering all output channels
     int b_mode_override;                           // -1: by form; 2: MN-major Matrix[K,N] (linear forward)
     // output
@@ -497,6 +522,8 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     p.n_real = q.n_real;
     p.n_pad = q.n_tile ? q.n_tile : ceil_div(q.n_real, 16) * 16;
     p.n_tiles = ceil_div(q.n_real, p.n_pad);
+    p.k_splits = 1;
+    p.split_stride = 0;
     p.kc_per_tap = Cc / KC;
     p.c_plane = Cc;
     p.Jh = q.Jh; p.Jw = q.Jw; p.Nimg = q.N;
@@ -619,6 +646,25 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         count_tc_launch();
         return check_launch("halo_tc");
     }
+    // ---- split-K (linear layers): fp32 partials into the workspace, finished by splitk_finish_kernel
+    void* final_out = p.out;
+    const float* final_bias = p.bias;
+    const int final_act = p.act;
+    if (q.k_splits > 1) {
+        int ks = q.k_splits;
+        if (ks > p.kc_per_tap / 4) ks = p.kc_per_tap / 4;
+        if (ks < 1) ks = 1;
+        ks = ceil_div(p.kc_per_tap, ceil_div(p.kc_per_tap, ks));     // no empty split
+        const long long mn = (long long)q.N * q.n_real;
+        if (ks > 1 && p.num_classes == 1 && p.cls[0].tap_count == 1 && !q.out_f32 && workspace && ws_bytes >= (size_t)ks * mn * sizeof(float)) {
+            p.k_splits = ks;
+            p.split_stride = mn;
+            p.out = workspace;
+            p.out_f32 = 1;
+            p.bias = nullptr;
+            p.act = DMV_ACT_NONE;
+        }
+    }
     // ---- shared memory / grid
     const int stage_bytes = 128 * row_bytes + p.n_pad * row_bytes;
     // The pipeline is latency-bound (one TMA box per tap): keep as many bytes in flight per SM as
@@ -629,7 +675,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
-    const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles;
+    const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles * p.k_splits;
     int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > total_tiles) grid = total_tiles;
     cudaError_t e;
@@ -645,7 +691,17 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         return DMV_E_CUDA;
     }
     count_tc_launch();
-    return check_launch("igemm_tc");
+    int rc_l = check_launch("igemm_tc");
+    if (rc_l) return rc_l;
+    if (p.k_splits > 1) {
+        const long long mn = (long long)q.N * q.n_real;
+        long long blocks = ceil_div_ll(mn, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        splitk_finish_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), final_bias, reinterpret_cast<bf16*>(final_out), mn,
+                                                           q.n_real, p.k_splits, final_act);
+        return check_launch("splitk_finish");
+    }
+    return DMV_OK;
 }
 
 // taps of the F form (conv-fwd-like): A pixel = out*stride + (r - pt, s - pl)
@@ -716,7 +772,7 @@ int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* 
     if (rc) return rc;
     Problem q;
     q.src = x; q.N = B; q.Hs = H; q.Ws = W; q.Cs = Cin; q.src_stride = stride;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = false; q.n_tile = 0; q.b_mode_override = -1;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = false; q.n_tile = 0; q.b_mode_override = -1; q.k_splits = 1;
     q.out = y; q.out_f32 = (ydt == DMV_DT_F32); q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cout; q.out_mul = 1;
     q.Jh = ph.out; q.Jw = pw.out; q.bias = bias; q.act = act;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -733,7 +789,7 @@ int tc_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, 
     if (rc) return rc;
     Problem q;
     q.src = dy; q.N = B; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cout; q.src_stride = 1;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = true; q.n_tile = 0; q.b_mode_override = -1;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cin; q.w_co = Cout; q.g_form = true; q.n_tile = 0; q.b_mode_override = -1; q.k_splits = 1;
     q.out = dx; q.out_f32 = 0; q.out_H = H; q.out_W = W; q.n_real = Cin; q.out_mul = stride;
     q.Jh = ceil_div(H, stride); q.Jw = ceil_div(W, stride); q.bias = nullptr; q.act = DMV_ACT_NONE;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -750,7 +806,7 @@ int tc_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hou
     if (rc) return rc;
     Problem q;
     q.src = x; q.N = B; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cin; q.src_stride = 1;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = true; q.n_tile = 0; q.b_mode_override = -1;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = true; q.n_tile = 0; q.b_mode_override = -1; q.k_splits = 1;
     q.out = y; q.out_f32 = (ydt == DMV_DT_F32); q.out_H = Hout; q.out_W = Wout; q.n_real = Cout; q.out_mul = stride;
     q.Jh = ceil_div(Hout, stride); q.Jw = ceil_div(Wout, stride); q.bias = nullptr; q.act = act;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -768,7 +824,7 @@ int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, in
     if (rc) return rc;
     Problem q;
     q.src = dy; q.N = B; q.Hs = Hout; q.Ws = Wout; q.Cs = Cout; q.src_stride = stride;
-    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = false; q.n_tile = 0; q.b_mode_override = -1;
+    q.w_hwio = w; q.kh = kh; q.kw = kw; q.w_ci = Cout; q.w_co = Cin; q.g_form = false; q.n_tile = 0; q.b_mode_override = -1; q.k_splits = 1;
     q.out = dx; q.out_f32 = 0; q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cin; q.out_mul = 1;
     q.Jh = ph.out; q.Jw = pw.out; q.bias = nullptr; q.act = DMV_ACT_NONE;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -777,7 +833,20 @@ int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, in
 
 // linear forward: Y[M,N] = X[M,K] Matrix[K,N] + b.  A = X (K-major rows), B = Matrix as stored (MN-major),
 // N tiles of 64 columns so that the weight stream (the whole cost at M = 64) is spread over >= 64 CTAs.
-int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, cudaStream_t st) {
+static int linear_splits(int n_tiles, int kblocks) {
+    int ks = ceil_div(2 * num_sms(), n_tiles);
+    if (ks > kblocks / 4) ks = kblocks / 4;
+    return ks < 1 ? 1 : ks;
+}
+
+size_t tc_linear_workspace(int M, int K, int N) {
+    const int a = linear_splits(ceil_div(N, 64), K / 32), b = linear_splits(ceil_div(K, 64), N / 32);
+    const size_t fa = (size_t)a * M * N * 4, fb = (size_t)b * M * K * 4;
+    return (fa > fb ? fa : fb) + 256;
+}
+
+int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
     if (K % 32 || N % 8) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_linear_fwd: need K % 32 == 0 and N % 8 == 0");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
@@ -786,14 +855,15 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int 
     Problem q;
     q.src = x; q.N = M; q.Hs = 1; q.Ws = 1; q.Cs = K; q.src_stride = 1;
     q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = false; q.n_tile = 64; q.b_mode_override = 2;
+    q.k_splits = (M <= 128) ? linear_splits(ceil_div(N, 64), K / ((K % 64 == 0) ? 64 : 32)) : 1;
     q.out = y; q.out_f32 = 0; q.out_H = 1; q.out_W = 1; q.n_real = N; q.out_mul = 1;
     q.Jh = 1; q.Jw = 1; q.bias = bias; q.act = act;
-    return launch_igemm(q, p, nullptr, 0, st);
+    return launch_igemm(q, p, ws, ws_bytes, st);
 }
 
 // linear dgrad: dX[M,K] = dY[M,N] Matrix[K,N]^T.  A = dY rows, B = Matrix rows (contraction over N is contiguous:
 // K-major), output columns = K in tiles of 64.
-int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, cudaStream_t st) {
+int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (N % 32 || K % 8) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_linear_dgrad: need N % 32 == 0 and K % 8 == 0");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
@@ -802,9 +872,10 @@ int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N
     Problem q;
     q.src = dy; q.N = M; q.Hs = 1; q.Ws = 1; q.Cs = N; q.src_stride = 1;
     q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = true; q.n_tile = 64; q.b_mode_override = -1;
+    q.k_splits = (M <= 128) ? linear_splits(ceil_div(K, 64), N / ((N % 64 == 0) ? 64 : 32)) : 1;
     q.out = dx; q.out_f32 = 0; q.out_H = 1; q.out_W = 1; q.n_real = K; q.out_mul = 1;
     q.Jh = 1; q.Jw = 1; q.bias = nullptr; q.act = DMV_ACT_NONE;
-    return launch_igemm(q, p, nullptr, 0, st);
+    return launch_igemm(q, p, ws, ws_bytes, st);
 }
 
 // ---- thin-channel layers (3-channel image side of e0, 2-channel side of the flow head) -------------------
@@ -840,7 +911,7 @@ int tc_thin_fwd(const void* thin, int thin_dtype, const void* w, const float* bi
     if (rc) return rc;
     Problem q;
     q.src = base; q.N = N; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Kp; q.src_stride = 1;
-    q.w_hwio = base + Pb; q.kh = 1; q.kw = 1; q.w_ci = Kp; q.w_co = Cw; q.g_form = false; q.n_tile = 0; q.b_mode_override = 3;
+    q.w_hwio = base + Pb; q.kh = 1; q.kw = 1; q.w_ci = Kp; q.w_co = Cw; q.g_form = false; q.n_tile = 0; q.b_mode_override = 3; q.k_splits = 1;
     q.out = out; q.out_f32 = (out_dtype == DMV_DT_F32); q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cw; q.out_mul = 1;
     q.Jh = ph.out; q.Jw = pw.out; q.bias = bias; q.act = act;
     return launch_igemm(q, p, nullptr, 0, st);

@@ -254,8 +254,9 @@ class _Linear(torch.autograd.Function):
         assert wk == K, (wvar.name, wvar.shape, x.shape)
         y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
         _tag[0] = wvar.name
+        ws = workspace(_lib.load().dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), x.device)
         call("dmv_linear_fwd", _p(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), M, K, N, ACT[act],
-             algo, _stream(x))
+             _p(ws), ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
         ctx.cfg = (wvar, bvar, act, algo)
         return y
@@ -283,7 +284,8 @@ class _Linear(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty_like(x)
-            call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, algo, st)
+            ws = workspace(_lib.load().dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), x.device)
+            call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
         ws = workspace(nws, x.device)
         call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,

@@ -165,9 +165,10 @@ int dmv_deconv2d_wgrad(const void* x_bf16, const void* dy, int dy_dtype, float* 
 
 /* replaces tf.matmul(x, Matrix) + b -- linear_msra, tf_utils.py:54-67, and its gradients */
 int dmv_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, void* y_bf16, int M,
-                   int K, int N, int act, int algo, void* stream);
+                   int K, int N, int act, void* workspace, size_t workspace_bytes, int algo,
+                   void* stream);
 int dmv_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int M, int K, int N,
-                     int algo, void* stream);
+                     void* workspace, size_t workspace_bytes, int algo, void* stream);
 int dmv_linear_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, float* db, int M, int K,
                      int N, void* workspace, size_t workspace_bytes, int algo, void* stream);
 
