@@ -62,6 +62,74 @@ struct IgemmParams {
     void* out;
 };
 
+// Epilogue of one accumulator tile for one thread (= one output pixel): TMEM -> registers in 16-column
+// chunks, + bias (shared memory copy when the layer has a single N tile), activation (uniform switch hoisted
+// out of the element loop), NHWC store (bf16 or fp32).
+__device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t taddr, bool ok, long long opix, int ncol0, int ks,
+                                             const float* __restrict__ s_bias) {
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!ok) continue;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+        if (p.bias) {
+            if (s_bias) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] += s_bias[c0 + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (ncol0 + c0 + k < p.n_real) f[k] += __ldg(p.bias + ncol0 + c0 + k);
+            }
+        }
+        switch (p.act) {
+            case DMV_ACT_LRELU:
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = 0.6f * f[k] + 0.4f * fabsf(f[k]);
+                break;
+            case DMV_ACT_RELU:
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = 0.5f * f[k] + 0.5f * fabsf(f[k]);
+                break;
+            case DMV_ACT_TANH:
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = tanhf(f[k]);
+                break;
+            default: break;
+        }
+        if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)ks * p.split_stride + opix * p.n_real + ncol0 + c0;
+            if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 3) == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(o + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+            } else {
+                for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = f[k];
+            }
+        } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + ncol0 + c0;
+            if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
+                uint4 q0, q1;
+                __nv_bfloat162 h;
+                h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[2], f[3]); q0.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[4], f[5]); q0.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[6], f[7]); q0.w = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[8], f[9]); q1.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[10], f[11]); q1.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[12], f[13]); q1.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[14], f[15]); q1.w = *reinterpret_cast<uint32_t*>(&h);
+                reinterpret_cast<uint4*>(o)[0] = q0;
+                reinterpret_cast<uint4*>(o)[1] = q1;
+            } else {
+                for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
+            }
+        }
+    }
+}
+
 template <int KC>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
@@ -77,6 +145,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     uint64_t* tfull_bar = empty_bar + p.stages;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);     // [n_pad], zero padded (single N tile only)
+    if (p.n_tiles == 1)
+        for (int i = threadIdx.x; i < p.n_pad; i += kThreads) s_bias[i] = (p.bias && i < p.n_real) ? __ldg(p.bias + i) : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_cols = 32;
@@ -210,48 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (ok) {
-                    float f[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const int col = ncol0 + c0 + k;
-                        float x = __uint_as_float(v[k]);
-                        if (p.bias && col < p.n_real) x += __ldg(p.bias + col);
-                        f[k] = apply_act(x, p.act);
-                    }
-                    if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out) + (long long)ks * p.split_stride + opix * p.n_real + ncol0 + c0;
-                        if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 3) == 0) {
-#pragma unroll
-                            for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(o + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
-                        } else {
-                            for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = f[k];
-                        }
-                    } else {
-                        bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + ncol0 + c0;
-                        if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
-                            uint4 q0, q1;
-                            __nv_bfloat162 h;
-                            h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[2], f[3]); q0.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[4], f[5]); q0.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[6], f[7]); q0.w = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[8], f[9]); q1.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[10], f[11]); q1.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[12], f[13]); q1.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[14], f[15]); q1.w = *reinterpret_cast<uint32_t*>(&h);
-                            reinterpret_cast<uint4*>(o)[0] = q0;
-                            reinterpret_cast<uint4*>(o)[1] = q1;
-                        } else {
-                            for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
-                        }
-                    }
-                }
-            }
+            epilogue_row(p, taddr, ok, opix, ncol0, ks, p.n_tiles == 1 ? s_bias : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -274,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 // pixel rows further and strides one window row per 8-row core group.  This works because the
 // shared-memory swizzle is a pure function of the address (established with tools/probe), and it cuts
 // the L2 -> SM traffic of a 5x5 layer by ~13x.  All kh*kw weight tiles are loaded once per CTA.
-template <int KC>
+template <int KC, int NT>
 __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_b,
                                                             const __grid_constant__ IgemmParams p) {
@@ -296,6 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     uint64_t* s_bdesc = w_bar + 1;                 // [ntaps] weight-tile descriptors
     uint32_t* s_aoff = reinterpret_cast<uint32_t*>(s_bdesc + kMaxTaps);   // [ntaps] tap offsets (16-byte units)
     uint32_t* tmem_slot = s_aoff + kMaxTaps;
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+    for (int i = threadIdx.x; i < p.n_pad; i += kThreads) s_bias[i] = (p.bias && i < p.n_real) ? __ldg(p.bias + i) : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_cols = 32;
@@ -360,21 +392,37 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            // the issue loop is single-threaded: with a compile-time tap count the descriptors live in registers
+            // and every MMA costs one 64-bit add
+            uint64_t r_b[NT ? NT : 1];
+            uint32_t r_a[NT ? NT : 1];
+            if (NT) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) { r_b[j] = s_bdesc[j]; r_a[j] = s_aoff[j]; }
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_pad);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                // the issue loop is single-threaded: keep it to one add and one shared load per tap
                 const uint64_t a_base = a_tmpl | (uint64_t)((smem_u32(s_a + (size_t)stage * a_stage) & 0x3FFFF) >> 4);
-#pragma unroll 5
-                for (int j = 0; j < ntaps; ++j) {
-                    const uint64_t adesc = a_base + (uint64_t)s_aoff[j];
-                    const uint64_t bdesc = s_bdesc[j];
+                if (NT) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k)
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | k) ? 1u : 0u);
+                    for (int j = 0; j < NT; ++j) {
+                        const uint64_t adesc = a_base + (uint64_t)r_a[j];
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k)
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), r_b[j] + (uint64_t)(2 * k), idesc, (j | k) ? 1u : 0u);
+                    }
+                } else {
+                    for (int j = 0; j < ntaps; ++j) {
+                        const uint64_t adesc = a_base + (uint64_t)s_aoff[j];
+                        const uint64_t bdesc = s_bdesc[j];
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k)
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | k) ? 1u : 0u);
+                    }
                 }
                 tc_commit(&empty_bar[stage]);
                 tc_commit(&tfull_bar[acc]);
@@ -398,42 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (ok) {
-                    float f[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        float x = __uint_as_float(v[k]);
-                        if (p.bias && c0 + k < p.n_real) x += __ldg(p.bias + c0 + k);
-                        f[k] = apply_act(x, p.act);
-                    }
-                    if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out) + opix * p.n_real + c0;
-                        for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = f[k];
-                    } else {
-                        bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + c0;
-                        if (c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
-                            uint4 q0, q1;
-                            __nv_bfloat162 h;
-                            h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[2], f[3]); q0.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[4], f[5]); q0.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[6], f[7]); q0.w = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[8], f[9]); q1.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[10], f[11]); q1.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[12], f[13]); q1.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(f[14], f[15]); q1.w = *reinterpret_cast<uint32_t*>(&h);
-                            reinterpret_cast<uint4*>(o)[0] = q0;
-                            reinterpret_cast<uint4*>(o)[1] = q1;
-                        } else {
-                            for (int k = 0; k < 16 && c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
-                        }
-                    }
-                }
-            }
+            epilogue_row(p, taddr, ok, opix, 0, 0, s_bias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -541,7 +554,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     const int row_bytes = KC * 2;
     // ---- halo eligibility: stride-1 source, one channel chunk, one tap class, one N tile, weights resident
     bool halo_ok = false;
-    int halo_stages = 0;
+    int halo_stages = 0, halo_ctas_per_sm = 1;
     size_t halo_smem = 0;
     if (q.src_stride == 1 && p.num_classes == 1 && p.kc_per_tap == 1 && p.n_tiles == 1 && p.b_mode != 2 && q.out_mul == 1 &&
         q.Jh * q.Jw >= 256 && !getenv("DMV_NO_HALO")) {
@@ -557,9 +570,15 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         const size_t wbytes = (size_t)p.cls[0].tap_count * p.n_pad * row_bytes;
         const size_t a_stage = ((size_t)p.halo_h * p.halo_pitch * row_bytes + 1023) & ~(size_t)1023;
         if (p.halo_pitch <= 256 && p.halo_h <= 256 && wbytes + 2 * a_stage <= 200 * 1024) {
-            halo_stages = (int)((200 * 1024 - wbytes) / a_stage);
+            // two CTAs per SM (the epilogue of one overlaps the MMAs of the other) when the weights leave room
+            if (p.n_pad <= 128 && wbytes + 3 * a_stage <= 104 * 1024) {
+                halo_ctas_per_sm = 2;
+                halo_stages = (int)((104 * 1024 - wbytes) / a_stage);
+            } else {
+                halo_stages = (int)((200 * 1024 - wbytes) / a_stage);
+            }
             if (halo_stages > 6) halo_stages = 6;
-            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8 + kMaxTaps) * sizeof(uint64_t) + kMaxTaps * 4 + 16 + 1024;
+            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8 + kMaxTaps) * sizeof(uint64_t) + kMaxTaps * 4 + 32 + 256 * sizeof(float) + 1024;
             halo_ok = true;
             // the halo kernel tiles the image 8 wide x 16 tall, one image per tile
             p.BW = 8; p.BH = 16; p.NB = 1; p.rows = 128;
@@ -629,16 +648,21 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         int rc = encode_map(&map_h, q.src, 5, dims, strides, box, row_bytes);
         if (rc) return rc;
         p.stages = halo_stages;
-        int grid = num_sms();
+        int grid = num_sms() * halo_ctas_per_sm;
         if (grid > p.tiles_per_class) grid = p.tiles_per_class;
-        cudaError_t e;
+        cudaError_t e = cudaSuccess;
+        const int nt = p.cls[0].tap_count;
+#define DMV_LAUNCH_HALO(KCV, NTV)                                                                                          \
+    do {                                                                                                                   \
+        e = cudaFuncSetAttribute(halo_kernel<KCV, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem);      \
+        if (e == cudaSuccess) halo_kernel<KCV, NTV><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);                  \
+    } while (0)
         if (KC == 64) {
-            e = cudaFuncSetAttribute(halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem);
-            if (e == cudaSuccess) halo_kernel<64><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);
+            if (nt == 25) DMV_LAUNCH_HALO(64, 25); else if (nt == 9) DMV_LAUNCH_HALO(64, 9); else DMV_LAUNCH_HALO(64, 0);
         } else {
-            e = cudaFuncSetAttribute(halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem);
-            if (e == cudaSuccess) halo_kernel<32><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);
+            if (nt == 25) DMV_LAUNCH_HALO(32, 25); else if (nt == 9) DMV_LAUNCH_HALO(32, 9); else DMV_LAUNCH_HALO(32, 0);
         }
+#undef DMV_LAUNCH_HALO
         if (e != cudaSuccess) {
             set_error("tc halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return DMV_E_CUDA;
@@ -674,7 +698,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 32 + 256 * sizeof(float) + 1024;
     const int total_tiles = p.num_classes * p.tiles_per_class * p.n_tiles * p.k_splits;
     int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > total_tiles) grid = total_tiles;
