@@ -16,17 +16,42 @@
 //
 // HBM-bound: algorithmic bytes per output pixel are 8 + 8C (fwd), 16 + 8C (grad_warp only),
 // 8 + 8C (grad_data pass).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
 using namespace dmv;
 
+// tuning knobs (tools/sampler_variants.sh sweeps them; the defaults are the measured best)
+#ifndef SAMPLER_MINBLOCKS
+#define SAMPLER_MINBLOCKS 5
+#endif
+#ifndef SAMPLER_CPASYNC
+#define SAMPLER_CPASYNC 16     // 0: ld.global + st.shared, 4: cp.async 4-byte, 16: cp.async 16-byte on an aligned window
+#endif
+#ifndef SAMPLER_PREREDUCE
+#define SAMPLER_PREREDUCE 1   // reduce the tap box over a thread's pixels before the warp reduction
+#endif
+#ifndef SAMPLER_STAGE_KB
+#define SAMPLER_STAGE_KB 40
+#endif
+#ifndef SAMPLER_TMA
+#define SAMPLER_TMA 1          // route image-shaped C in {1,3,4} calls to sampler_tma_kernel
+#endif
+#ifndef SAMPLER_TMA_MINBLOCKS
+#define SAMPLER_TMA_MINBLOCKS 5
+#endif
+#ifndef SAMPLER_BOX
+#define SAMPLER_BOX 40         // source window box of the TMA kernel, pixels per side
+#endif
+#ifndef SAMPLER_BOX_L
+#define SAMPLER_BOX_L 48       // second, larger box tried when the tap box does not fit the first
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTilePix = 1024;
 constexpr int kPPT = kTilePix / kThreads;  // pixels per thread
-constexpr int kStageFloats = 10240;        // 40 KB source window
+constexpr int kStageFloats = SAMPLER_STAGE_KB * 256;   // source window in floats
 constexpr int kSrcTileW = 32, kSrcTileH = 16;
 
 struct Geom {
@@ -91,8 +116,16 @@ __device__ __forceinline__ void reduce_box(int* s_box, bool valid, int fx, int f
 }
 
 // MODE 0: forward.  MODE 1: grad wrt warp/flow.
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int CT, int MODE>
-__global__ void __launch_bounds__(kThreads) sampler_tile_kernel(
+__global__ void __launch_bounds__(kThreads, SAMPLER_MINBLOCKS) sampler_tile_kernel(
     const float* __restrict__ data, const float* __restrict__ wf, const float* __restrict__ grad_out,
     float* __restrict__ out, int32_t* __restrict__ dbg_idx, uint8_t* __restrict__ dbg_mask, Geom g) {
     extern __shared__ float s_win[];
@@ -108,6 +141,9 @@ __global__ void __launch_bounds__(kThreads) sampler_tile_kernel(
     int pi[kPPT], pj[kPPT];
     bool inb[kPPT];
     const int tw_mask = (1 << g.tw_shift) - 1;
+#if SAMPLER_PREREDUCE
+    int bxlo = 0x7fffffff, bxhi = -0x7fffffff, bylo = 0x7fffffff, byhi = -0x7fffffff;
+#endif
 #pragma unroll
     for (int k = 0; k < kPPT; ++k) {
         const int p = k * kThreads + tid;
@@ -119,22 +155,56 @@ __global__ void __launch_bounds__(kThreads) sampler_tile_kernel(
         if (inb[k]) smp[k] = load_sample(wf, g, b, pi[k], pj[k]);
         const int fx = smp[k].valid ? (int)floorf(smp[k].x) : 0;
         const int fy = smp[k].valid ? (int)floorf(smp[k].y) : 0;
+#if SAMPLER_PREREDUCE
+        if (smp[k].valid) {
+            bxlo = min(bxlo, max(fx, 0)); bxhi = max(bxhi, min(fx + 1, g.W - 1));
+            bylo = min(bylo, max(fy, 0)); byhi = max(byhi, min(fy + 1, g.H - 1));
+        }
+#else
         reduce_box(s_box, smp[k].valid, fx, fy, g.W, g.H);
+#endif
     }
+#if SAMPLER_PREREDUCE
+    bxlo = __reduce_min_sync(0xffffffffu, bxlo); bxhi = __reduce_max_sync(0xffffffffu, bxhi);
+    bylo = __reduce_min_sync(0xffffffffu, bylo); byhi = __reduce_max_sync(0xffffffffu, byhi);
+    if ((tid & 31) == 0) {
+        atomicMin(&s_box[0], bxlo); atomicMax(&s_box[1], bxhi);
+        atomicMin(&s_box[2], bylo); atomicMax(&s_box[3], byhi);
+    }
+#endif
     __syncthreads();
     const int xmin = s_box[0], xmax = s_box[1], ymin = s_box[2], ymax = s_box[3];
     const bool any_valid = xmin <= xmax;
     const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
+#if SAMPLER_CPASYNC == 16
+    // window start rounded down to 16 bytes (rows are 16-byte aligned when W*C % 4 == 0); pitch = 4 mod 8 floats
+    const bool vec16 = (((g.W * C) & 3) == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
+    const int a0 = vec16 ? ((xmin * C) & ~3) : xmin * C;
+    const int seg = vec16 ? ((((xmax + 1) * C - a0) + 3) & ~3) : (nx * C);
+    const int pitch = vec16 ? (seg | 4) : (seg | 1);
+#else
+    const int a0 = xmin * C;
     const int seg = nx * C;
     const int pitch = seg | 1;  // odd pitch: a column read by 32 lanes hits 32 banks
+#endif
     const bool staged = any_valid && ((long long)ny * pitch <= kStageFloats);
     if (staged) {
         const int warp = tid >> 5, lane = tid & 31;
         for (int r = warp; r < ny; r += kWarps) {
-            const float* src = data + (((long long)b * g.H + ymin + r) * g.W + xmin) * C;
+            const float* src = data + ((long long)b * g.H + ymin + r) * g.W * C + a0;
             float* dst = s_win + r * pitch;
+#if SAMPLER_CPASYNC == 16
+            if (vec16) { for (int e = lane * 4; e < seg; e += 128) cp_async16(dst + e, src + e); }
+            else { for (int e = lane; e < seg; e += 32) cp_async4(dst + e, src + e); }
+#elif SAMPLER_CPASYNC == 4
+            for (int e = lane; e < seg; e += 32) cp_async4(dst + e, src + e);
+#else
             for (int e = lane; e < seg; e += 32) dst[e] = __ldg(src + e);
+#endif
         }
+#if SAMPLER_CPASYNC
+        cp_async_wait_all();
+#endif
     }
     __syncthreads();
 
@@ -169,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) sampler_tile_kernel(
         const float* base;
         if (staged) {
             base = s_win;
-            o_ff = (long long)(fy - ymin) * pitch + (fx - xmin) * C;
+            o_ff = (long long)(fy - ymin) * pitch + (fx * C - a0);
             o_cf = o_ff + C;
             o_fc = o_ff + pitch;
             o_cc = o_fc + C;
@@ -205,6 +275,193 @@ __global__ void __launch_bounds__(kThreads) sampler_tile_kernel(
         }
         if (MODE == 1) reinterpret_cast<float2*>(out)[opix] = s.valid ? make_float2(gw0, gw1) : make_float2(0.f, 0.f);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA kernel: the training-path form of forward / grad_warp for image-shaped outputs with C in
+// {1,3,4} and 16-byte aligned rows.  Same arithmetic (same bits) as sampler_tile_kernel, but all bulk
+// movement is done by the TMA engine so the LSU pipe only carries the flow loads and the tap gathers:
+//   * the SOURCE WINDOW of the tile (tap bounding box, reduced from the flow) is one
+//     cp.async.bulk.tensor box load in EXTENDED coordinates: the box may start at x = -1 / y = -1
+//     and run past W / H, and TMA's out-of-bounds zero fill is exactly the resampler's one-pixel zero
+//     border -- taps need no in-range predicates (w * 0 = +0 leaves the sum's bits unchanged);
+//   * MODE 0 writes its results to a shared tile that one bulk tensor STORE sends to global (ragged
+//     edges are clipped by the tensor map); MODE 1 receives grad_out the same way (bulk load);
+//   * lanes own consecutive pixels of a row: scalar LDS/STS at stride C are bank-conflict-free for
+//     smooth flows, flow loads / grad_flow stores are coalesced 8-byte accesses.
+constexpr int kBoxS = SAMPLER_BOX, kBoxL = SAMPLER_BOX_L;   // source window box (pixels); tap boxes beyond the larger one fall back to global gathers
+
+template <int C, int MODE>
+__global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_kernel(
+    const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_src_l,
+    const __grid_constant__ CUtensorMap map_io, const float* __restrict__ data, const float* __restrict__ wf, float* __restrict__ out,
+    int32_t* __restrict__ dbg_idx, uint8_t* __restrict__ dbg_mask, Geom g) {
+    extern __shared__ __align__(128) float s_dyn[];
+    float* s_win = s_dyn;                              // [box][box * C], box = kBoxS or kBoxL
+    float* s_io = s_dyn + kBoxL * kBoxL * C;           // [32][32 * C]: MODE 0 results, MODE 1 grad_out
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_box[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int b, i0, j0;
+    tile_origin(g, blockIdx.x, b, i0, j0);
+    if (tid < 4) s_box[tid] = (tid & 1) ? -0x7fffffff : 0x7fffffff;
+    if (tid == 0) {
+        tc::mbar_init(&s_bar[0], 1);
+        tc::mbar_init(&s_bar[1], 1);
+        tc::fence_barrier_init();
+        tc::fence_proxy_async();
+        if (MODE == 1) {
+            tc::mbar_expect_tx(&s_bar[1], 32 * 32 * C * 4);
+            tc::tma_load_3d(s_io, &map_io, &s_bar[1], j0 * C, i0, b);
+        }
+    }
+    __syncthreads();
+
+    const int j = j0 + lane;
+    float sx[kPPT], sy[kPPT];
+    bool valid[kPPT];
+    int fx[kPPT], fy[kPPT];
+    int bxlo = 0x7fffffff, bxhi = -0x7fffffff, bylo = 0x7fffffff, byhi = -0x7fffffff;
+    const float fW = (float)g.W, fH = (float)g.H;
+    const long long img_pix = (long long)b * g.Ho * g.Wo;
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+        const int i = i0 + warp + k * kWarps;
+        const bool inb = (i < g.Ho) && (j < g.Wo);
+        float2 f = make_float2(0.f, 0.f);
+        if (inb) f = __ldg(reinterpret_cast<const float2*>(wf) + img_pix + (long long)i * g.Wo + j);
+        sx[k] = f.x; sy[k] = f.y;
+        if (g.flags & DMV_SAMPLER_ADD_GRID) {
+            if (g.flags & DMV_SAMPLER_GRID_XY) {
+                sx[k] = __fadd_rn(f.x, (float)j);
+                sy[k] = __fadd_rn(f.y, (float)i);
+            } else {
+                sx[k] = __fadd_rn(f.x, (float)i);
+                sy[k] = __fadd_rn(f.y, (float)j);
+            }
+        }
+        valid[k] = inb && (sx[k] > -1.0f) && (sy[k] > -1.0f) && (sx[k] < fW) && (sy[k] < fH);
+        fx[k] = valid[k] ? __float2int_rd(sx[k]) : 0;
+        fy[k] = valid[k] ? __float2int_rd(sy[k]) : 0;
+        if (valid[k]) {
+            bxlo = min(bxlo, fx[k]); bxhi = max(bxhi, fx[k] + 1);
+            bylo = min(bylo, fy[k]); byhi = max(byhi, fy[k] + 1);
+        }
+    }
+    bxlo = __reduce_min_sync(0xffffffffu, bxlo); bxhi = __reduce_max_sync(0xffffffffu, bxhi);
+    bylo = __reduce_min_sync(0xffffffffu, bylo); byhi = __reduce_max_sync(0xffffffffu, byhi);
+    if (lane == 0) {
+        atomicMin(&s_box[0], bxlo); atomicMax(&s_box[1], bxhi);
+        atomicMin(&s_box[2], bylo); atomicMax(&s_box[3], byhi);
+    }
+    __syncthreads();
+    // tap box in EXTENDED coordinates (-1 .. W, -1 .. H)
+    const int xlo = s_box[0], xhi = s_box[1], ylo = s_box[2], yhi = s_box[3];
+    const bool any_valid = xlo <= xhi;
+    // the box must start on a 16-byte boundary of the row: x origin floored to 4 pixels unless C == 4 (-1 -> -4)
+    const int xa = (C == 4) ? xlo : (xlo & ~3);
+    const int span = max(xhi - xa, yhi - ylo);
+    const bool staged = any_valid && (span < kBoxL);
+    const int box = (span < kBoxS) ? kBoxS : kBoxL;   // smallest box that holds the taps
+    const int kPitch = box * C;
+    if (staged) {
+        if (tid == 0) {
+            tc::mbar_expect_tx(&s_bar[0], box * box * C * 4);
+            tc::tma_load_3d(s_win, span < kBoxS ? &map_src : &map_src_l, &s_bar[0], xa * C, ylo, b);
+        }
+        tc::mbar_wait(&s_bar[0], 0);
+    }
+    if (MODE == 1) tc::mbar_wait(&s_bar[1], 0);
+
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+        const int r = warp + k * kWarps;              // row of the tile
+        const int i = i0 + r;
+        const bool inb = (i < g.Ho) && (j < g.Wo);
+        const int cx = fx[k] + 1, cy = fy[k] + 1;
+        const float dx = valid[k] ? __fsub_rn((float)cx, sx[k]) : 0.f;
+        const float dy = valid[k] ? __fsub_rn((float)cy, sy[k]) : 0.f;
+        if (MODE == 0 && (dbg_idx || dbg_mask) && inb) {
+            const long long opix = img_pix + (long long)i * g.Wo + j;
+            unsigned mask = 0;
+            if (valid[k]) {
+                const bool fxi = fx[k] >= 0, cxi = cx <= g.W - 1, fyi = fy[k] >= 0, cyi = cy <= g.H - 1;
+                mask = 1u | ((fxi && fyi) ? 2u : 0u) | ((cxi && cyi) ? 4u : 0u) | ((fxi && cyi) ? 8u : 0u) |
+                       ((cxi && fyi) ? 16u : 0u);
+            }
+            if (dbg_idx) reinterpret_cast<int4*>(dbg_idx)[opix] = valid[k] ? make_int4(fx[k], fy[k], cx, cy) : make_int4(0, 0, 0, 0);
+            if (dbg_mask) dbg_mask[opix] = (uint8_t)mask;
+        }
+        const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
+        float p_ff[C], p_cc[C], p_fc[C], p_cf[C];
+        if (staged) {
+            const float* t = s_win + (valid[k] ? (fy[k] - ylo) * kPitch + (fx[k] - xa) * C : 0);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                p_ff[c] = t[c]; p_cf[c] = t[C + c]; p_fc[c] = t[kPitch + c]; p_cc[c] = t[kPitch + C + c];
+            }
+        } else {  // tap box larger than the window: predicated gathers from global (L1/L2)
+            const bool fxi = fx[k] >= 0, cxi = cx <= g.W - 1, fyi = fy[k] >= 0, cyi = cy <= g.H - 1;
+            const float* base = data + (((long long)b * g.H + fy[k]) * g.W + fx[k]) * C;
+            const int rowf = g.W * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                p_ff[c] = (valid[k] && fxi && fyi) ? __ldg(base + c) : 0.f;
+                p_cf[c] = (valid[k] && cxi && fyi) ? __ldg(base + C + c) : 0.f;
+                p_fc[c] = (valid[k] && fxi && cyi) ? __ldg(base + rowf + c) : 0.f;
+                p_cc[c] = (valid[k] && cxi && cyi) ? __ldg(base + rowf + C + c) : 0.f;
+            }
+        }
+        float* io = s_io + (r * 32 + lane) * C;
+        if (MODE == 0) {
+            const float w_ff = __fmul_rn(dx, dy), w_cc = __fmul_rn(omdx, omdy), w_fc = __fmul_rn(dx, omdy),
+                        w_cf = __fmul_rn(omdx, dy);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float v = __fmul_rn(w_ff, p_ff[c]);
+                v = __fadd_rn(v, __fmul_rn(w_cc, p_cc[c]));
+                v = __fadd_rn(v, __fmul_rn(w_fc, p_fc[c]));
+                v = __fadd_rn(v, __fmul_rn(w_cf, p_cf[c]));
+                io[c] = valid[k] ? v : 0.f;
+            }
+        } else {
+            float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float gc = io[c];
+                const float a0 = __fadd_rn(__fmul_rn(omdy, __fsub_rn(p_cc[c], p_fc[c])), __fmul_rn(dy, __fsub_rn(p_cf[c], p_ff[c])));
+                const float a1 = __fadd_rn(__fmul_rn(omdx, __fsub_rn(p_cc[c], p_cf[c])), __fmul_rn(dx, __fsub_rn(p_fc[c], p_ff[c])));
+                g0 = __fadd_rn(g0, __fmul_rn(gc, a0));
+                g1 = __fadd_rn(g1, __fmul_rn(gc, a1));
+            }
+            if (inb) reinterpret_cast<float2*>(out)[img_pix + (long long)i * g.Wo + j] = valid[k] ? make_float2(g0, g1) : make_float2(0.f, 0.f);
+        }
+    }
+    if (MODE == 0) {
+        tc::fence_proxy_async();          // generic-proxy writes of s_io -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            tc::tma_store_3d(&map_io, s_io, j0 * C, i0, b);
+            tc::bulk_commit_wait_read();  // the tile must stay in shared memory until the store has read it
+        }
+    }
+}
+
+int encode_f32_map(CUtensorMap* map, const float* base, int inner, int rows, int batch, int box_inner, int box_rows) {
+    tc::EncodeTiledFn enc = tc::get_encode();
+    if (!enc) return fail(DMV_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    tc::bind_context();
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * 4 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("sampler: cuTensorMapEncodeTiled failed (%d) dims %d %d %d box %d %d", (int)r, inner, rows, batch, box_inner, box_rows);
+        return DMV_E_CUDA;
+    }
+    return DMV_OK;
 }
 
 // Pre-pass of grad_data: tap box of every output tile.
@@ -340,6 +597,32 @@ template <int MODE>
 int launch_tile(const float* data, const float* wf, const float* go, float* out, int32_t* di, uint8_t* dm,
                 const Geom& g, cudaStream_t st) {
     const int grid = g.B * g.tiles_x * g.tiles_y;
+    const bool aligned = (((uintptr_t)data | (uintptr_t)wf | (uintptr_t)go | (uintptr_t)out) & 15) == 0;
+    if (SAMPLER_TMA && g.tw_shift == 5 && (g.C == 1 || g.C == 3 || g.C == 4) && ((g.W * g.C) & 3) == 0 && ((g.Wo * g.C) & 3) == 0 &&
+        aligned && (!di || ((uintptr_t)di & 15) == 0)) {
+        CUtensorMap map_src, map_src_l, map_io;
+        int rc = encode_f32_map(&map_src, data, g.W * g.C, g.H, g.B, kBoxS * g.C, kBoxS);
+        if (rc) return rc;
+        rc = encode_f32_map(&map_src_l, data, g.W * g.C, g.H, g.B, kBoxL * g.C, kBoxL);
+        if (rc) return rc;
+        rc = encode_f32_map(&map_io, MODE == 0 ? out : go, g.Wo * g.C, g.Ho, g.B, 32 * g.C, 32);
+        if (rc) return rc;
+        const size_t wsm = (size_t)(kBoxL * kBoxL + 32 * 32) * g.C * sizeof(float);
+#define DMV_LAUNCH_TMA(CT)                                                                               \
+    do {                                                                                                 \
+        static bool attr_done = false;                                                                   \
+        if (!attr_done) {                                                                                \
+            cudaFuncSetAttribute(sampler_tma_kernel<CT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm); \
+            attr_done = true;                                                                            \
+        }                                                                                                \
+        sampler_tma_kernel<CT, MODE><<<grid, kThreads, wsm, st>>>(map_src, map_src_l, map_io, data, wf, out, di, dm, g); \
+    } while (0)
+        if (g.C == 1) DMV_LAUNCH_TMA(1);
+        else if (g.C == 3) DMV_LAUNCH_TMA(3);
+        else DMV_LAUNCH_TMA(4);
+#undef DMV_LAUNCH_TMA
+        return check_launch(MODE == 0 ? "sampler_fwd(tma)" : "sampler_grad_warp(tma)");
+    }
     const size_t smem = kStageFloats * sizeof(float);
 #define DMV_LAUNCH_TILE(CT)                                                                              \
     do {                                                                                                 \

@@ -70,12 +70,14 @@ def test_golden_vectors(golden_dir):
     assert np.array_equal(rxy["out"], g["quirk_img"])
 
 
+# W = 70: rows are not 16-byte multiples -> generic tile kernel; W = 72: the TMA kernel for C in {1,3,4}
+@pytest.mark.parametrize("geom", [(45, 70, 37, 51), (45, 72, 37, 52)])
 @pytest.mark.parametrize("C", [1, 2, 3, 4, 6])
 @pytest.mark.parametrize("regime", ["jitter", "rotation", "absolute", "boundary"])
-def test_parity_regimes(C, regime):
-    rng = np.random.default_rng(hash((C, regime)) % 2**31)
-    B, H, W = 3, 45, 70                                     # ragged: not multiples of the 32x32 tile
-    Ho, Wo = (H, W) if regime != "absolute" else (37, 51)
+def test_parity_regimes(C, regime, geom):
+    rng = np.random.default_rng((C * 7919 + len(regime) * 104729 + geom[1]) % 2**31)
+    B, H, W = 3, geom[0], geom[1]                           # ragged: not multiples of the 32x32 tile
+    Ho, Wo = (H, W) if regime != "absolute" else geom[2:]
     data = rng.random((B, H, W, C), dtype=np.float32)
     ii, jj = np.meshgrid(np.arange(Ho, dtype=np.float32), np.arange(Wo, dtype=np.float32), indexing="ij")
     if regime == "jitter":          # training regime at init: identity + U(-3,3), XY order so H != W works

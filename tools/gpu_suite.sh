@@ -8,7 +8,7 @@ what=${1:-all}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
 if [[ $what == all || $what == tests ]]; then
-  for f in test_sampler_gpu test_layers_gpu test_model_gpu; do
+  for f in test_sampler_gpu test_layers_gpu test_tc_gpu test_model_gpu; do
     timeout 900 python -m pytest tests/$f.py -m gpu -q -x --tb=short > gpurun_out/$f.log 2>&1
     echo "$f exit $?" | tee -a gpurun_out/summary.txt
     tail -5 gpurun_out/$f.log
@@ -28,4 +28,10 @@ if [[ $what == all || $what == ncu ]]; then
   timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/bench_short.json 2>&1 &&
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?" | tee -a gpurun_out/summary.txt
+  # dominant kernel of the step (Adam) + the tensor-core kernels, one --set full capture each
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:adam_multi -c 1 -f -o gpurun_out/adam_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-micro --eager > gpurun_out/ncu_adam.log 2>&1
+  echo "ncu adam exit $?" | tee -a gpurun_out/summary.txt
+  timeout 300 python tools/prof_conv.py > gpurun_out/prof_conv_plain.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"halo_kernel|wgrad_kernel|igemm_kernel" -c 8 -f -o gpurun_out/conv_prof python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1
+  echo "ncu conv exit $?" | tee -a gpurun_out/summary.txt
 fi

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds sampler.cu with different tuning knobs into tools/variants/*.so (run HERE), prints the list.
+set -e
+cd "$(dirname "$0")/.."
+mkdir -p tools/variants
+rm -f tools/variants/*.so
+CS=dynamic_multiview_3d_b200/csrc
+while read -r name flags; do
+  [ -z "$name" ] && continue
+  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $flags -shared -o tools/variants/$name.so $CS/sampler.cu $CS/api.cu &
+done <<LIST
+a_tile -DSAMPLER_TMA=0
+tma_40_48_mb5 -DSAMPLER_TMA_MINBLOCKS=5
+tma_40_56_mb4 -DSAMPLER_TMA_MINBLOCKS=4 -DSAMPLER_BOX_L=56
+tma_40_40_mb5 -DSAMPLER_TMA_MINBLOCKS=5 -DSAMPLER_BOX_L=40
+tma_40_40_mb6 -DSAMPLER_TMA_MINBLOCKS=6 -DSAMPLER_BOX_L=40
+LIST
+wait
+ls tools/variants
