@@ -6,6 +6,10 @@
 #include <stddef.h>
 
 namespace dmv {
+// out[i] = sum_z part[z * n + i], deterministic: warp w of a CTA sums z = w, w + ZW, ... in order, then the ZW
+// warp sums are added in warp order.  The z loop is spread over up to 32 warps so short outputs (bias
+// gradients: n = C) are not one long dependent chain.
+int reduce_partials(const float* part, float* out, long long n, int splits, cudaStream_t st);
 size_t simt_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
 size_t act_bwd_bias_workspace(long long rows, int C);
 int act_bwd_bias(const void* dy, const void* y, void* dpre, float* db, long long rows, int C, int act, void* ws, size_t ws_bytes,

@@ -15,6 +15,7 @@
 // W is a deterministic split-K: partial tiles go to the workspace and a second kernel adds
 // them in split order.
 #include "common.cuh"
+#include "conv_impl.h"
 
 namespace {
 using namespace dmv;
@@ -194,12 +195,29 @@ __global__ void __launch_bounds__(256) conv_w_kernel(const TBig* __restrict__ Bi
     if (ci_b < g.Cin && co_b < g.Cout) out[(long long)ci_b * g.Cout + co_b] = a11;
 }
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int splits) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += part[(long long)z * n + i];
-        out[i] = s;
+template <int ZW>
+__global__ void __launch_bounds__(32 * ZW) reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
+                                                                   int splits) {
+    __shared__ float red[ZW][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < n) {
+        int z = w;
+        for (; z + 3 * ZW < splits; z += 4 * ZW) {      // four independent loads in flight, added in z order
+            const float a = part[(long long)z * n + i], b = part[(long long)(z + ZW) * n + i];
+            const float c = part[(long long)(z + 2 * ZW) * n + i], d = part[(long long)(z + 3 * ZW) * n + i];
+            s0 += a; s1 += b; s2 += c; s3 += d;
+        }
+        for (; z < splits; z += ZW) s0 += part[(long long)z * n + i];
+    }
+    red[w][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < ZW; ++k) t += red[k][lane];
+        out[i] = t;
     }
 }
 
@@ -226,7 +244,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ Y, fl
 // dpre = dy * act'(y) fused with the bias gradient db[c] = sum_rows dpre[row][c]  (bf16 [rows][C], C % 8 == 0).
 // CTA = (CGB column groups of 8 channels) x (256/CGB row lanes) over a contiguous row range; grid.x tiles the
 // columns, grid.y the rows.  Four rows are in flight per thread.  CTA partials are summed in grid.y order by
-// splitk_reduce_kernel (deterministic).
+// reduce_partials (deterministic).
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dpre,
                                                             float* __restrict__ part, long long rows, int C8, int cgb, long long rows_per_cta,
                                                             int act) {
@@ -332,9 +350,8 @@ int run_wgrad(const TBig* big, const TSm* sm, float* dw, const ConvGeom& g, void
     int rc = check_launch("conv_wgrad_simt");
     if (rc) return rc;
     long long blocks = ceil_div_ll(n, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, dw, n, p.splits);
-    return check_launch("splitk_reduce");
+    (void)blocks;
+    return reduce_partials(part, dw, n, p.splits, st);
 }
 
 template <typename T>
@@ -349,8 +366,7 @@ int run_colsum(const T* y, float* db, long long pixels, int C, void* ws, size_t 
     colsum_kernel<T><<<grid, 256, 0, st>>>(y, part, pixels, C, chunk);
     int rc = check_launch("colsum");
     if (rc) return rc;
-    splitk_reduce_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, db, C, (int)splits);
-    return check_launch("colsum_reduce");
+    return reduce_partials(part, db, C, (int)splits, st);
 }
 
 template <typename TX, typename TY>
@@ -373,6 +389,15 @@ int run_g(const void* s, const void* w, void* b, const ConvGeom& g, int act, cud
 // ------------------------------------------------------------------ SIMT entry points
 // (called by the public dispatchers in conv_api.cu)
 namespace dmv {
+
+int reduce_partials(const float* part, float* out, long long n, int splits, cudaStream_t st) {
+    const long long blocks = ceil_div_ll(n, 32);
+    // few columns: spread z over many warps; many columns: enough CTAs already, keep the chains per thread short anyway
+    if (blocks >= 148 * 8 || splits <= 8) reduce_partials_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(part, out, n, splits);
+    else if (blocks >= 148 || splits <= 32) reduce_partials_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(part, out, n, splits);
+    else reduce_partials_kernel<32><<<(unsigned)blocks, 1024, 0, st>>>(part, out, n, splits);
+    return check_launch("reduce_partials");
+}
 
 size_t act_bwd_bias_workspace(long long rows, int C) {
     (void)rows;
@@ -399,8 +424,7 @@ int act_bwd_bias(const void* dy, const void* y, void* dpre, float* db, long long
     act_bwd_bias_kernel<<<grid, 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dpre, part, rows, C8, cgb, per, act);
     int rc = check_launch("act_bwd_bias");
     if (rc) return rc;
-    splitk_reduce_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, db, C, (int)row_ctas);
-    return check_launch("act_bwd_bias reduce");
+    return reduce_partials(part, db, C, (int)row_ctas, st);
 }
 
 int simt_bias_grad(const void* dy_bf16, float* db, long long pixels, int C, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -174,15 +174,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     }
 }
 
-__global__ void slice_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int slices) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float s = 0.f;
-        for (int z = 0; z < slices; ++z) s += part[(long long)z * n + i];
-        out[i] = s;
-    }
-}
-
 // pixel chunk box: rows = BW*BH*NB a multiple of 16, <= max_rows, maximising the useful fraction
 void choose_chunk(int Jh, int Jw, int N, int max_rows, int& BW, int& BH, int& NB) {
     double best = -1.0;
@@ -315,10 +306,7 @@ int run_wgrad(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
     int rc = check_launch("wgrad_tc");
     if (rc) return rc;
     if (p.slices > 1) {
-        long long blocks = ceil_div_ll(p.out_elems, 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        slice_reduce_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(ws), q.dw, p.out_elems, p.slices);
-        rc = check_launch("wgrad_tc reduce");
+        rc = reduce_partials(reinterpret_cast<const float*>(ws), q.dw, p.out_elems, p.slices, st);
     }
     return rc;
 }
