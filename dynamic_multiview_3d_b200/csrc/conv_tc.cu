@@ -56,6 +56,7 @@ struct IgemmParams {
     int k_splits;                 // linear layers: the contraction is cut into k_splits ranges (fp32 partials + finish kernel)
     long long split_stride;       // elements between the partial outputs of consecutive splits
     int halo_pitch, halo_h, min_dh, min_dw;   // halo kernel: window rows x pitch pixels, origin offset of the window
+    int d2s, d2s_c;               // sub-pixel form: column (class, c) of a tile row goes to output pixel (2*jh + py, 2*jw + px), channel c
     TapClass cls[4];
     Tap taps[kMaxTaps];
     const float* bias;
@@ -125,6 +126,70 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t tadd
                 reinterpret_cast<uint4*>(o)[1] = q1;
             } else {
                 for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) o[k] = __float2bfloat16_rn(f[k]);
+            }
+        }
+    }
+}
+
+// Sub-pixel epilogue (stride-2 G forms run as ONE stride-1 problem, see launch_subpixel): the accumulator row of
+// class-grid pixel (jh, jw) holds 4 x C columns (class-major); class (py, px) goes to output pixel (2jh + py, 2jw + px).
+__device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t taddr, bool row_ok, int n, int jh, int jw) {
+    const int C = p.d2s_c;
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!row_ok || c0 >= 4 * C) continue;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+        switch (p.act) {
+            case DMV_ACT_LRELU:
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = 0.6f * f[k] + 0.4f * fabsf(f[k]);
+                break;
+            case DMV_ACT_RELU:
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = 0.5f * f[k] + 0.5f * fabsf(f[k]);
+                break;
+            case DMV_ACT_TANH:
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = tanhf(f[k]);
+                break;
+            default: break;
+        }
+        if ((C & 15) == 0) {          // the 16 columns belong to one class
+            const int cls = c0 / C, cc = c0 - cls * C;
+            const int oy = 2 * jh + (cls >> 1), ox = 2 * jw + (cls & 1);
+            if (oy >= p.out_H || ox >= p.out_W) continue;
+            const long long o = (((long long)n * p.out_H + oy) * p.out_W + ox) * C + cc;
+            if (p.out_f32) {
+                float* q = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(q + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+            } else {
+                uint4 q0, q1;
+                __nv_bfloat162 h;
+                h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[2], f[3]); q0.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[4], f[5]); q0.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[6], f[7]); q0.w = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[8], f[9]); q1.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[10], f[11]); q1.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[12], f[13]); q1.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2bfloat162_rn(f[14], f[15]); q1.w = *reinterpret_cast<uint32_t*>(&h);
+                uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + o);
+                q[0] = q0;
+                q[1] = q1;
+            }
+        } else {                      // thin heads (C = 2 flow channels): element-wise
+            for (int k = 0; k < 16 && c0 + k < 4 * C; ++k) {
+                const int cls = (c0 + k) / C, cc = (c0 + k) - cls * C;
+                const int oy = 2 * jh + (cls >> 1), ox = 2 * jw + (cls & 1);
+                if (oy >= p.out_H || ox >= p.out_W) continue;
+                const long long o = (((long long)n * p.out_H + oy) * p.out_W + ox) * C + cc;
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = f[k];
+                else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(f[k]);
             }
         }
     }
@@ -446,7 +511,8 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            epilogue_row(p, taddr, ok, opix, 0, 0, s_bias);
+            if (p.d2s) epilogue_row_d2s(p, taddr, (oy < p.Jh) && (ox < p.Jw), n, oy, ox);
+            else epilogue_row(p, taddr, ok, opix, 0, 0, s_bias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -588,6 +654,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
             p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
         }
     }
+    if (p.d2s && !halo_ok) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc subpixel: shape not covered by the halo kernel");
     // ---- A map: 5-D (C', W', P, H', N)
     CUtensorMap map_a, map_b;
     {
@@ -728,6 +795,54 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     return DMV_OK;
 }
 
+// ---- sub-pixel form of the stride-2 G problems (deconv fwd, conv dgrad) ---------------------------------
+// The four output-parity classes of a stride-2 transposed convolution read the SAME stride-1 source through
+// the same few shifts (3 x 3 for a 5 x 5 kernel, 2 x 2 for 3 x 3).  Concatenating the classes along N turns the
+// layer into one stride-1 convolution with S shifts and 4 * C output columns whose weight matrix is the
+// reference weights scattered by (shift, class) -- zero where a class has no tap at that shift -- followed by a
+// depth-to-space store.  One halo load then serves all taps (the per-tap form re-reads the source kh * kw
+// times from L2 and is bound by it), and the MMA N grows from C to 4 C.
+struct SubpixelTable {
+    int S;
+    short dh[16], dw[16];
+    int tap[4][16];      // reference tap id r * kw + s of (class, shift), -1: none
+};
+
+__global__ void pack_subpixel_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int n_real, int Cs, int n_rows, SubpixelTable t) {
+    const long long K = (long long)t.S * Cs, total = (long long)n_rows * K;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int row = (int)(i / K);
+        const int kk = (int)(i - (long long)row * K);
+        const int j = kk / Cs, k = kk - j * Cs;
+        const int cls = row / n_real, n = row - cls * n_real;
+        bf16 v = __float2bfloat16_rn(0.f);
+        if (cls < 4) {
+            const int id = t.tap[cls][j];
+            if (id >= 0) v = w[((long long)id * n_real + n) * Cs + k];      // w[tap][n][k]
+        }
+        out[i] = v;
+    }
+}
+
+bool subpixel_eligible(int Cs, int n_real, int Jh, int Jw, int kh, int kw) {
+    if (getenv("DMV_NO_SUBPIXEL") || getenv("DMV_NO_HALO")) return false;
+    if (!(Cs == 32 || Cs == 64) || n_real > 64 || n_real < 1) return false;
+    if (n_real >= 16 && (n_real & 15)) return false;
+    if (n_real < 16 && (16 % n_real)) return false;
+    if (Jh * Jw < 256 || kh > 5 || kw > 5) return false;
+    // the halo kernel keeps all S weight tiles resident next to two input windows
+    const int S = ((kh + 2) / 2) * ((kw + 2) / 2), dh = (kh + 2) / 2 - 1, dw = (kw + 2) / 2 - 1;
+    const size_t wbytes = (size_t)S * ceil_div(4 * n_real, 16) * 16 * Cs * 2;
+    const size_t a_stage = ((size_t)(16 + dh) * (8 + dw) * Cs * 2 + 1023) & ~(size_t)1023;
+    return wbytes + 2 * a_stage <= 200 * 1024;
+}
+
+size_t subpixel_workspace(int Cs, int n_real, int kh, int kw) {
+    const int S = ((kh + 2) / 2) * ((kw + 2) / 2);          // upper bound on the number of shifts
+    return (size_t)ceil_div(4 * n_real, 16) * 16 * S * Cs * 2 + 256;
+}
+
 // taps of the F form (conv-fwd-like): A pixel = out*stride + (r - pt, s - pl)
 int build_f(IgemmParams& p, int kh, int kw, int stride, int pt, int pl) {
     if (kh * kw > kMaxTaps) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: too many taps");
@@ -774,6 +889,58 @@ int build_g(IgemmParams& p, int kh, int kw, int stride, int pt, int pl, int w_co
     return DMV_OK;
 }
 
+// Stride-2 G problem as one stride-1 halo launch (see SubpixelTable).  w is the reference layout read as
+// w[tap][n_real][Cs] (conv dgrad: [kh][kw][Cin][Cout]; deconv fwd: [kh][kw][Cout_t][Cin_t]).
+int launch_subpixel(const void* src, int N, int Hs, int Ws, int Cs, const void* w, int kh, int kw, int pt, int pl, void* out, int out_f32,
+                    int out_H, int out_W, int n_real, int act, void* ws, size_t ws_bytes, cudaStream_t st) {
+    IgemmParams g;
+    memset(&g, 0, sizeof(g));
+    int rc = build_g(g, kh, kw, 2, pt, pl, Cs);
+    if (rc) return rc;
+    SubpixelTable t;
+    memset(&t, 0, sizeof(t));
+    for (int c = 0; c < 4; ++c)
+        for (int j = 0; j < 16; ++j) t.tap[c][j] = -1;
+    for (int c = 0; c < 4; ++c) {
+        const TapClass& tc_ = g.cls[c];
+        const int cls = tc_.py * 2 + tc_.px;
+        for (int j = 0; j < tc_.tap_count; ++j) {
+            const Tap& tp = g.taps[tc_.tap_begin + j];
+            int sidx = -1;
+            for (int z = 0; z < t.S; ++z)
+                if (t.dh[z] == tp.dh && t.dw[z] == tp.dw) sidx = z;
+            if (sidx < 0) {
+                if (t.S >= 16) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc subpixel: too many shifts");
+                sidx = t.S++;
+                t.dh[sidx] = tp.dh; t.dw[sidx] = tp.dw;
+            }
+            t.tap[cls][sidx] = tp.id;
+        }
+    }
+    const int n_rows = ceil_div(4 * n_real, 16) * 16;
+    const size_t need = (size_t)n_rows * t.S * Cs * 2;
+    if (!ws || ws_bytes < need || ((uintptr_t)ws & 15)) return fail(DMV_E_WORKSPACE, "tc subpixel: workspace too small");
+    long long blocks = ceil_div_ll((long long)n_rows * t.S * Cs, 256);
+    if (blocks > 1184) blocks = 1184;
+    pack_subpixel_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)w, (bf16*)ws, n_real, Cs, n_rows, t);
+    rc = check_launch("tc pack subpixel");
+    if (rc) return rc;
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_classes = 1;
+    p.cls[0] = TapClass{0, t.S, 0, 0, 0};
+    for (int j = 0; j < t.S; ++j) {
+        p.taps[j].dh = t.dh[j]; p.taps[j].dw = t.dw[j]; p.taps[j].ph = 0; p.taps[j].pw = 0; p.taps[j].id = j;
+    }
+    p.d2s = 1; p.d2s_c = n_real;
+    Problem q;
+    q.src = src; q.N = N; q.Hs = Hs; q.Ws = Ws; q.Cs = Cs; q.src_stride = 1;
+    q.w_hwio = ws; q.kh = 1; q.kw = t.S; q.w_ci = t.S * Cs; q.w_co = n_rows; q.g_form = false; q.n_tile = 0; q.b_mode_override = 3; q.k_splits = 1;
+    q.out = out; q.out_f32 = out_f32; q.out_H = out_H; q.out_W = out_W; q.n_real = n_rows; q.out_mul = 1;
+    q.Jh = ceil_div(out_H, 2); q.Jw = ceil_div(out_W, 2); q.bias = nullptr; q.act = act;
+    return launch_igemm(q, p, nullptr, 0, st);
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------
@@ -782,7 +949,11 @@ int build_g(IgemmParams& p, int kh, int kw, int stride, int pt, int pl, int w_co
 namespace dmv {
 
 
-size_t tc_pack_workspace(int taps, int Cin, int Cout) { return (size_t)taps * Cin * Cout * 2 + 256; }
+size_t tc_pack_workspace(int taps, int Cin, int Cout) {
+    // F-form packed copy, or the sub-pixel matrix of a stride-2 G form (4 classes x <= taps shifts, rows padded to 16)
+    const size_t big = Cin > Cout ? Cin : Cout, small = Cin > Cout ? Cout : Cin;
+    return (size_t)taps * (4 * big + 16) * (small < 32 ? 32 : small) * 2 + 256;
+}
 
 // conv fwd: F form, A = x
 int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin, int Cout,
@@ -807,6 +978,8 @@ int tc_conv_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, 
                   void* ws, size_t ws_bytes, cudaStream_t st) {
     if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_conv_dgrad: stride");
     const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+    if (stride == 2 && subpixel_eligible(Cout, Cin, ceil_div(H, 2), ceil_div(W, 2), kh, kw) && ws_bytes >= subpixel_workspace(Cout, Cin, kh, kw))
+        return launch_subpixel(dy, B, ph.out, pw.out, Cout, w, kh, kw, ph.before, pw.before, dx, 0, H, W, Cin, DMV_ACT_NONE, ws, ws_bytes, st);
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     int rc = build_g(p, kh, kw, stride, ph.before, pw.before, Cout);
@@ -824,6 +997,10 @@ int tc_deconv_fwd(const void* x, const void* w, void* y, int ydt, int B, int Hou
                   int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_deconv_fwd: stride");
     const SamePad ph = same_pad(Hout, kh, stride), pw = same_pad(Wout, kw, stride);
+    if (stride == 2 && subpixel_eligible(Cin, Cout, ceil_div(Hout, 2), ceil_div(Wout, 2), kh, kw) &&
+        ws_bytes >= subpixel_workspace(Cin, Cout, kh, kw))
+        return launch_subpixel(x, B, ph.out, pw.out, Cin, w, kh, kw, ph.before, pw.before, y, ydt == DMV_DT_F32, Hout, Wout, Cout, act, ws,
+                               ws_bytes, st);
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     int rc = build_g(p, kh, kw, stride, ph.before, pw.before, Cin);

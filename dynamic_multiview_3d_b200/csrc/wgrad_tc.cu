@@ -15,6 +15,8 @@
 // the pixel slices go to the workspace and are summed in slice order by a second kernel
 // (deterministic split-K); a single slice writes dW directly.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "conv_impl.h"
 
@@ -174,6 +176,162 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Halo variant for stride-1 layers with one channel chunk per tap (Cb = 32 or 64) and Cs = 32 or 64:
+// the five largest weight gradients of the graph.  Instead of one TMA box per tap and pixel chunk
+// (kh*kw re-reads of the input from L2, which bounds the generic kernel), the CTA loads the
+// (BH + kh - 1) x (8 + kw - 1) input window of an 8-wide x BH-tall gradient tile ONCE.  The A operand
+// of a tap is that window addressed through an MN-major descriptor that starts (r * pitch + s) pixel
+// rows further: K group g (8 pixels of tile row 2k + g) sits SBO = one window row apart, and the
+// M = 128 rows of one MMA are 128 / CB taps that are neighbours in s (LBO = one pixel) or in r
+// (LBO = one window row).  Shared-memory swizzling is a function of the address alone, so shifted
+// starts read exactly what TMA wrote.
+constexpr int kMaxHTiles = 32;
+struct HTile {
+    short r0, s0, dir, nvalid;    // first tap, stacking direction (0: along s, 1: along r), taps that exist
+};
+struct WHaloParams {
+    int m_tiles, tiles_per_group, groups;
+    int CB, row_bytes_a, row_bytes_b, Cb, Cs;     // Cs = UMMA N (one N tile)
+    int BH, pitch, halo_h, kw, pt, pl;
+    int tiles_w, tiles_h, chunks, slices, chunks_per_slice, stages;
+    int a_stage, b_stage;                          // bytes per stage (1024-aligned)
+    long long out_elems;
+    float* out;
+    HTile tile[kMaxHTiles];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ WHaloParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int stage_bytes = p.a_stage + p.b_stage;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + 1024);   // 1 KB slack: absent taps of a ragged M tile
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* done_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int w = blockIdx.x;
+    const int slice = w % p.slices; w /= p.slices;
+    const int grp = w;
+    const int mt0 = grp * p.tiles_per_group;
+    const int n_mt = min(p.m_tiles, mt0 + p.tiles_per_group) - mt0;
+    const int ch0 = slice * p.chunks_per_slice;
+    const int ch1 = min(p.chunks, ch0 + p.chunks_per_slice);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(p.tiles_per_group * p.Cs)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = (uint32_t)(p.halo_h * p.pitch * p.row_bytes_a + p.BH * 8 * p.row_bytes_b);
+            for (int ch = ch0; ch < ch1; ++ch) {
+                int t = ch;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], tx);
+                tma_load_5d(sa, &map_a, &full_bar[stage], 0, tw * 8 - p.pl, 0, th * p.BH - p.pt, t);
+                tma_load_5d(sa + p.a_stage, &map_b, &full_bar[stage], 0, tw * 8, 0, th * p.BH, t);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cs >> 3) << 17) |
+                                   ((128u >> 4) << 24);
+            const uint32_t row_step = (uint32_t)(p.pitch * p.row_bytes_a);          // one window row
+            // per M tile: descriptor bits that do not depend on the stage
+            uint64_t a_hi[kMaxHTiles];
+            uint32_t a_off[kMaxHTiles];
+            for (int i = 0; i < n_mt; ++i) {
+                const HTile& t = p.tile[mt0 + i];
+                const uint32_t lbo = t.dir ? row_step : (uint32_t)p.row_bytes_a;
+                uint64_t d = 0;
+                d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+                d |= (uint64_t)((row_step >> 4) & 0x3FFF) << 32;                     // SBO: next tile row = next 8-pixel K group
+                d |= (uint64_t)1 << 46;
+                d |= (uint64_t)(p.row_bytes_a == 128 ? 2 : 4) << 61;
+                a_hi[i] = d;
+                a_off[i] = (uint32_t)((t.r0 * p.pitch + t.s0) * p.row_bytes_a);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = ch0; ch < ch1; ++ch) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t bdesc = make_mnmajor_desc(sa + p.a_stage, p.row_bytes_b, 1024);
+                for (int i = 0; i < n_mt; ++i) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(i * p.Cs);
+                    const uint32_t a0 = sa + a_off[i];
+                    for (int k = 0; k < p.BH / 2; ++k) {    // 16 pixels per MMA = tile rows 2k, 2k + 1
+                        const uint64_t adesc = a_hi[i] | (uint64_t)(((a0 + 2u * k * row_step) & 0x3FFFF) >> 4);
+                        tc_mma_bf16(d_tmem, adesc, bdesc + (uint64_t)((k * 16 * p.row_bytes_b) >> 4), idesc, (ch > ch0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(done_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        float* outp = p.out + (long long)slice * p.out_elems;
+        const bool have = ch1 > ch0;
+        const int j = m / p.CB, c = m % p.CB;
+        for (int i = 0; i < n_mt; ++i) {
+            const HTile& t = p.tile[mt0 + i];
+            const bool ok = j < t.nvalid;
+            const int r = t.r0 + (t.dir ? j : 0), s2 = t.s0 + (t.dir ? 0 : j);
+            const long long row = ok ? (long long)(r * p.kw + s2) * p.Cb + c : 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * p.Cs);
+            for (int c0 = 0; c0 < p.Cs; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (ok) {
+                    float* o = outp + row * p.Cs + c0;
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4)
+                        *reinterpret_cast<float4*>(o + k) =
+                            have ? make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // pixel chunk box: rows = BW*BH*NB a multiple of 16, <= max_rows, maximising the useful fraction
 void choose_chunk(int Jh, int Jw, int N, int max_rows, int& BW, int& BH, int& NB) {
     double best = -1.0;
@@ -245,7 +403,111 @@ bool wgrad_eligible(int Cb, int Cs, int taps) {
     return true;
 }
 
+
+// ---- halo variant: planning and launch
+bool whalo_eligible(const WProblem& q) {
+    if (getenv("DMV_NO_WHALO")) return false;
+    if (q.stride != 1 || q.kh * q.kw == 1) return false;
+    if (!(q.Cb == 32 || q.Cb == 64) || !(q.Cs == 32 || q.Cs == 64)) return false;
+    if (q.Hs != q.Hb || q.Ws != q.Wb) return false;          // stride-1 SAME: gradient and input share the resolution
+    if (q.Hs * q.Ws < 256 || q.kw > 8 || q.kh > 8) return false;
+    return true;
+}
+
+int plan_whalo(const WProblem& q, WHaloParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.CB = q.Cb; p.Cb = q.Cb; p.Cs = q.Cs;
+    p.row_bytes_a = q.Cb * 2; p.row_bytes_b = q.Cs * 2;
+    p.kw = q.kw; p.pt = q.pt; p.pl = q.pl;
+    // tile height: an even number of rows <= 16 that wastes the fewest rows of the image
+    int best_bh = 16; double best = -1.0;
+    for (int bh = 16; bh >= 8; bh -= 2) {
+        const double eff = (double)q.Hs / (ceil_div(q.Hs, bh) * bh);
+        if (eff > best + 1e-9) { best = eff; best_bh = bh; }
+    }
+    p.BH = best_bh;
+    p.pitch = 8 + q.kw - 1;
+    p.halo_h = p.BH + q.kh - 1;
+    p.tiles_w = ceil_div(q.Ws, 8);
+    p.tiles_h = ceil_div(q.Hs, p.BH);
+    p.chunks = p.tiles_w * p.tiles_h * q.N;
+    // M tiles: 128 / CB taps each; rows of taps first (stacked along s), the leftover column stacked along r,
+    // any ragged remainder again along s so that absent taps only read a few pixels past the window
+    const int spt = 128 / p.CB;
+    int n = 0;
+    const int full = q.kw / spt, rem = q.kw % spt;
+    for (int r = 0; r < q.kh; ++r)
+        for (int f = 0; f < full; ++f) p.tile[n++] = HTile{(short)r, (short)(f * spt), 0, (short)spt};
+    if (rem) {
+        if (rem == 1) {                       // one leftover tap per row: stack rows
+            int r = 0;
+            for (; r + spt <= q.kh; r += spt) p.tile[n++] = HTile{(short)r, (short)(q.kw - 1), 1, (short)spt};
+            for (; r < q.kh; ++r) p.tile[n++] = HTile{(short)r, (short)(q.kw - 1), 0, 1};
+        } else {
+            for (int r = 0; r < q.kh; ++r) p.tile[n++] = HTile{(short)r, (short)(full * spt), 0, (short)rem};
+        }
+    }
+    if (n > kMaxHTiles) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad halo: too many M tiles");
+    p.m_tiles = n;
+    p.tiles_per_group = 512 / p.Cs;
+    if (p.tiles_per_group > n) p.tiles_per_group = n;
+    p.groups = ceil_div(n, p.tiles_per_group);
+    p.tiles_per_group = ceil_div(n, p.groups);               // balance the groups
+    int slices = ceil_div(num_sms(), p.groups);
+    if (slices > p.chunks) slices = p.chunks;
+    p.chunks_per_slice = ceil_div(p.chunks, slices);
+    p.slices = ceil_div(p.chunks, p.chunks_per_slice);
+    p.out_elems = (long long)q.kh * q.kw * q.Cb * q.Cs;
+    p.a_stage = (p.halo_h * p.pitch * p.row_bytes_a + 1023) & ~1023;
+    p.b_stage = (p.BH * 8 * p.row_bytes_b + 1023) & ~1023;
+    return DMV_OK;
+}
+
+int run_wgrad_halo(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
+    WHaloParams p;
+    int rc = plan_whalo(q, p);
+    if (rc) return rc;
+    const size_t need = p.slices > 1 ? (size_t)p.slices * p.out_elems * sizeof(float) : 0;
+    if (need > 0 && (!ws || ws_bytes < need)) return fail(DMV_E_WORKSPACE, "tc wgrad halo: workspace too small");
+    p.out = p.slices > 1 ? reinterpret_cast<float*>(ws) : q.dw;
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)q.Cb, (cuuint64_t)q.Wb, 1, (cuuint64_t)q.Hb, (cuuint64_t)q.N};
+        const cuuint64_t pix = (cuuint64_t)q.Cb * 2;
+        cuuint64_t strides[4] = {pix, (cuuint64_t)q.Wb * pix, (cuuint64_t)q.Wb * pix, (cuuint64_t)q.Hb * q.Wb * pix};
+        cuuint32_t box[5] = {(cuuint32_t)q.Cb, (cuuint32_t)p.pitch, 1u, (cuuint32_t)p.halo_h, 1u};
+        rc = encode_map(&map_a, q.big, 5, dims, strides, box, p.row_bytes_a);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)q.Cs, (cuuint64_t)q.Ws, 1, (cuuint64_t)q.Hs, (cuuint64_t)q.N};
+        const cuuint64_t pix = (cuuint64_t)q.Cs * 2;
+        cuuint64_t strides[4] = {pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Hs * q.Ws * pix};
+        cuuint32_t box[5] = {(cuuint32_t)q.Cs, 8u, 1u, (cuuint32_t)p.BH, 1u};
+        rc = encode_map(&map_b, q.small, 5, dims, strides, box, p.row_bytes_b);
+        if (rc) return rc;
+    }
+    const int stage_bytes = p.a_stage + p.b_stage;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad halo: stage does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("tc wgrad halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return DMV_E_CUDA;
+    }
+    wgrad_halo_kernel<<<p.groups * p.slices, kThreads, smem, st>>>(map_a, map_b, p);
+    count_tc_launch();
+    rc = check_launch("wgrad_halo_tc");
+    if (rc) return rc;
+    if (p.slices > 1) rc = reduce_partials(reinterpret_cast<const float*>(ws), q.dw, p.out_elems, p.slices, st);
+    return rc;
+}
+
 int run_wgrad(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (whalo_eligible(q)) return run_wgrad_halo(q, ws, ws_bytes, st);
     if (!wgrad_eligible(q.Cb, q.Cs, q.kh * q.kw)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: channel counts not covered");
     if (q.stride != 1 && q.stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: stride");
     if (q.stride == 2 && ((q.Hb & 1) || (q.Wb & 1))) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: stride-2 source needs even H and W");

@@ -35,6 +35,11 @@ SMALL = [  # kind, k, s, H(big side), cin, cout, B
     ("conv", 3, 1, 14, 128, 128, 2), ("conv", 5, 1, 28, 64, 64, 2), ("conv", 3, 2, 28, 64, 128, 2), ("conv", 5, 1, 24, 32, 64, 1),
     ("deconv", 3, 2, 14, 256, 128, 3), ("deconv", 3, 2, 28, 128, 64, 2), ("deconv", 5, 2, 16, 64, 32, 3), ("deconv", 5, 2, 32, 32, 2, 2),
     ("deconv", 3, 1, 16, 32, 2, 2),
+    # halo weight-gradient kernel: ragged M tiles (3 taps per row, 128/CB = 4 or 2 per MMA), ragged image tiling
+    ("conv", 3, 1, 20, 32, 32, 2), ("conv", 3, 1, 18, 64, 64, 2), ("conv", 5, 1, 22, 64, 32, 2), ("conv", 4, 1, 16, 32, 32, 1),
+    # sub-pixel form of the stride-2 G problems (deconv fwd / conv dgrad as one stride-1 halo launch + depth-to-space)
+    ("deconv", 3, 2, 32, 64, 32, 2), ("conv", 3, 2, 36, 32, 32, 2), ("deconv", 5, 2, 34, 32, 16, 1), ("conv", 5, 2, 36, 32, 64, 1),
+    ("deconv", 5, 2, 36, 64, 64, 1),
 ]
 
 

@@ -26,7 +26,7 @@ if [[ $what == all || $what == ncu ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:sampler -c 6 -f -o gpurun_out/sampler_prof python tools/prof_sampler.py > gpurun_out/ncu_sampler.log 2>&1
   echo "ncu sampler exit $?" | tee -a gpurun_out/summary.txt
   timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/bench_short.json 2>&1 &&
-  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/ncu_launches.log 2>&1
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro --eager > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?" | tee -a gpurun_out/summary.txt
   # dominant kernel of the step (Adam) + the tensor-core kernels, one --set full capture each
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:adam_multi -c 1 -f -o gpurun_out/adam_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-micro --eager > gpurun_out/ncu_adam.log 2>&1
