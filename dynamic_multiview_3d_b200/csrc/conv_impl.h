@@ -40,6 +40,19 @@ int tc_thin_fwd(const void* thin, int thin_dtype, const void* w_bf16, const floa
 int tc_thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw,
                   int stride, void* ws, size_t ws_bytes, cudaStream_t st);
 bool thin_wgrad_eligible(int taps, int Ct, int Cw);
+// thin stride-2 layers through space-to-depth (thin_simt.cu / conv_tc.cu / wgrad_tc.cu): X2[n][h/2][w/2][32] holds the
+// 2x2 pixel block of the thin tensor as channels (ph, pw, c), zero padded to 32; the layer is then a stride-1 conv
+// over X2 with kh2 x kw2 shifts starting at (dh0, dw0)
+struct S2dGeom {
+    int dh0, kh2, dw0, kw2;
+};
+bool thin_s2d_eligible(int Hb, int Wb, int Ct, int Cw, int kh, int kw, int stride);
+S2dGeom thin_s2d_geom(int Hb, int Wb, int kh, int kw);
+int thin_s2d_prep(const void* thin, int thin_dtype, void* X2, int N, int Hb, int Wb, int Ct, cudaStream_t st);
+// W2p[cw][(shift, ch')] (bf16, K-major) from w[r][s][ct][cw]
+int thin_s2d_pack_weights(const void* w_bf16, void* packed, int Ct, int Cw, int kh, int kw, int pt, int pl, S2dGeom g, cudaStream_t st);
+// dW[r][s][ct][cw] (fp32) gathered from dW2[shift][ch'][cw]
+int thin_s2d_gather_dw(const float* dw2, float* dw, int Ct, int Cw, int kh, int kw, int pt, int pl, S2dGeom g, cudaStream_t st);
 int thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride,
                void* ws, size_t ws_bytes, cudaStream_t st);
 

@@ -8,6 +8,8 @@
 // group) holds R x 8 accumulators and streams pixels, loading its 8 wide channels with one
 // 16-byte load and its R thin values through L1.  Warps/CTAs take interleaved pixels; CTA
 // partials are summed in CTA order by the shared split-K reduce (deterministic).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_impl.h"
 
@@ -193,9 +195,128 @@ int run_thin(const TT* thin, const bf16* wide, float* dw, const ThinGeom& g, voi
     thin_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(part, dw, n, ctas);
     return check_launch("thin_wgrad reduce");
 }
+
+// ---- space-to-depth path of the thin stride-2 layers -------------------------------------------------------
+// X2[n][y][x][(ph*2 + pw)*Ct + c] = thin[n][2y + ph][2x + pw][c], channels 4*Ct .. 31 zero.  A CTA stages one pair of
+// thin rows (contiguous in memory) in shared memory with 16-byte loads; four threads build one X2 pixel, one 16-byte
+// channel group each, so the stores of a warp are 512 contiguous bytes.
+template <typename TT>
+__global__ void __launch_bounds__(256) thin_s2d_prep_kernel(const TT* __restrict__ thin, uint4* __restrict__ X2, int N, int Hb, int Wb, int Ct) {
+    extern __shared__ float s_rows[];             // [2][Wb * Ct]
+    const int H2 = Hb >> 1, W2 = Wb >> 1, row_elems = Wb * Ct, q = threadIdx.x & 3;
+    int off[8];                                   // source offset of channel 8q + k relative to pixel 2x of row 2y; -1: zero
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ch = 8 * q + k, blk = ch / Ct, c = ch - blk * Ct;
+        off[k] = (ch < 4 * Ct) ? (blk >> 1) * row_elems + (blk & 1) * Ct + c : -1;
+    }
+    for (long long rp = blockIdx.x; rp < (long long)N * H2; rp += gridDim.x) {
+        const TT* src = thin + rp * 2 * row_elems;        // rows 2y and 2y + 1 of image n are adjacent
+        if (sizeof(TT) == 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((2 * row_elems) & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            for (int e = threadIdx.x; e < (2 * row_elems) >> 2; e += 256) reinterpret_cast<float4*>(s_rows)[e] = __ldg(s4 + e);
+        } else {
+            for (int e = threadIdx.x; e < 2 * row_elems; e += 256) s_rows[e] = load_as_float(src + e);
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < W2 * 4; o += 256) {
+            const int base = (o >> 2) * 2 * Ct;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = off[k] >= 0 ? s_rows[base + off[k]] : 0.f;
+            uint4 u;
+            __nv_bfloat162 h;
+            h = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+            X2[rp * W2 * 4 + o] = u;
+        }
+        __syncthreads();
+    }
+}
+
+// reference tap (r, s) and thin channel of entry (shift j, ch') of the s2d weight matrix; false: structural zero
+__device__ __forceinline__ bool s2d_entry(int j, int ch, int Ct, int kh, int kw, int pt, int pl, dmv::S2dGeom g, int& tap, int& c) {
+    if (ch >= 4 * Ct) return false;
+    const int dh = g.dh0 + j / g.kw2, dw = g.dw0 + j % g.kw2;
+    const int blk = ch / Ct;
+    c = ch - blk * Ct;
+    const int r = 2 * dh + (blk >> 1) + pt, s = 2 * dw + (blk & 1) + pl;
+    if (r < 0 || r >= kh || s < 0 || s >= kw) return false;
+    tap = r * kw + s;
+    return true;
+}
+
+__global__ void thin_s2d_pack_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int Ct, int Cw, int kh, int kw, int pt, int pl,
+                                     dmv::S2dGeom g) {
+    const int K = g.kh2 * g.kw2 * 32, total = Cw * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cw = i / K, kk = i - cw * K;
+        int tap, c;
+        bf16 v = __float2bfloat16_rn(0.f);
+        if (s2d_entry(kk >> 5, kk & 31, Ct, kh, kw, pt, pl, g, tap, c)) v = w[((long long)tap * Ct + c) * Cw + cw];
+        out[i] = v;
+    }
+}
+
+__global__ void thin_s2d_gather_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int Ct, int Cw, int kh, int kw, int pt, int pl,
+                                       dmv::S2dGeom g) {
+    const int total = g.kh2 * g.kw2 * 32 * Cw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cw = i % Cw, kk = i / Cw;
+        int tap, c;
+        if (s2d_entry(kk >> 5, kk & 31, Ct, kh, kw, pt, pl, g, tap, c)) dw[((long long)tap * Ct + c) * Cw + cw] = dw2[i];
+    }
+}
+
 }  // namespace
 
 namespace dmv {
+
+
+static int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+S2dGeom thin_s2d_geom(int Hb, int Wb, int kh, int kw) {
+    const SamePad ph = same_pad(Hb, kh, 2), pw = same_pad(Wb, kw, 2);
+    S2dGeom g;
+    g.dh0 = floor_div2(-ph.before);
+    g.kh2 = floor_div2(kh - 1 - ph.before) - g.dh0 + 1;
+    g.dw0 = floor_div2(-pw.before);
+    g.kw2 = floor_div2(kw - 1 - pw.before) - g.dw0 + 1;
+    return g;
+}
+
+bool thin_s2d_eligible(int Hb, int Wb, int Ct, int Cw, int kh, int kw, int stride) {
+    if (getenv("DMV_NO_S2D")) return false;
+    if (stride != 2 || (Hb & 1) || (Wb & 1) || 4 * Ct > 32 || Ct < 1) return false;
+    if (!(Cw == 32 || Cw == 64)) return false;
+    if ((Hb / 2) * (Wb / 2) < 256) return false;       // below this the halo kernels are not used
+    const S2dGeom g = thin_s2d_geom(Hb, Wb, kh, kw);
+    return g.kh2 * g.kw2 > 1 && g.kh2 <= 3 && g.kw2 <= 3;
+}
+
+int thin_s2d_prep(const void* thin, int thin_dtype, void* X2, int N, int Hb, int Wb, int Ct, cudaStream_t st) {
+    long long blocks = (long long)N * (Hb / 2);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const size_t smem = (size_t)2 * Wb * Ct * sizeof(float);
+    if (smem > 48 * 1024) return fail(DMV_E_UNSUPPORTED_SHAPE, "thin_s2d_prep: row pair does not fit shared memory");
+    if (thin_dtype == DMV_DT_F32)
+        thin_s2d_prep_kernel<float><<<(int)blocks, 256, smem, st>>>((const float*)thin, (uint4*)X2, N, Hb, Wb, Ct);
+    else
+        thin_s2d_prep_kernel<bf16><<<(int)blocks, 256, smem, st>>>((const bf16*)thin, (uint4*)X2, N, Hb, Wb, Ct);
+    return check_launch("thin_s2d_prep");
+}
+
+int thin_s2d_pack_weights(const void* w, void* packed, int Ct, int Cw, int kh, int kw, int pt, int pl, S2dGeom g, cudaStream_t st) {
+    thin_s2d_pack_kernel<<<ceil_div(Cw * g.kh2 * g.kw2 * 32, 256), 256, 0, st>>>((const bf16*)w, (bf16*)packed, Ct, Cw, kh, kw, pt, pl, g);
+    return check_launch("thin_s2d_pack");
+}
+
+int thin_s2d_gather_dw(const float* dw2, float* dw, int Ct, int Cw, int kh, int kw, int pt, int pl, S2dGeom g, cudaStream_t st) {
+    thin_s2d_gather_kernel<<<ceil_div(Cw * g.kh2 * g.kw2 * 32, 256), 256, 0, st>>>(dw2, dw, Ct, Cw, kh, kw, pt, pl, g);
+    return check_launch("thin_s2d_gather");
+}
 
 int thin_patch_cols(int taps, int Ct) { return ceil_div(taps * Ct, 32) * 32; }
 

@@ -332,6 +332,145 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_co
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// 2-D stacked halo variant for Cb = Cs = 32: taps are stacked along BOTH MMA dimensions.  With the virtual column
+// u = ox + s,   dW[r, s] = sum_{oy, u} x[oy + r - pt, u - pl] * dy[oy, u - s],
+// so for a tile of (oy, u) the A operand stacks up to four r (rows of the x window, LBO = one window row) along M and
+// the B operand stacks all kw values of s (columns of a dy window with a (kw - 1)-pixel halo on the left, LBO = one
+// pixel, in DEcreasing s) along N.  One MMA is M = 128 x N = 32 kw instead of M = 128 x N = 32: 3.5x fewer MMAs for a
+// 5 x 5 layer, and the MN-major operand fetch (the bound of the 1-D form) is amortised over kw times the math.
+struct WHalo2Params {
+    int m_tiles;                  // ceil(kh / 4) accumulators of N = 32 * kw columns
+    int kh, kw, pt, pl, BH, pitch_b;
+    int tiles_w, tiles_h, chunks, slices, chunks_per_slice, stages;
+    int a_stage, b_stage;
+    long long out_elems;
+    float* out;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_halo2d_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                    const __grid_constant__ CUtensorMap map_b,
+                                                                    const __grid_constant__ WHalo2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int stage_bytes = p.a_stage + p.b_stage;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + 2048);   // slack: absent r taps of the last M tile
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* done_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slice = blockIdx.x;
+    const int ch0 = slice * p.chunks_per_slice;
+    const int ch1 = min(p.chunks, ch0 + p.chunks_per_slice);
+    const int N = 32 * p.kw;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(p.m_tiles * N)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = (uint32_t)((p.BH + p.kh - 1) * 8 * 64 + p.BH * p.pitch_b * 64);
+            for (int ch = ch0; ch < ch1; ++ch) {
+                int t = ch;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], tx);
+                tma_load_5d(sa, &map_a, &full_bar[stage], 0, tw * 8 - p.pl, 0, th * p.BH - p.pt, t);
+                tma_load_5d(sa + p.a_stage, &map_b, &full_bar[stage], 0, tw * 8 - (p.kw - 1), 0, th * p.BH, t);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            // A: spans = r (LBO one 8-pixel window row = 512 B), K groups = tile rows (SBO 512 B)
+            uint64_t a_hi = 0;
+            a_hi |= (uint64_t)(512u >> 4) << 16;
+            a_hi |= (uint64_t)(512u >> 4) << 32;
+            a_hi |= (uint64_t)1 << 46;
+            a_hi |= (uint64_t)4 << 61;
+            // B: spans = s descending (LBO one pixel = 64 B), K groups = window rows (SBO pitch_b pixels)
+            const uint32_t b_row = (uint32_t)(p.pitch_b * 64);
+            uint64_t b_hi = 0;
+            b_hi |= (uint64_t)(64u >> 4) << 16;
+            b_hi |= (uint64_t)((b_row >> 4) & 0x3FFF) << 32;
+            b_hi |= (uint64_t)1 << 46;
+            b_hi |= (uint64_t)4 << 61;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = ch0; ch < ch1; ++ch) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)p.a_stage;
+                for (int i = 0; i < p.m_tiles; ++i) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(i * N);
+                    for (int k = 0; k < p.BH / 2; ++k) {
+                        const uint64_t adesc = a_hi | (uint64_t)(((sa + (uint32_t)(4 * i + 2 * k) * 512u) & 0x3FFFF) >> 4);
+                        const uint64_t bdesc = b_hi | (uint64_t)(((sb + (uint32_t)(2 * k) * b_row) & 0x3FFFF) >> 4);
+                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (ch > ch0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(done_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        float* outp = p.out + (long long)slice * p.out_elems;
+        const bool have = ch1 > ch0;
+        const int j = m >> 5, ci = m & 31;
+        for (int i = 0; i < p.m_tiles; ++i) {
+            const int r = 4 * i + j;
+            const bool ok = r < p.kh;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * N);
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (ok) {
+                    const int s2 = p.kw - 1 - (c0 >> 5);
+                    float* o = outp + ((long long)(r * p.kw + s2) * 32 + ci) * 32 + (c0 & 31);
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4)
+                        *reinterpret_cast<float4*>(o + k) =
+                            have ? make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // pixel chunk box: rows = BW*BH*NB a multiple of 16, <= max_rows, maximising the useful fraction
 void choose_chunk(int Jh, int Jw, int N, int max_rows, int& BW, int& BH, int& NB) {
     double best = -1.0;
@@ -506,7 +645,76 @@ int run_wgrad_halo(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st
     return rc;
 }
 
+// ---- 2-D stacked halo variant (Cb = Cs = 32)
+bool whalo2d_eligible(const WProblem& q) {
+    if (getenv("DMV_NO_WHALO2D")) return false;
+    if (!whalo_eligible(q)) return false;
+    if (q.Cb != 32 || q.Cs != 32) return false;
+    return ceil_div(q.kh, 4) * 32 * q.kw <= 512 && 32 * q.kw <= 256;
+}
+
+int run_wgrad_halo2d(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
+    WHalo2Params p;
+    memset(&p, 0, sizeof(p));
+    p.kh = q.kh; p.kw = q.kw; p.pt = q.pt; p.pl = q.pl;
+    p.m_tiles = ceil_div(q.kh, 4);
+    int best_bh = 16; double best = -1.0;
+    for (int bh = 16; bh >= 8; bh -= 2) {
+        const double eff = (double)q.Hs / (ceil_div(q.Hs, bh) * bh);
+        if (eff > best + 1e-9) { best = eff; best_bh = bh; }
+    }
+    p.BH = best_bh;
+    p.pitch_b = 8 + q.kw - 1;
+    p.tiles_w = ceil_div(q.Ws + q.kw - 1, 8);          // virtual columns u = ox + s
+    p.tiles_h = ceil_div(q.Hs, p.BH);
+    p.chunks = p.tiles_w * p.tiles_h * q.N;
+    int slices = num_sms();
+    if (slices > p.chunks) slices = p.chunks;
+    p.chunks_per_slice = ceil_div(p.chunks, slices);
+    p.slices = ceil_div(p.chunks, p.chunks_per_slice);
+    p.out_elems = (long long)q.kh * q.kw * 32 * 32;
+    p.a_stage = ((p.BH + q.kh - 1) * 8 * 64 + 1023) & ~1023;
+    p.b_stage = (p.BH * p.pitch_b * 64 + 1023) & ~1023;
+    const size_t need = p.slices > 1 ? (size_t)p.slices * p.out_elems * sizeof(float) : 0;
+    if (need > 0 && (!ws || ws_bytes < need)) return fail(DMV_E_WORKSPACE, "tc wgrad halo2d: workspace too small");
+    p.out = p.slices > 1 ? reinterpret_cast<float*>(ws) : q.dw;
+    CUtensorMap map_a, map_b;
+    int rc;
+    {
+        cuuint64_t dims[5] = {32, (cuuint64_t)q.Wb, 1, (cuuint64_t)q.Hb, (cuuint64_t)q.N};
+        cuuint64_t strides[4] = {64, (cuuint64_t)q.Wb * 64, (cuuint64_t)q.Wb * 64, (cuuint64_t)q.Hb * q.Wb * 64};
+        cuuint32_t box[5] = {32u, 8u, 1u, (cuuint32_t)(p.BH + q.kh - 1), 1u};
+        rc = encode_map(&map_a, q.big, 5, dims, strides, box, 64);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[5] = {32, (cuuint64_t)q.Ws, 1, (cuuint64_t)q.Hs, (cuuint64_t)q.N};
+        cuuint64_t strides[4] = {64, (cuuint64_t)q.Ws * 64, (cuuint64_t)q.Ws * 64, (cuuint64_t)q.Hs * q.Ws * 64};
+        cuuint32_t box[5] = {32u, (cuuint32_t)p.pitch_b, 1u, (cuuint32_t)p.BH, 1u};
+        rc = encode_map(&map_b, q.small, 5, dims, strides, box, 64);
+        if (rc) return rc;
+    }
+    const int stage_bytes = p.a_stage + p.b_stage;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad halo2d: stage does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 2048 + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("tc wgrad halo2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return DMV_E_CUDA;
+    }
+    wgrad_halo2d_kernel<<<p.slices, kThreads, smem, st>>>(map_a, map_b, p);
+    count_tc_launch();
+    rc = check_launch("wgrad_halo2d_tc");
+    if (rc) return rc;
+    if (p.slices > 1) rc = reduce_partials(reinterpret_cast<const float*>(ws), q.dw, p.out_elems, p.slices, st);
+    return rc;
+}
+
 int run_wgrad(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (whalo2d_eligible(q)) return run_wgrad_halo2d(q, ws, ws_bytes, st);
     if (whalo_eligible(q)) return run_wgrad_halo(q, ws, ws_bytes, st);
     if (!wgrad_eligible(q.Cb, q.Cs, q.kh * q.kw)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: channel counts not covered");
     if (q.stride != 1 && q.stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: stride");
@@ -632,8 +840,26 @@ int tc_thin_wgrad(const void* thin, int thin_dtype, const void* wide, float* dw,
                   int stride, void* ws, size_t ws_bytes, cudaStream_t st) {
     const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
     const int rows = kh * kw * Ct, Kp = thin_patch_cols(kh * kw, Ct);
-    if (!wgrad_eligible(Kp, Cw, 1)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_thin_wgrad: channel counts not covered");
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    if (thin_s2d_eligible(Hb, Wb, Ct, Cw, kh, kw, stride)) {
+        // space-to-depth: stride-1 weight gradient over X2 (halo kernel), then the (shift, block) entries are gathered into dW
+        const S2dGeom g2 = thin_s2d_geom(Hb, Wb, kh, kw);
+        const int S = g2.kh2 * g2.kw2;
+        const size_t Xb = al((size_t)N * (Hb / 2) * (Wb / 2) * 64), Db = al((size_t)S * 32 * Cw * 4);
+        if (!ws || ws_bytes < Xb + Db || ((uintptr_t)ws & 255)) return fail(DMV_E_WORKSPACE, "tc_thin_wgrad: workspace too small or unaligned");
+        uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+        int rc = thin_s2d_prep(thin, thin_dtype, base, N, Hb, Wb, Ct, st);
+        if (rc) return rc;
+        float* dw2 = reinterpret_cast<float*>(base + Xb);
+        WProblem q;
+        q.big = base; q.N = N; q.Hb = Hb / 2; q.Wb = Wb / 2; q.Cb = 32; q.stride = 1;
+        q.small = wide; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cw;
+        q.kh = g2.kh2; q.kw = g2.kw2; q.pt = -g2.dh0; q.pl = -g2.dw0; q.dw = dw2;
+        rc = run_wgrad(q, base + Xb + Db, ws_bytes - Xb - Db, st);
+        if (rc) return rc;
+        return thin_s2d_gather_dw(dw2, dw, Ct, Cw, kh, kw, ph.before, pw.before, g2, st);
+    }
+    if (!wgrad_eligible(Kp, Cw, 1)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_thin_wgrad: channel counts not covered");
     const size_t Pb = al((size_t)N * ph.out * pw.out * Kp * 2), Db = al((size_t)Kp * Cw * 4);
     const size_t parts = tc_wgrad_workspace(1, Kp, Cw, (long long)N * ph.out * pw.out);
     if (!ws || ws_bytes < Pb + Db + parts || ((uintptr_t)ws & 255)) return fail(DMV_E_WORKSPACE, "tc_thin_wgrad: workspace too small or unaligned");

@@ -39,9 +39,10 @@ def timeit(name, fn, flop):
     print("%-34s %8.1f us  %7.1f TFLOP/s" % (name, us, flop / us / 1e6), flush=True)
 
 
-def conv(name, H, k, s, cin, cout):
+def conv(name, H, k, s, cin, cout, f32in=False):
     Ho = -(-H // s)
-    x = torch.randn((B, H, H, cin), device=dev).to(bf)
+    x = torch.randn((B, H, H, cin), device=dev).to(torch.float32 if f32in else bf)
+    xdt = 1 if f32in else 0
     w = (torch.randn((k, k, cin, cout), device=dev) * 0.05).to(bf)
     b = torch.zeros(cout, device=dev)
     y = torch.empty((B, Ho, Ho, cout), device=dev, dtype=bf)
@@ -50,11 +51,12 @@ def conv(name, H, k, s, cin, cout):
     dw = torch.empty((k, k, cin, cout), device=dev)
     ws = ws_for(max(L.dmv_conv_workspace_size(B, H, H, cin, cout, k, k, s), L.dmv_wgrad_workspace_size(B, H, H, cin, cout, k, k, s)))
     flop = 2.0 * B * Ho * Ho * k * k * cin * cout
-    timeit(name + " fwd", lambda: _lib.call("dmv_conv2d_fwd", x.data_ptr(), 0, w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, B, H, H, cin, cout,
+    timeit(name + " fwd", lambda: _lib.call("dmv_conv2d_fwd", x.data_ptr(), xdt, w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, B, H, H, cin, cout,
                                             k, k, s, 1, ws.data_ptr(), ws.numel(), 0, st), flop)
-    timeit(name + " dgrad", lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, cin, cout, k, k, s,
-                                              ws.data_ptr(), ws.numel(), 0, st), flop)
-    timeit(name + " wgrad", lambda: _lib.call("dmv_conv2d_wgrad", x.data_ptr(), 0, dy.data_ptr(), dw.data_ptr(), None, B, H, H, cin, cout, k, k,
+    if not f32in:
+        timeit(name + " dgrad", lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, cin, cout, k, k, s,
+                                                  ws.data_ptr(), ws.numel(), 0, st), flop)
+    timeit(name + " wgrad", lambda: _lib.call("dmv_conv2d_wgrad", x.data_ptr(), xdt, dy.data_ptr(), dw.data_ptr(), None, B, H, H, cin, cout, k, k,
                                               s, ws.data_ptr(), ws.numel(), 0, st), flop)
 
 
@@ -77,6 +79,7 @@ def deconv(name, Ho, k, s, cin, cout, f32out=False):
                                               ws.data_ptr(), ws.numel(), 0, st), flop)
 
 
+conv("e0 c5s2 224 3>32", 224, 5, 2, 3, 32, True)
 conv("e0_0 c5s1 112 32>32", 112, 5, 1, 32, 32)
 conv("e1 c5s2 112 32>32", 112, 5, 2, 32, 32)
 conv("e1_0 c5s1 56 32>32", 56, 5, 1, 32, 32)
