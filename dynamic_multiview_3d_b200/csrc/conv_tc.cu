@@ -1034,14 +1034,40 @@ int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, in
 
 // linear forward: Y[M,N] = X[M,K] Matrix[K,N] + b.  A = X (K-major rows), B = Matrix as stored (MN-major),
 // N tiles of 64 columns so that the weight stream (the whole cost at M = 64) is spread over >= 64 CTAs.
-static int linear_splits(int n_tiles, int kblocks) {
-    int ks = ceil_div(2 * num_sms(), n_tiles);
-    if (ks > kblocks / 4) ks = kblocks / 4;
-    return ks < 1 ? 1 : ks;
+static int linear_ntile() {
+    const char* e = getenv("DMV_LINEAR_NTILE");
+    const int v = e ? atoi(e) : 64;
+    return (v == 64 || v == 128 || v == 256) ? v : 64;
+}
+
+// Split count of a linear layer's contraction: the launch is n_tiles x ks equal tiles on a persistent grid; pick the
+// ks whose tile count fills whole waves of the grid best (a ragged last wave idles most SMs for a whole tile time).
+static int linear_splits(int n_tiles, int kblocks, int n_tile) {
+    if (kblocks < 1 || n_tiles < 1) return 1;
+    const int grid = num_sms() * (n_tile <= 64 ? 2 : 1);
+    int kmax = kblocks / 4;
+    if (kmax < 1) kmax = 1;
+    if (kmax > 32) kmax = 32;
+    int best = 1;
+    double best_eff = -1.0;
+    for (int ks = 1; ks <= kmax; ++ks) {
+        const int tiles = n_tiles * ceil_div(kblocks, ceil_div(kblocks, ks));
+        const int waves = ceil_div(tiles, grid);
+        if (waves > 2) break;
+        const double eff = (double)tiles / ((double)waves * grid);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = ks; }
+    }
+    return best;
+}
+
+static int linear_ntile_for(long long weights) {
+    if (getenv("DMV_LINEAR_NTILE")) return linear_ntile();
+    return weights >= (32ll << 20) ? 128 : 64;      // wider weight boxes for the two 51 M-parameter layers
 }
 
 size_t tc_linear_workspace(int M, int K, int N) {
-    const int a = linear_splits(ceil_div(N, 64), K / 32), b = linear_splits(ceil_div(K, 64), N / 32);
+    const int nt = linear_ntile_for((long long)K * N);
+    const int a = linear_splits(ceil_div(N, nt), K / ((K % 64 == 0) ? 64 : 32), nt), b = linear_splits(ceil_div(K, nt), N / ((N % 64 == 0) ? 64 : 32), nt);
     const size_t fa = (size_t)a * M * N * 4, fb = (size_t)b * M * K * 4;
     return (fa > fb ? fa : fb) + 256;
 }
@@ -1055,8 +1081,8 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int 
     if (rc) return rc;
     Problem q;
     q.src = x; q.N = M; q.Hs = 1; q.Ws = 1; q.Cs = K; q.src_stride = 1;
-    q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = false; q.n_tile = 64; q.b_mode_override = 2;
-    q.k_splits = (M <= 128) ? linear_splits(ceil_div(N, 64), K / ((K % 64 == 0) ? 64 : 32)) : 1;
+    q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = false; q.n_tile = linear_ntile_for((long long)K * N); q.b_mode_override = 2;
+    q.k_splits = (M <= 128) ? linear_splits(ceil_div(N, q.n_tile), K / ((K % 64 == 0) ? 64 : 32), q.n_tile) : 1;
     q.out = y; q.out_f32 = 0; q.out_H = 1; q.out_W = 1; q.n_real = N; q.out_mul = 1;
     q.Jh = 1; q.Jw = 1; q.bias = bias; q.act = act;
     return launch_igemm(q, p, ws, ws_bytes, st);
@@ -1072,8 +1098,8 @@ int tc_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N
     if (rc) return rc;
     Problem q;
     q.src = dy; q.N = M; q.Hs = 1; q.Ws = 1; q.Cs = N; q.src_stride = 1;
-    q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = true; q.n_tile = 64; q.b_mode_override = -1;
-    q.k_splits = (M <= 128) ? linear_splits(ceil_div(K, 64), N / ((N % 64 == 0) ? 64 : 32)) : 1;
+    q.w_hwio = w; q.kh = 1; q.kw = 1; q.w_ci = K; q.w_co = N; q.g_form = true; q.n_tile = linear_ntile_for((long long)K * N); q.b_mode_override = -1;
+    q.k_splits = (M <= 128) ? linear_splits(ceil_div(K, q.n_tile), N / ((N % 64 == 0) ? 64 : 32), q.n_tile) : 1;
     q.out = dx; q.out_f32 = 0; q.out_H = 1; q.out_W = 1; q.n_real = K; q.out_mul = 1;
     q.Jh = 1; q.Jw = 1; q.bias = nullptr; q.act = DMV_ACT_NONE;
     return launch_igemm(q, p, ws, ws_bytes, st);

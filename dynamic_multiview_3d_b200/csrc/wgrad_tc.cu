@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* done_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    float* s_tr = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 1024);   // [4 warps][32 x 32] epilogue transpose tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work item of this CTA
@@ -148,23 +149,34 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         tc_fence_after();
         float* outp = p.out + (long long)slice * p.out_elems;
         const bool have = ch1 > ch0;
+        // The accumulator arrives one ROW per lane; stored as is, a warp's 16-byte stores land 32 rows apart and
+        // the large linear-layer gradients (205 MB) become request-bound.  Each warp therefore transposes 32 x 32
+        // blocks through a private XOR-swizzled shared tile and writes four full 128-byte lines per instruction.
+        float* s_t = s_tr + (warp - 2) * 1024;
         for (int i = 0; i < n_mt; ++i) {
-            const int bi = (mt0 + i) * p.boxes_per_tile + m / p.CB;
+            const int bi = (mt0 + i) * p.boxes_per_tile + m / p.CB;       // warp-uniform: 32 | CB
             const bool ok = bi < p.n_boxes;
-            const long long row = ok ? (long long)p.box[bi].row0 + (m % p.CB) : 0;
+            const long long row0 = ok ? (long long)p.box[bi].row0 + ((quarter * 32) % p.CB) : 0;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * p.n_tile);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld16(taddr + (uint32_t)(c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                 tmem_ld_wait();
-                if (ok) {
-                    float* o = outp + row * p.Cs + nt * p.n_tile + c0;
+                if (!ok) continue;
 #pragma unroll
-                    for (int k = 0; k < 16; k += 4)
-                        *reinterpret_cast<float4*>(o + k) =
-                            have ? make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(s_t + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                        have ? make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = t * 4 + (lane >> 3), cc = lane & 7;
+                    const float4 q = *reinterpret_cast<const float4*>(s_t + rr * 32 + ((cc ^ (rr & 7)) << 2));
+                    *reinterpret_cast<float4*>(outp + (row0 + rr) * p.Cs + nt * p.n_tile + c0 + cc * 4) = q;
                 }
+                __syncwarp();
             }
         }
     }
@@ -764,7 +776,8 @@ int run_wgrad(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (stages > 6) stages = 6;
     if (stages < 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: stage does not fit shared memory");
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    // stages | 1 KB of barriers | 16 KB of epilogue transpose tiles | alignment slack
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 4 * 4096 + 1024;
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("tc wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

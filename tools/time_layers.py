@@ -79,6 +79,33 @@ def deconv(name, Ho, k, s, cin, cout, f32out=False):
                                               ws.data_ptr(), ws.numel(), 0, st), flop)
 
 
+def linear(name, K, N):
+    M = B
+    x = torch.randn((M, K), device=dev).to(bf)
+    w = (torch.randn((K, N), device=dev) * 0.02).to(bf)
+    b = torch.zeros(N, device=dev)
+    y = torch.empty((M, N), device=dev, dtype=bf)
+    dy = torch.randn((M, N), device=dev).to(bf)
+    dx = torch.empty_like(x)
+    dw = torch.empty((K, N), device=dev)
+    ws = ws_for(max(L.dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), L.dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)))
+    flop = 2.0 * M * K * N
+    nb = K * N
+    timeit(name + " fwd", lambda: _lib.call("dmv_linear_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, K, N, 1, ws.data_ptr(),
+                                            ws.numel(), 0, st), flop)
+    timeit(name + " dgrad", lambda: _lib.call("dmv_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, K, N, ws.data_ptr(), ws.numel(),
+                                              0, st), flop)
+    timeit(name + " wgrad", lambda: _lib.call("dmv_linear_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), None, M, K, N, ws.data_ptr(),
+                                              ws.numel(), 0, st), flop)
+    if not filt or filt in name:
+        print("    (%s: weight stream %.1f MB bf16 -> %.1f us at 6.5 TB/s; dW %.1f MB fp32 -> %.1f us)" % (
+            name, nb * 2 / 1e6, nb * 2 / 6.5e6, nb * 4 / 1e6, nb * 4 / 6.5e6))
+
+
+linear("fc1 lin 12544>4096", 12544, 4096)
+linear("a3 lin 4160>4096", 4160, 4096)
+linear("a4 lin 4096>4096", 4096, 4096)
+linear("a5 lin 4096>12544", 4096, 12544)
 conv("e0 c5s2 224 3>32", 224, 5, 2, 3, 32, True)
 conv("e0_0 c5s1 112 32>32", 112, 5, 1, 32, 32)
 conv("e1 c5s2 112 32>32", 112, 5, 2, 32, 32)
