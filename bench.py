@@ -242,7 +242,7 @@ def main():
         conf["algo"] = args.algo
     model = pkg.AppearanceFlowModel(conf)
     if world > 1:
-        data_parallel.attach(model, bucket_mb=32.0)
+        data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128")))
     b = make_batch(BATCH, H, "onehot19", seed=1234, rank=rank)
     host = {k: torch.from_numpy(b[k]).pin_memory() for k in ("image0", "image1", "disp")}
     devb = {k: v.to(dev) for k, v in host.items()}

@@ -151,6 +151,8 @@ class AppearanceFlowModel(object):
 
     # -- checkpoint surface (tf.train.Saver over global variables, train.py:70-71) -----------
     def state_dict(self):
+        if hasattr(self, "_dp") and hasattr(self._dp, "gather_full_state"):
+            self._dp.gather_full_state()        # sharded data parallelism: masters and moments live with their owners
         sd = self.store.state_dict()
         if self.optimizer is not None:
             for k, v in self.store.vars.items():

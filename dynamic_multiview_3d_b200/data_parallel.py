@@ -86,10 +86,213 @@ class GradientAllReducer:
         self.launched = []
 
 
-def attach(model, bucket_mb=32.0, group=None):
-    """Make ``model.train_step`` data-parallel over the default (or given) process group."""
+def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None):
+    """Uniform chunks of the flat buffer for the sharded mode.  Returns (chunks, var2chunks, expected):
+    chunks = [(start, end)] tiling [0, alloc) (every length a multiple of world*256), var2chunks maps a
+    variable name to the chunks it overlaps, expected[c] = number of trainable variables overlapping chunk c."""
+    unit = world * 256
+    chunk_elems = max(unit, (chunk_elems // unit) * unit)
+    assert alloc % unit == 0, "flat buffers must be allocated to a multiple of world*256 elements"
+    chunks = [(s, min(alloc, s + chunk_elems)) for s in range(0, alloc, chunk_elems)]
+    var2chunks, expected = {}, [0] * len(chunks)
+    for name, off, n in var_table:
+        if trainable is not None and name not in trainable:
+            continue
+        cs = list(range(off // chunk_elems, (off + n - 1) // chunk_elems + 1))
+        var2chunks[name] = cs
+        for c in cs:
+            expected[c] += 1
+    return chunks, var2chunks, expected
+
+
+class ShardedGradientReducer:
+    """ZeRO-1 style exchange: per chunk a reduce-scatter of the gradients (each rank receives the sum of
+    its 1/world slice, in place), Adam on the owned slices only (optimizer state and the fp32 masters are
+    updated by their owner), then an all-gather of the refreshed bf16 compute copies.  Against the plain
+    allreduce this moves 25 % fewer bytes over NVLink and divides the HBM-bound Adam pass (15 % of a
+    single-GPU step) by the world size.  Chunks are launched on a side stream as soon as the last
+    gradient overlapping them has been written (backward produces them from the end of the buffer)."""
+
+    def __init__(self, store, chunk_mb=32.0, group=None):
+        self.store = store
+        self.flat = store.flat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # [0, shard_end): weights, sharded; [shard_end, alloc): biases, replicated (their fp32 masters feed the epilogues)
+        self.shard_end = getattr(store, "shard_end", store.alloc)
+        table = [(v.name, v.offset, -(-v.numel // 64) * 64) for v in store.vars.values() if v.offset < self.shard_end]
+        trainable = {v.name for v in store.trainable_vars()}
+        self.chunks, self.var2chunks, self.expected = plan_chunks(table, self.shard_end, int(chunk_mb * (1 << 20) / 4), self.world, trainable)
+        self.pending = list(self.expected)
+        self.rep_names = {v.name for v in store.vars.values() if v.offset >= self.shard_end and v.name in trainable}
+        self.rep_pending = len(self.rep_names)
+        self.cuda = self.flat["grad"].is_cuda
+        self.comm_stream = torch.cuda.Stream(device=self.flat["grad"].device) if self.cuda else None
+        self.launched = []
+        self.native = (not dist.is_initialized()) or dist.get_backend(group) == "nccl"
+        self.adam = None        # ShardedTFAdam: when attached, a chunk's update and bf16 all-gather follow its reduce-scatter
+        self.started = False
+
+    def owned(self, c):
+        s, e = self.chunks[c]
+        n = (e - s) // self.world
+        return s + self.rank * n, s + (self.rank + 1) * n
+
+    def on_grad_ready(self, var):
+        name = var.name if hasattr(var, "name") else var
+        if not self.started:
+            self.started = True
+            if self.adam is not None:
+                self.adam.tick()            # on the main stream, ahead of every chunk of this step
+        if name in self.rep_names:
+            self.rep_pending -= 1
+            if self.rep_pending == 0:
+                self._launch(-1)
+            return
+        for c in self.var2chunks.get(name, ()):
+            self.pending[c] -= 1
+            if self.pending[c] == 0:
+                self._launch(c)
+
+    def _reduce_scatter(self, c):
+        if c < 0:                          # the replicated tail: plain allreduce
+            dist.all_reduce(self.flat["grad"][self.shard_end:self.store.alloc], op=dist.ReduceOp.SUM, group=self.group)
+            return
+        s, e = self.chunks[c]
+        a, b = self.owned(c)
+        g = self.flat["grad"]
+        if self.native:
+            dist.reduce_scatter_tensor(g[a:b], g[s:e], op=dist.ReduceOp.SUM, group=self.group)
+        else:                              # gloo (CPU host-logic tests): same result on the owned slice
+            dist.all_reduce(g[s:e], op=dist.ReduceOp.SUM, group=self.group)
+
+    def _launch(self, c):
+        """Chunk pipeline on the side stream: reduce-scatter -> Adam on the owned slice -> all-gather of the bf16
+        copies.  Every variable overlapping the chunk has finished its backward (dgrad included), so nothing on the
+        main stream reads these weights again in this step and the whole tail overlaps the rest of backward."""
+        if c >= 0:
+            self.launched.append(c)
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.flat["grad"].device))
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                if self.world > 1:
+                    self._reduce_scatter(c)
+                if self.adam is not None and c >= 0:
+                    self.adam.update_chunk(c, self.comm_stream.cuda_stream)
+                    self.all_gather("half", c)
+        elif self.world > 1:
+            self._reduce_scatter(c)
+
+    def finish(self):
+        for c, p in enumerate(self.pending):
+            if p > 0 and self.expected[c] > 0:
+                self._launch(c)
+        if self.rep_pending > 0 and self.rep_names:
+            self._launch(-1)
+        self.rep_pending = len(self.rep_names)
+        self.started = False
+        if self.cuda:
+            torch.cuda.current_stream(self.flat["grad"].device).wait_stream(self.comm_stream)
+        self.order = list(self.launched)
+        self.pending = list(self.expected)
+        self.launched = []
+
+    def all_gather(self, key, c):
+        """In-place all-gather of chunk c of flat[key] from the owners' slices."""
+        if self.world == 1:
+            return
+        s, e = self.chunks[c]
+        a, b = self.owned(c)
+        t = self.flat[key]
+        if self.native:
+            dist.all_gather_into_tensor(t[s:e], t[a:b], group=self.group)
+        else:
+            parts = [torch.empty_like(t[a:b]) for _ in range(self.world)]
+            dist.all_gather(parts, t[a:b].clone(), group=self.group)
+            t[s:e].copy_(torch.cat(parts))
+
+    def gather_full_state(self):
+        """Checkpoint time: every rank gets the complete fp32 masters and Adam moments."""
+        for c in range(len(self.chunks)):
+            if self.expected[c] > 0:
+                for key in ("master", "m", "v"):
+                    self.all_gather(key, c)
+
+
+class ShardedTFAdam:
+    """TFAdam over the slices this rank owns, chunk by chunk; each chunk's bf16 all-gather is enqueued on the
+    side stream right behind its update so the exchange overlaps the remaining updates."""
+
+    def __init__(self, base, red):
+        import ctypes as C
+        self.base, self.red = base, red
+        self.state = base.state
+        self.lr, self.beta1, self.beta2, self.eps, self.grad_scale = base.lr, base.beta1, base.beta2, base.eps, base.grad_scale
+        f = red.flat
+        self.args = {}
+        for c in range(len(red.chunks)):
+            if red.expected[c] == 0:
+                continue
+            a, b = red.owned(c)
+            vp = C.c_void_p * 1
+            self.args[c] = (vp(f["master"].data_ptr() + 4 * a), vp(f["grad"].data_ptr() + 4 * a), vp(f["m"].data_ptr() + 4 * a),
+                            vp(f["v"].data_ptr() + 4 * a), vp(f["half"].data_ptr() + 2 * a), (C.c_longlong * 1)(b - a))
+        a, b = red.shard_end, red.store.alloc     # replicated biases: every rank updates all of them
+        self.rep = None
+        if b > a and red.rep_names:
+            vp = C.c_void_p * 1
+            self.rep = (vp(f["master"].data_ptr() + 4 * a), vp(f["grad"].data_ptr() + 4 * a), vp(f["m"].data_ptr() + 4 * a),
+                        vp(f["v"].data_ptr() + 4 * a), vp(f["half"].data_ptr() + 2 * a), (C.c_longlong * 1)(b - a))
+
+    def tick(self):
+        from . import functional as F
+        st = torch.cuda.current_stream(self.red.flat["grad"].device).cuda_stream
+        F._tag[0] = "adam"
+        F.call("dmv_adam_tick", self.state.data_ptr(), self.lr, self.beta1, self.beta2, st)
+
+    def update_chunk(self, c, st):
+        from . import functional as F
+        p, g, m, v, h, n = self.args[c]
+        F._tag[0] = "adam"
+        F.call("dmv_adam_multi", p, g, m, v, h, n, 1, self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale, st)
+
+    def step(self):
+        """Called after ShardedGradientReducer.finish(): the sharded chunks are already updated and gathered (side
+        stream, joined); what is left is the replicated bias tail, whose allreduce has completed."""
+        from . import functional as F
+        if self.rep is not None:
+            st = torch.cuda.current_stream(self.red.flat["grad"].device).cuda_stream
+            p, g, m, v, h, n = self.rep
+            F._tag[0] = "adam"
+            F.call("dmv_adam_multi", p, g, m, v, h, n, 1, self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale, st)
+
+    @property
+    def t(self):
+        return int(self.state[3].item())
+
+
+def attach(model, bucket_mb=32.0, group=None, mode=None):
+    """Make ``model.train_step`` data-parallel over the default (or given) process group.
+    mode "sharded" (default): reduce-scatter + owner-only Adam + bf16 all-gather; "allreduce": replicated Adam."""
+    import os
     store = model.store
-    table = [(v.name, v.offset, -(-v.numel // 64) * 64) for v in store.vars.values()]
+    mode = mode or os.environ.get("DMV_DP_MODE", "sharded")
+    if mode == "sharded":
+        red = ShardedGradientReducer(store, bucket_mb, group)
+        store.grad_ready_hook = red.on_grad_ready
+        model._dp = red
+        model.world_size = red.world
+        if red.world > 1:
+            dist.broadcast(store.flat["master"], src=0, group=group)
+            store.refresh_half()
+        if model.optimizer is not None:
+            model.optimizer = ShardedTFAdam(model.optimizer, red)
+            red.adam = model.optimizer
+        return red
+    table = sorted(((v.name, v.offset, -(-v.numel // 64) * 64) for v in store.vars.values()), key=lambda t: t[1])
     red = GradientAllReducer(store.flat["grad"], table, bucket_mb, group, {v.name for v in store.trainable_vars()})
     store.grad_ready_hook = red.on_grad_ready
     model._dp = red

@@ -34,7 +34,7 @@ class TFAdam:
 
     def _coalesce(self):
         runs = []
-        for v in self.vars:
+        for v in sorted(self.vars, key=lambda u: u.offset):
             pad_end = v.offset + -(-v.numel // 64) * 64
             if runs and runs[-1][1] == v.offset:
                 runs[-1][1] = pad_end

@@ -124,23 +124,36 @@ class VariableStore:
         receive a gradient (the dead FCs of highdim_angle.py:8-9) must be excluded."""
         if self.finalized:
             return
+        # Weights first (creation order), biases last: the fp32 bias masters are read directly by the conv / linear
+        # epilogues, so under sharded data parallelism (data_parallel.py) they must stay replicated on every rank;
+        # keeping them in one contiguous tail region makes that a single small allreduce.
         total = 0
         for v in self.vars.values():
             if trainable is not None:
                 v.trainable = bool(trainable(v.name))
-            v.offset = total
-            total += int(math.ceil(v.numel / _ALIGN)) * _ALIGN
+        for v in self.vars.values():
+            if not v.name.endswith("/b"):
+                v.offset = total
+                total += int(math.ceil(v.numel / _ALIGN)) * _ALIGN
+        self.shard_end = total = -(-total // 16384) * 16384
+        for v in self.vars.values():
+            if v.name.endswith("/b"):
+                v.offset = total
+                total += int(math.ceil(v.numel / _ALIGN)) * _ALIGN
         dev = self.device
         self.total = total
+        # the buffers are allocated to a multiple of 16384 elements so that data-parallel shards (world x 256
+        # elements, data_parallel.py) tile them exactly; the tail stays zero
+        self.alloc = alloc = -(-total // 16384) * 16384
         if dev.type == "meta":
             self.finalized = True
             return
         self.flat = {
-            "master": torch.zeros(total, dtype=torch.float32, device=dev),
-            "grad": torch.zeros(total, dtype=torch.float32, device=dev),
-            "m": torch.zeros(total, dtype=torch.float32, device=dev),
-            "v": torch.zeros(total, dtype=torch.float32, device=dev),
-            "half": torch.zeros(total, dtype=torch.bfloat16, device=dev),
+            "master": torch.zeros(alloc, dtype=torch.float32, device=dev),
+            "grad": torch.zeros(alloc, dtype=torch.float32, device=dev),
+            "m": torch.zeros(alloc, dtype=torch.float32, device=dev),
+            "v": torch.zeros(alloc, dtype=torch.float32, device=dev),
+            "half": torch.zeros(alloc, dtype=torch.bfloat16, device=dev),
         }
         for v in self.vars.values():
             sl = slice(v.offset, v.offset + v.numel)

@@ -68,9 +68,12 @@ def test_variable_tables_match_reference_graph(cls, kind, H):
     dead = [v.name for v in m.store.vars.values() if not v.trainable]
     assert dead == (["a0/Matrix", "a0/b", "a1/Matrix", "a1/b"] if kind == "highdim" else [])
     # flat offsets are 64-element aligned and non-overlapping
-    offs = [(v.offset, v.numel) for v in m.store.vars.values()]
+    # (weights in creation order, then the biases in one tail region that sharded data parallelism keeps replicated)
+    offs = sorted((v.offset, v.numel) for v in m.store.vars.values())
     assert all(o % 64 == 0 for o, _ in offs)
     assert all(o2 >= o1 + n1 for (o1, n1), (o2, _) in zip(offs, offs[1:]))
+    assert m.store.shard_end % 16384 == 0 and m.store.alloc % 16384 == 0
+    assert all((v.offset >= m.store.shard_end) == v.name.endswith("/b") for v in m.store.vars.values())
 
 
 @pytest.mark.parametrize("head", ["tanh", "flow"])
@@ -158,6 +161,79 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+_SHARD_WORKER = r"""
+import os, sys, types, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from dynamic_multiview_3d_b200.data_parallel import ShardedGradientReducer, plan_chunks
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["MASTER_PORT"], rank=rank, world_size=world)
+sizes = [64, 192, 4096, 64, 8192, 128]
+vars_, off = {}, 0
+for i, n in enumerate(sizes):
+    vars_["v%%d" %% i] = types.SimpleNamespace(name="v%%d" %% i, offset=off, numel=n, trainable=(i != 3)); off += n
+alloc = -(-off // 16384) * 16384
+store = types.SimpleNamespace(vars=vars_, alloc=alloc, trainable_vars=lambda: [v for v in vars_.values() if v.trainable],
+                              flat={k: torch.zeros(alloc) for k in ("grad", "master", "m", "v", "half")})
+red = ShardedGradientReducer(store, chunk_mb=2048 * 4 / (1 << 20))        # 2048-element chunks
+assert all((e - s) %% (world * 256) == 0 for s, e in red.chunks) and red.chunks[-1][1] == alloc
+g = store.flat["grad"]
+for i in reversed(range(6)):
+    if i == 3: continue
+    v = vars_["v%%d" %% i]
+    g[v.offset:v.offset + v.numel] = float(rank + 1) * (i + 1)
+    red.on_grad_ready(v)
+red.finish()
+tot = float(sum(range(1, world + 1)))
+exp = torch.zeros(alloc)
+for i, v in enumerate(vars_.values()):
+    if i != 3: exp[v.offset:v.offset + v.numel] = tot * (i + 1)
+for c in range(len(red.chunks)):                  # the OWNED slice of every live chunk holds the global sum
+    if red.expected[c] == 0: continue
+    a, b = red.owned(c)
+    assert torch.equal(g[a:b], exp[a:b]), (c, a, b)
+# owner-only update, then the all-gather restores identical replicas
+for c in range(len(red.chunks)):
+    if red.expected[c] == 0: continue
+    a, b = red.owned(c)
+    store.flat["half"][a:b] = g[a:b] * 0.5
+    red.all_gather("half", c)
+live = torch.zeros(alloc, dtype=torch.bool)
+for c, (s, e) in enumerate(red.chunks):
+    if red.expected[c]: live[s:e] = True
+assert torch.equal(store.flat["half"][live], (exp * 0.5)[live])
+assert red.pending == red.expected and red.launched == []
+print("rank", rank, "ok", len(red.chunks), "chunks")
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_reduce_scatter_world_size_2_gloo(tmp_path):
+    script = tmp_path / "ws.py"
+    script.write_text(_SHARD_WORKER % ROOT)
+    port = str(31500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
+def test_chunk_plan_tiles_the_buffer():
+    from dynamic_multiview_3d_b200.data_parallel import plan_chunks
+    table, off = [], 0
+    for i, n in enumerate([64, 128, 1 << 20, 64, 3 << 20, 256]):
+        table.append(("v%d" % i, off, n))
+        off += n
+    alloc = -(-off // 16384) * 16384
+    chunks, v2c, exp = plan_chunks(table, alloc, 1 << 20, 8, {"v%d" % i for i in range(6)})
+    assert chunks[0][0] == 0 and chunks[-1][1] == alloc and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+    assert all((e - s) % (8 * 256) == 0 for s, e in chunks)
+    assert v2c["v4"] == [1, 2, 3, 4] and v2c["v0"] == [0] and sum(exp) == sum(len(c) for c in v2c.values())
 
 
 def test_synthetic_batches_are_deterministic_and_in_range():

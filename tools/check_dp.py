@@ -1,0 +1,49 @@
+"""torchrun --nproc-per-node N tools/check_dp.py : the sharded (reduce-scatter + owner Adam + all-gather) and the
+allreduce data-parallel modes must produce the same parameters, identical on every rank."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import dynamic_multiview_3d_b200 as pkg  # noqa: E402
+from dynamic_multiview_3d_b200 import data_parallel  # noqa: E402
+from dynamic_multiview_3d_b200.synthetic import make_batch  # noqa: E402
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+res = {}
+for mode in ("allreduce", "allreduce2", "sharded"):
+    model = pkg.AppearanceFlowModel({"batch_size": 4, "learning_rate": 1e-3, "image_size": 64, "viewpoint_dim": 19, "seed": 0})
+    data_parallel.attach(model, bucket_mb=4.0, mode=mode.rstrip("2"))
+    b = make_batch(4, 64, "onehot19", seed=7, rank=rank)
+    args = [torch.from_numpy(b[k]).to(dev) for k in ("image0", "image1", "disp")]
+    losses = [float(model.train_step(*args)) for _ in range(3)]
+    sd = model.state_dict()
+    res[mode + "_sd"] = {k: v.float() for k, v in sd.items() if not k.startswith("__")}
+    res[mode] = (losses, torch.cat([sd[k].reshape(-1).float() for k in sorted(sd) if not k.startswith("__")]).to(dev))
+    half = model.store.flat["half"][:model.store.total].float()
+    ref = half.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(half, ref), "bf16 replicas differ across ranks in mode " + mode
+la2, pa2 = res["allreduce2"]
+print("rank %d run-to-run (allreduce twice) max rel param diff %.3g" % (rank, float((res["allreduce"][1] - pa2).abs().max() / pa2.abs().max())))
+la, pa = res["allreduce"]
+ls, ps = res["sharded"]
+if rank == 0:
+    rows = []
+    for k, v in res["allreduce_sd"].items():
+        w = res["sharded_sd"][k]
+        rows.append((float((v - w).abs().max() / max(float(v.abs().max()), 1e-12)), k, tuple(v.shape)))
+    for r in sorted(rows, reverse=True)[:12]:
+        print("   diff %.3g %s %s" % r)
+err = float((pa - ps).abs().max() / pa.abs().max())
+print("rank %d losses allreduce %s sharded %s  max rel param diff %.3g" % (rank, la, ls, err))
+assert err < 1e-5, err
+dist.barrier()
+if rank == 0:
+    print("check_dp ok")
+os._exit(0)
