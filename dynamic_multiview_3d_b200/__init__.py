@@ -8,6 +8,7 @@ from . import _lib, functional, tf_utils  # noqa: F401
 from .appearance_flow_model import (AppearanceFlowModel, AppearanceFlowTinghui, AppFlowHighDimAngle,  # noqa: F401
                                     AppFlowLowDimAngle)
 from .main_model import Base_Prediction_Model  # noqa: F401
+from .multiobject_appflow import MultiObjectAppFlow, MultiViewFusionAppFlow  # noqa: F401
 from .optimizer import TFAdam  # noqa: F401
 from .variables import VariableStore, use_store  # noqa: F401
 

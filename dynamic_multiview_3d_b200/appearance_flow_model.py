@@ -49,9 +49,7 @@ class AppearanceFlowModel(object):
         self.flow_field = self.gen = self.loss = None
         self.optimizer = None
         # "graph build": one forward on zeros creates every variable in reference order
-        B = self.batch_size
-        z_img = torch.zeros([B] + self.image_shape, dtype=torch.float32, device=self.device)
-        z_disp = torch.zeros([B, self.viewpoint_dim], dtype=torch.float32, device=self.device)
+        z_img, z_disp = self._zeros_for_build()
         if self.device.type == "meta":
             with torch.no_grad(), F.meta_mode():
                 self.forward(z_img, z_disp)
@@ -62,6 +60,11 @@ class AppearanceFlowModel(object):
         self.t_vars = self.store.trainable_vars()
         if build_loss and self.device.type != "meta":
             self.optimizer = TFAdam(self.store, conf["learning_rate"])
+
+    def _zeros_for_build(self):
+        B = self.batch_size
+        return (torch.zeros([B] + self.image_shape, dtype=torch.float32, device=self.device),
+                torch.zeros([B, self.viewpoint_dim], dtype=torch.float32, device=self.device))
 
     # dead variables of the high-dim viewpoint encoder receive no gradient (TF skips None grads)
     def _trainable(self, name):
@@ -107,6 +110,7 @@ class AppearanceFlowModel(object):
         d2_0 = conv2d_msra(d2, 64, 5, 5, 1, 1, "d2_0", act=a, algo=g)
         d1 = deconv2d_msra(d2_0, [B, 16 * h5, 16 * h5, 32], 5, 5, 2, 2, "d1", act=a, algo=g)
         d1_0 = conv2d_msra(d1, 32, 5, 5, 1, 1, "d1_0", act=a, algo=g)
+        self._last_decoder = d1_0            # subclasses hang further heads here (multi-view confidence)
         # flow head: no activation (appearance_flow_model.py:125); fp32 out for the sampler
         return deconv2d_msra(d1_0, [B, H, H, 2], 5, 5, 2, 2, "flow_field", act=None, algo=g, out_dtype=torch.float32)
 

@@ -61,3 +61,40 @@ def make_batch(batch, size=224, viewpoint="onehot19", seed=1234, rank=0, depth=F
     if depth:
         out.update(depth0=depth0, depth1=depth1, mask1=mask1)
     return out
+
+
+def make_multiobject_batch(batch, size=128, seed=1234, rank=0):
+    """Two-object scenes under the tensor names of read_tf_records_multobj.py:65-80 / multiobject_appflow.py:31-43:
+    two blobs (objects 0 and 1) seen from a source and a target viewpoint, their indicator masks, the per-object
+    target renders (``*_only0/1``) and depth maps (far plane 1.0, objects at 0.3-0.6)."""
+    rng = np.random.default_rng(seed + rank)
+    H = W = size
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    names3 = ["image0", "image1", "image1_only0", "image1_only1"]
+    names1 = ["image0_mask0", "image0_mask1", "image1_mask0", "image1_mask1", "depth0", "depth1", "depth1_only0", "depth1_only1"]
+    out = {k: np.full((batch, H, W, 3), 0.5, np.float32) for k in names3}
+    out.update({k: np.zeros((batch, H, W, 1), np.float32) for k in names1 if "mask" in k})
+    out.update({k: np.ones((batch, H, W, 1), np.float32) for k in names1 if "depth" in k})
+    disp = np.zeros((batch, 2), np.float32)
+
+    def ell(cx, cy, yaw, a, b):
+        c, s = np.cos(yaw), np.sin(yaw)
+        u = ((xx - cx) * c + (yy - cy) * s) / a
+        v = (-(xx - cx) * s + (yy - cy) * c) / b
+        return (u * u + v * v) <= 1.0
+
+    for n in range(batch):
+        daz = rng.uniform(-0.6, 0.6)
+        disp[n] = (0.0, daz)
+        for ob in range(2):
+            col = rng.uniform(0.1, 0.9, size=3).astype(np.float32)
+            cx, cy = rng.uniform(0.3, 0.7) * W, rng.uniform(0.3, 0.7) * H
+            yaw, dval = rng.uniform(0, np.pi), rng.uniform(0.3, 0.6)
+            m0, m1 = ell(cx, cy, yaw, 0.18 * W, 0.09 * H), ell(cx, cy, yaw + daz, 0.18 * W, 0.09 * H)
+            out["image0"][n][m0] = col; out["image0_mask%d" % ob][n][m0] = 1.0; out["depth0"][n][m0] = dval
+            out["image1"][n][m1] = col; out["image1_mask%d" % ob][n][m1] = 1.0; out["depth1"][n][m1] = dval
+            out["image1_only%d" % ob][n][m1] = col; out["depth1_only%d" % ob][n][m1] = dval
+    for k in names3:
+        out[k] = np.clip(out[k] + rng.normal(0, 0.02, out[k].shape).astype(np.float32), 0, 1)
+    out["displacement"] = disp
+    return out

@@ -75,7 +75,9 @@ def install_reference_aliases():
     }
     try:
         from . import main_model as mm
+        from . import multiobject_appflow as mo
         names["main_model"] = mm
+        names["multiobject_appflow"] = mo
     except ImportError:
         pass
     for k, mod in names.items():

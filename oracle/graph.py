@@ -308,7 +308,7 @@ def _decode_angle(ops, P, disp, kind):
     raise ValueError(kind)
 
 
-def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False):
+def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False, extra_heads=None):
     """appearance_flow_model.py:83-127 (kind base/highdim/lowdim) or
     appearance_flow_tinghui.py:13-46 (kind tinghui).  image0 NHWC [B,H,H,3], disp [B,V].
     Returns dict with flow_field, warp_pts, gen (NHWC) and, if keep, every activation."""
@@ -362,9 +362,13 @@ def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False):
         d = D("d2", d, 8 * h5, 32); d = C("d2_0", d, 1)
         d = D("d1", d, 16 * h5, 32); d = C("d1_0", d, 1)
         flow = D("flow_field", d, H, 2, 2, None)
+        # further linear heads on the last decoder activation (config 5's confidence logit)
+        extra = {n: ops.nhwc(ops.deconv(d, P[n + "/w"], (B, H, H, c), 2)) for n, c in (extra_heads or [])}
     warp = ops.warp_pts(flow)
     gen = ops.resample(x, warp)
     out = {"flow_field": ops.nhwc(flow), "warp_pts": warp, "gen": ops.nhwc(gen)}
+    if extra_heads:
+        out["heads"] = extra
     if keep:
         out["acts"] = {k: (ops.nhwc(v) if getattr(v, "ndim", 0) == 4 else v) for k, v in acts.items()}
     return out
@@ -506,3 +510,123 @@ def fuse_views(ops, gens, logits):
     Definition adopted in SURVEY 8(f)-3 (after Zhou et al. 2016) -- parity unpinned."""
     w = ops.softmax_views(logits)
     return (w * gens).sum(0)
+
+
+# --- M4 : multiobject_appflow.py ------------------------------------------------ #
+_MO_INPUTS = [("use_color", "image0", "pre_image0_f", 3), ("use_depth", "depth0", "pre_dimage0_f", 1),
+              (None, "image0_mask0", "pre_mask0_ob0", 1), (None, "image0_mask1", "pre_mask0_ob1", 1)]
+
+
+def _mo_heads(conf):
+    """Decoder heads in the order multiobject_appflow.py:189-218 pops them: (attribute, scope, kind)."""
+    heads = []
+    if "use_color" in conf:
+        if "combination_image" in conf:
+            heads.append(("gen_image1", "dec_image1", "flow"))
+        if "gen_sep_images" in conf:
+            heads += [("gen_image1_only0", "dec_image1_only0", "flow"), ("gen_image1_only1", "dec_image1_only1", "flow")]
+    if "use_depth" in conf:
+        if "combination_image" in conf:
+            heads.append(("gen_depth1", "dec_dimage1_f", "tanh"))
+        if "gen_sep_images" in conf:
+            heads += [("gen_depth1_only0", "dec_depth1_only0", "tanh"), ("gen_depth1_only1", "dec_depth1_only1", "tanh")]
+    if "predict_target_masks" in conf:
+        heads += [("gen_image1_mask0", "dec_image1_mask0", "tanh"), ("gen_image1_mask1", "dec_image1_mask1", "tanh")]
+    return heads
+
+
+def multiobject_param_shapes(H, V, conf):
+    """MultiObjectAppFlow (multiobject_appflow.py:80-221): variables in creation order."""
+    s = {}
+    n_in = 0
+    for key, _, scope, cin in _MO_INPUTS:
+        if key is None or key in conf:
+            _pre_encoder_shapes(s, scope, cin); n_in += 1
+    heads = _mo_heads(conf)
+    _trunk_shapes(s, H, V, n_in, len(heads), fully_conv="fully_conv" in conf)
+    for _, scope, kind in heads:
+        _decoder_shapes(s, scope, 2 if kind == "flow" else 1)
+    return s
+
+
+def multiobject_forward(ops, params, conf, batch):
+    """multiobject_appflow.py:123-221.  batch: dict of NHWC arrays under the reference's attribute names.
+    Every flow head samples image0 (:193-198); split_list.pop() hands out channel groups from the END."""
+    P = {k: ops.asarray(v) for k, v in params.items()}
+    B, H = batch["image0"].shape[0], batch["image0"].shape[1]
+    feats = []
+    for key, attr, scope, _ in _MO_INPUTS:
+        if key is None or key in conf:
+            feats.append(_pre_encode(ops, P, ops.from_nhwc(batch[attr]), scope))
+    heads = _mo_heads(conf)
+    d3_0 = _trunk(ops, P, ops.concat(feats, 3), ops.asarray(batch["displacement"]), B, H, fully_conv="fully_conv" in conf)
+    split = ops.split_c(d3_0, len(heads))
+    src = ops.from_nhwc(batch["image0"])
+    out = {}
+    for attr, scope, kind in heads:
+        pre = _decode(ops, P, split.pop(), scope, B, H, 2 if kind == "flow" else 1)
+        out[attr] = ops.nhwc(ops.resample(src, ops.warp_pts(pre))) if kind == "flow" else ops.nhwc(ops.tanh(pre))
+    return out
+
+
+def multiobject_loss(ops, out, conf, batch):
+    """multiobject_appflow.py:223-283."""
+    perm = (lambda x: x.permute(0, 3, 1, 2)) if ops.name == "torch-cpu" else (lambda x: x)
+    A = lambda k: perm(ops.asarray(batch[k]))
+    G = lambda k: perm(out[k])
+    tot = 0.0
+
+    def pair(gen, tgt, mask, factor):
+        if "masked_image_loss" in conf:
+            return ops.masked_l2(G(gen), A(tgt), A(mask)) * factor
+        return ops.euclidean(G(gen), A(tgt)) * factor
+
+    if "use_color" in conf:
+        if "combination_image" in conf:
+            tot = tot + ops.euclidean(G("gen_image1"), A("image1"))
+        if "gen_sep_images" in conf:
+            tot = tot + pair("gen_image1_only0", "image1_only0", "image1_mask0", 1.0)
+            tot = tot + pair("gen_image1_only1", "image1_only1", "image1_mask1", 1.0)
+    if "use_depth" in conf:
+        f = conf["use_depth"]
+        if "combination_image" in conf:
+            tot = tot + ops.euclidean(G("gen_depth1"), A("depth1"))          # :260 -- no depth factor on the combined image
+        if "gen_sep_images" in conf:
+            tot = tot + pair("gen_depth1_only0", "depth1_only0", "image1_mask0", f)
+            tot = tot + pair("gen_depth1_only1", "depth1_only1", "image1_mask1", f)
+    if "predict_target_masks" in conf:
+        f = conf["predict_target_masks"]
+        tot = tot + ops.euclidean(G("gen_image1_mask0"), A("image1_mask0")) * f
+        tot = tot + ops.euclidean(G("gen_image1_mask1"), A("image1_mask1")) * f
+    return tot
+
+
+# --- config 5 : multi-view appearance flow with confidence fusion (NOT in the reference) ---------- #
+def multiview_param_shapes(H, V):
+    """The single-view graph (appearance_flow_model.py:83-127) plus a 1-channel confidence head `conf_field`
+    next to `flow_field`; the same weights serve every source view."""
+    s = appflow_param_shapes(H, V, "base")
+    _deconv(s, "conf_field", 5, 1, 32)
+    return s
+
+
+def multiview_forward(ops, params, images0, disps):
+    """images0 [Vw,B,H,H,3] source views, disps [Vw,B,V] their viewpoint change to the target.  Every view runs
+    the single-view network (shared weights); view v yields gen_v = warp(src_v, flow_v) and a confidence logit;
+    fused = sum_v softmax_v(logit)_v * gen_v   (after Zhou et al. 2016)."""
+    Vw = images0.shape[0]
+    gens, logits, flows = [], [], []
+    for v in range(Vw):
+        o = appearance_flow_forward(ops, params, images0[v], disps[v], "base", extra_heads=[("conf_field", 1)])
+        gens.append(o["gen"]); logits.append(o["heads"]["conf_field"]); flows.append(o["flow_field"])
+    stack = (lambda xs: np.stack(xs, 0)) if ops.name == "numpy" else (lambda xs: __import__("torch").stack(xs, 0))
+    gens, logits = stack(gens), stack(logits)
+    return {"gens": gens, "logits": logits, "flows": stack(flows), "fused": fuse_views(ops, gens, logits)}
+
+
+def multiview_loss(ops, out, image1, mode="l2"):
+    tgt = ops.asarray(image1)
+    fused = out["fused"]
+    if ops.name == "torch-cpu":
+        fused, tgt = fused.permute(0, 3, 1, 2), tgt.permute(0, 3, 1, 2)
+    return ops.euclidean(fused, tgt) if mode == "l2" else ops.l1(fused, tgt)

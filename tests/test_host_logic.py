@@ -107,6 +107,33 @@ def test_reference_conf_loads_unchanged(tmp_path):
     assert train.checkpoint_iteration("/x/y/model120000") == 120000
 
 
+MO_CONFS = [{"use_color": "", "use_depth": 0.1, "combination_image": "", "gen_sep_images": "", "predict_target_masks": 0.1},
+            {"use_color": "", "combination_image": "", "fully_conv": ""}, {"use_depth": 1.0, "gen_sep_images": "", "masked_image_loss": ""}]
+
+
+@pytest.mark.parametrize("extra", MO_CONFS)
+def test_multiobject_variable_table_matches_reference_graph(extra):
+    """MultiObjectAppFlow creates the variables of multiobject_appflow.py:123-221 in the reference's order."""
+    import dynamic_multiview_3d_b200 as pkg
+    from oracle import graph as G
+    conf = dict({"batch_size": 2, "learning_rate": 1e-4, "image_size": 64, "viewpoint_dim": 2}, **extra)
+    m = pkg.MultiObjectAppFlow(conf, device="meta")
+    shapes = G.multiobject_param_shapes(64, 2, conf)
+    assert list(shapes) == list(m.store.vars)
+    for k, (_, shp) in shapes.items():
+        assert tuple(shp) == m.store.vars[k].shape, k
+    assert [h[0] for h in G._mo_heads(conf)] == [h[0] for h in m.heads]
+
+
+def test_multiview_variable_table():
+    import dynamic_multiview_3d_b200 as pkg
+    from oracle import graph as G
+    m = pkg.MultiViewFusionAppFlow({"batch_size": 2, "learning_rate": 1e-4, "image_size": 64, "viewpoint_dim": 2, "num_views": 4}, device="meta")
+    shapes = G.multiview_param_shapes(64, 2)
+    assert list(shapes) == list(m.store.vars)
+    assert tuple(m.gens.shape) == (4, 2, 64, 64, 3) and tuple(m.logits.shape) == (4, 2, 64, 64)
+
+
 def test_bucket_plan_is_reverse_contiguous():
     from dynamic_multiview_3d_b200.data_parallel import plan_buckets
     table, off = [], 0
