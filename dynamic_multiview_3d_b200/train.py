@@ -112,6 +112,7 @@ def main(argv=None):
     ap.add_argument("--device", default="0", help="the value for CUDA_VISIBLE_DEVICES")
     ap.add_argument("--pretrained", default=None, help="path to model file from which to resume training")
     ap.add_argument("--synthetic", action="store_true", default=True, help="synthetic car-render batches (no TFRecords)")
+    ap.add_argument("--tfrecords", action="store_true", help="read conf['data_dir'] TFRecords (read_tf_records.py) instead of synthetic batches")
     ap.add_argument("--num_iterations", type=int, default=None)
     args = ap.parse_args(argv)
     os.environ.setdefault("CUDA_VISIBLE_DEVICES", str(args.device))
@@ -132,9 +133,17 @@ def main(argv=None):
     step = GraphedTrainStep(model)
     V = "onehot19" if model.viewpoint_dim == 19 else "disp2"
     t_iter = []
+    reader = None
+    if args.tfrecords:                       # train.py:57 load_tfrec=True -> read_tf_records.build_tfrecord_input
+        from .read_tf_records import build_tfrecord_input
+        reader = build_tfrecord_input(dict(conf, image_size=model.image_shape[0]), training=True)
     for itr in range(itr_0, conf["num_iterations"] + 1):
         t0 = time.time()
-        batch = make_batch(model.batch_size, model.image_shape[0], V, seed=1234 + itr)
+        if reader is not None:
+            fb = reader.float_batch()
+            batch = {"image0": fb["image0"], "image1": fb["image1"], "disp": fb["displacement"]}
+        else:
+            batch = make_batch(model.batch_size, model.image_shape[0], V, seed=1234 + itr)
         loss = step(torch.from_numpy(batch["image0"]).pin_memory(), torch.from_numpy(batch["image1"]).pin_memory(),
                     torch.from_numpy(batch["disp"]).pin_memory())
         if itr % 10 == 0:
