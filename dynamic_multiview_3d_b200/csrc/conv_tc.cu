@@ -56,6 +56,8 @@ struct IgemmParams {
     int k_splits;                 // linear layers: the contraction is cut into k_splits ranges (fp32 partials + finish kernel)
     long long split_stride;       // elements between the partial outputs of consecutive splits
     int halo_pitch, halo_h, min_dh, min_dw;   // halo kernel: window rows x pitch pixels, origin offset of the window
+    int planes, plane_bytes;      // halo kernel over a stride-2 source: the two row-parity planes of the parity view are separate
+                                  // windows (tap.ph selects one); the column parity is folded into the 2C channels of a row
     int d2s, d2s_c;               // sub-pixel form: column (class, c) of a tile row goes to output pixel (2*jh + py, 2*jw + px), channel c
     TapClass cls[4];
     Tap taps[kMaxTaps];
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     const int ntaps = c.tap_count;
     const int wtile_bytes = p.n_pad * kRowBytes;
     const int a_bytes = p.halo_h * p.halo_pitch * kRowBytes;
-    const int a_stage = (a_bytes + 1023) & ~1023;
+    const int a_stage = p.planes * p.plane_bytes;          // plane_bytes = a_bytes rounded up to 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;
     uint8_t* s_a = smem + (size_t)ntaps * wtile_bytes;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     }
     if (threadIdx.x < ntaps) {      // MMA operand descriptors, computed once
         const Tap& tp = p.taps[c.tap_begin + threadIdx.x];
-        s_aoff[threadIdx.x] = (uint32_t)(((tp.dh - p.min_dh) * p.halo_pitch + (tp.dw - p.min_dw)) * kRowBytes) >> 4;
+        s_aoff[threadIdx.x] = (uint32_t)(((tp.dh - p.min_dh) * p.halo_pitch + (tp.dw - p.min_dw)) * kRowBytes + tp.ph * p.plane_bytes) >> 4;
         s_bdesc[threadIdx.x] = make_kmajor_desc(smem_u32(s_w) + (uint32_t)(threadIdx.x * wtile_bytes), kRowBytes);
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -437,8 +439,10 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
-                tma_load_5d(s_a + (size_t)stage * a_stage, &map_a, &full_bar[stage], 0, tw * 8 + p.min_dw, 0, th * 16 + p.min_dh, t);
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(a_bytes * p.planes));
+                for (int pl = 0; pl < p.planes; ++pl)
+                    tma_load_5d(s_a + (size_t)stage * a_stage + (size_t)pl * p.plane_bytes, &map_a, &full_bar[stage], 0, tw * 8 + p.min_dw, pl,
+                                th * 16 + p.min_dh, t);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -593,7 +597,9 @@ struct Problem {
 
 int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_bytes, cudaStream_t st) {
     const int Cc = q.Cs;                            // contraction channels per tap
-    const int KC = (Cc % 64 == 0) ? 64 : 32;
+    if (p.planes != 2) p.planes = 1;
+    const int KC = (p.planes == 2) ? 2 * Cc : ((Cc % 64 == 0) ? 64 : 32);      // planes == 2: a window row holds (pw, c) = 2C channels
+    if (p.planes == 2 && (Cc != 32 || q.src_stride != 2)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: stride-2 halo needs 32 source channels");
     if (Cc % 32 != 0) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: contraction channels must be a multiple of 32");
     if (q.n_tile == 0 && q.n_real > 256) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: more than 256 output channels");
     if (((uintptr_t)q.src & 15) || ((uintptr_t)q.w_hwio & 15) || ((uintptr_t)q.out & 15))
@@ -603,7 +609,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     p.n_tiles = ceil_div(q.n_real, p.n_pad);
     p.k_splits = 1;
     p.split_stride = 0;
-    p.kc_per_tap = Cc / KC;
+    p.kc_per_tap = (p.planes == 2) ? 1 : Cc / KC;
     p.c_plane = Cc;
     p.Jh = q.Jh; p.Jw = q.Jw; p.Nimg = q.N;
     choose_tile(q.Jh, q.Jw, q.N, p.BW, p.BH, p.NB);
@@ -622,7 +628,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     bool halo_ok = false;
     int halo_stages = 0, halo_ctas_per_sm = 1;
     size_t halo_smem = 0;
-    if (q.src_stride == 1 && p.num_classes == 1 && p.kc_per_tap == 1 && p.n_tiles == 1 && p.b_mode != 2 && q.out_mul == 1 &&
+    if ((q.src_stride == 1 || p.planes == 2) && p.num_classes == 1 && p.kc_per_tap == 1 && p.n_tiles == 1 && p.b_mode != 2 && q.out_mul == 1 &&
         q.Jh * q.Jw >= 256 && !getenv("DMV_NO_HALO")) {
         int dh0 = 1 << 20, dh1 = -(1 << 20), dw0 = 1 << 20, dw1 = -(1 << 20);
         for (int j = 0; j < p.cls[0].tap_count; ++j) {
@@ -634,14 +640,15 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         p.halo_h = 16 + (dh1 - dh0);
         p.halo_pitch = 8 + (dw1 - dw0);
         const size_t wbytes = (size_t)p.cls[0].tap_count * p.n_pad * row_bytes;
-        const size_t a_stage = ((size_t)p.halo_h * p.halo_pitch * row_bytes + 1023) & ~(size_t)1023;
-        if (p.halo_pitch <= 256 && p.halo_h <= 256 && wbytes + 2 * a_stage <= 200 * 1024) {
+        p.plane_bytes = (int)(((size_t)p.halo_h * p.halo_pitch * row_bytes + 1023) & ~(size_t)1023);
+        const size_t a_stage = (size_t)p.planes * p.plane_bytes;
+        if (p.halo_pitch <= 256 && p.halo_h <= 256 && wbytes + 2 * a_stage <= 220 * 1024) {
             // two CTAs per SM (the epilogue of one overlaps the MMAs of the other) when the weights leave room
             if (p.n_pad <= 128 && wbytes + 3 * a_stage <= 104 * 1024) {
                 halo_ctas_per_sm = 2;
                 halo_stages = (int)((104 * 1024 - wbytes) / a_stage);
             } else {
-                halo_stages = (int)((200 * 1024 - wbytes) / a_stage);
+                halo_stages = (int)((220 * 1024 - wbytes) / a_stage);
             }
             if (halo_stages > 6) halo_stages = 6;
             halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8 + kMaxTaps) * sizeof(uint64_t) + kMaxTaps * 4 + 32 + 256 * sizeof(float) + 1024;
@@ -654,7 +661,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
             p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
         }
     }
-    if (p.d2s && !halo_ok) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc subpixel: shape not covered by the halo kernel");
+    if ((p.d2s || p.planes == 2) && !halo_ok) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: shape not covered by the halo kernel");
     // ---- A map: 5-D (C', W', P, H', N)
     CUtensorMap map_a, map_b;
     {
@@ -708,9 +715,10 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     // ---- halo variant (see halo_kernel)
     if (halo_ok) {
         CUtensorMap map_h;
-        cuuint64_t dims[5] = {(cuuint64_t)q.Cs, (cuuint64_t)q.Ws, 1, (cuuint64_t)q.Hs, (cuuint64_t)q.N};
+        const cuuint64_t sp = (cuuint64_t)p.planes;            // 2: parity view [N][H/2][2][W/2][2C] of the same buffer
+        cuuint64_t dims[5] = {sp * q.Cs, (cuuint64_t)q.Ws / sp, sp, (cuuint64_t)q.Hs / sp, (cuuint64_t)q.N};
         const cuuint64_t pix = (cuuint64_t)q.Cs * 2;
-        cuuint64_t strides[4] = {pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Hs * q.Ws * pix};
+        cuuint64_t strides[4] = {sp * pix, (cuuint64_t)q.Ws * pix, sp * q.Ws * pix, (cuuint64_t)q.Hs * q.Ws * pix};
         cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)p.halo_pitch, 1u, (cuuint32_t)p.halo_h, 1u};
         int rc = encode_map(&map_h, q.src, 5, dims, strides, box, row_bytes);
         if (rc) return rc;
@@ -725,7 +733,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         if (e == cudaSuccess) halo_kernel<KCV, NTV><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);                  \
     } while (0)
         if (KC == 64) {
-            if (nt == 25) DMV_LAUNCH_HALO(64, 25); else if (nt == 9) DMV_LAUNCH_HALO(64, 9); else DMV_LAUNCH_HALO(64, 0);
+            if (nt == 25) DMV_LAUNCH_HALO(64, 25); else if (nt == 15) DMV_LAUNCH_HALO(64, 15); else if (nt == 9) DMV_LAUNCH_HALO(64, 9); else DMV_LAUNCH_HALO(64, 0);
         } else {
             if (nt == 25) DMV_LAUNCH_HALO(32, 25); else if (nt == 9) DMV_LAUNCH_HALO(32, 9); else DMV_LAUNCH_HALO(32, 0);
         }
@@ -889,6 +897,80 @@ int build_g(IgemmParams& p, int kh, int kw, int stride, int pt, int pl, int w_co
     return DMV_OK;
 }
 
+// ---- stride-2 F problems (conv fwd, deconv dgrad) with 32 source channels on the halo kernel ------------------
+// In the parity view [N][H/2][2][W/2][2C] a stride-2 tap (r, s) reads row plane ph = (r - pt) mod 2 at window shift
+// dh = floor((r - pt) / 2), and column shift dw = floor((s - pl) / 2) with the column parity pw selecting one half of
+// the 2C = 64 channels of a window row.  Folding pw into the contraction gives kh x ceil((kw + 1) / 2) taps of K = 64
+// (zero weights where s falls outside the kernel), each an ordinary shifted window of one of the TWO planes, which the
+// halo kernel loads once per tile instead of once per tap.
+static int fdiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+struct S2Table {
+    int n;
+    short dh[kMaxTaps], dw[kMaxTaps], ph[kMaxTaps], r[kMaxTaps], s0[kMaxTaps], s1[kMaxTaps];   // s0 / s1: kernel column of pw = 0 / 1, -1: none
+};
+
+__global__ void pack_f_s2_kernel(const bf16* __restrict__ w, bf16* __restrict__ out, int kw, int Cin, int Cout, S2Table t) {
+    const int K = t.n * 2 * Cin, total = Cout * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i / K, kk = i - co * K;
+        const int j = kk / (2 * Cin), rem = kk - j * 2 * Cin;
+        const int pw = rem / Cin, c = rem - pw * Cin;
+        const int sc = pw ? t.s1[j] : t.s0[j];
+        out[i] = sc >= 0 ? w[((long long)(t.r[j] * kw + sc) * Cin + c) * Cout + co] : __float2bfloat16_rn(0.f);
+    }
+}
+
+bool f_s2_eligible(int Cs, int n_real, int Jh, int Jw, int Hs, int Ws, int kh, int kw, int pt, int pl) {
+    if (getenv("DMV_NO_S2HALO") || getenv("DMV_NO_HALO")) return false;
+    if (Cs != 32 || (Hs & 1) || (Ws & 1) || Jh * Jw < 256 || n_real > 256 || (n_real & 15)) return false;
+    const int ndw = fdiv2(kw - 1 - pl) - fdiv2(-pl) + 1, ndh = fdiv2(kh - 1 - pt) - fdiv2(-pt) + 1;
+    const int taps = kh * ndw;
+    if (taps > kMaxTaps) return false;
+    const size_t wbytes = (size_t)taps * n_real * 128;
+    const size_t plane = ((size_t)(16 + ndh - 1) * (8 + ndw - 1) * 128 + 1023) & ~(size_t)1023;
+    return wbytes + 2 * 2 * plane <= 220 * 1024;
+}
+
+// src [N][Hs][Ws][32] bf16 read with stride 2; w is the reference layout [kh][kw][32][n_real]
+int launch_f_s2(const void* src, int N, int Hs, int Ws, const void* w, int kh, int kw, int pt, int pl, const float* bias, int act,
+                void* out, int out_f32, int out_H, int out_W, int n_real, void* ws, size_t ws_bytes, cudaStream_t st) {
+    S2Table t;
+    memset(&t, 0, sizeof(t));
+    const int dw_lo = fdiv2(-pl), dw_hi = fdiv2(kw - 1 - pl);
+    for (int r = 0; r < kh; ++r)
+        for (int dw = dw_lo; dw <= dw_hi; ++dw) {
+            const int j = t.n++;
+            const int dy = r - pt;
+            t.ph[j] = (short)(((dy % 2) + 2) % 2);
+            t.dh[j] = (short)((dy - t.ph[j]) / 2);
+            t.dw[j] = (short)dw;
+            t.r[j] = (short)r;
+            const int s0 = 2 * dw + pl, s1 = 2 * dw + 1 + pl;
+            t.s0[j] = (short)((s0 >= 0 && s0 < kw) ? s0 : -1);
+            t.s1[j] = (short)((s1 >= 0 && s1 < kw) ? s1 : -1);
+        }
+    const size_t need = (size_t)n_real * t.n * 64 * 2;
+    if (!ws || ws_bytes < need || ((uintptr_t)ws & 15)) return fail(DMV_E_WORKSPACE, "tc stride-2 halo: workspace too small");
+    pack_f_s2_kernel<<<ceil_div(n_real * t.n * 64, 256), 256, 0, st>>>((const bf16*)w, (bf16*)ws, kw, 32, n_real, t);
+    int rc = check_launch("tc pack stride-2");
+    if (rc) return rc;
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_classes = 1;
+    p.planes = 2;
+    p.cls[0] = TapClass{0, t.n, 0, 0, 0};
+    for (int j = 0; j < t.n; ++j) {
+        p.taps[j].dh = t.dh[j]; p.taps[j].dw = t.dw[j]; p.taps[j].ph = t.ph[j]; p.taps[j].pw = 0; p.taps[j].id = j;
+    }
+    Problem q;
+    q.src = src; q.N = N; q.Hs = Hs; q.Ws = Ws; q.Cs = 32; q.src_stride = 2;
+    q.w_hwio = ws; q.kh = 1; q.kw = t.n; q.w_ci = t.n * 64; q.w_co = n_real; q.g_form = false; q.n_tile = 0; q.b_mode_override = 3; q.k_splits = 1;
+    q.out = out; q.out_f32 = out_f32; q.out_H = out_H; q.out_W = out_W; q.n_real = n_real; q.out_mul = 1;
+    q.Jh = out_H; q.Jw = out_W; q.bias = bias; q.act = act;
+    return launch_igemm(q, p, nullptr, 0, st);
+}
+
 // Stride-2 G problem as one stride-1 halo launch (see SubpixelTable).  w is the reference layout read as
 // w[tap][n_real][Cs] (conv dgrad: [kh][kw][Cin][Cout]; deconv fwd: [kh][kw][Cout_t][Cin_t]).
 int launch_subpixel(const void* src, int N, int Hs, int Ws, int Cs, const void* w, int kh, int kw, int pt, int pl, void* out, int out_f32,
@@ -961,6 +1043,8 @@ int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* 
     if (xdt != DMV_DT_BF16) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_conv_fwd: bf16 input only");
     if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_conv_fwd: stride");
     const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+    if (stride == 2 && f_s2_eligible(Cin, Cout, ph.out, pw.out, H, W, kh, kw, ph.before, pw.before) && ws_bytes >= (size_t)Cout * kh * ((kw + 2) / 2) * 128)
+        return launch_f_s2(x, B, H, W, w, kh, kw, ph.before, pw.before, bias, act, y, ydt == DMV_DT_F32, ph.out, pw.out, Cout, ws, ws_bytes, st);
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     int rc = build_f(p, kh, kw, stride, ph.before, pw.before);
@@ -1019,6 +1103,8 @@ int tc_deconv_dgrad(const void* dy, int dydt, const void* w, void* dx, int B, in
     if (dydt != DMV_DT_BF16) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_deconv_dgrad: bf16 gradient only");
     if (stride != 1 && stride != 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_deconv_dgrad: stride");
     const SamePad ph = same_pad(Hout, kh, stride), pw = same_pad(Wout, kw, stride);
+    if (stride == 2 && f_s2_eligible(Cout, Cin, ph.out, pw.out, Hout, Wout, kh, kw, ph.before, pw.before) && ws_bytes >= (size_t)Cin * kh * ((kw + 2) / 2) * 128)
+        return launch_f_s2(dy, B, Hout, Wout, w, kh, kw, ph.before, pw.before, nullptr, DMV_ACT_NONE, dx, 0, ph.out, pw.out, Cin, ws, ws_bytes, st);
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     int rc = build_f(p, kh, kw, stride, ph.before, pw.before);

@@ -40,6 +40,8 @@ SMALL = [  # kind, k, s, H(big side), cin, cout, B
     # sub-pixel form of the stride-2 G problems (deconv fwd / conv dgrad as one stride-1 halo launch + depth-to-space)
     ("deconv", 3, 2, 32, 64, 32, 2), ("conv", 3, 2, 36, 32, 32, 2), ("deconv", 5, 2, 34, 32, 16, 1), ("conv", 5, 2, 36, 32, 64, 1),
     ("deconv", 5, 2, 36, 64, 64, 1),
+    # stride-2 F problems with 32 source channels on the halo kernel (two row-parity planes, column parity folded into K)
+    ("conv", 5, 2, 36, 32, 32, 2), ("conv", 3, 2, 34, 32, 64, 1), ("deconv", 5, 2, 36, 32, 32, 2), ("deconv", 3, 2, 40, 32, 32, 1),
 ]
 
 
