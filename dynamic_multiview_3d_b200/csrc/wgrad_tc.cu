@@ -483,6 +483,164 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo2d_kernel(const __grid_
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Stride-2 layers whose shifted tensor has 32 channels (e1, e2, d1, d2): the same 2-D stacking on the PARITY VIEW
+// [N][H/2][2][W/2][2C] of the big tensor.  A stride-2 tap (r, s) is plane ph = (r - pt) mod 2 at row shift
+// dh = floor((r - pt) / 2), and column shift dw = floor((s - pl) / 2) with the column parity pw choosing one half of
+// the 2C = 64 channels of a window row.  With the virtual column u = ox + dw,
+//     dW[r, s] = sum_{oy, u} X_ph[oy + dh, u, (pw, ci)] * dy[oy, u - dw],
+// so an M tile stacks two dh of one plane (2 x 64 rows, LBO = one window row) and N stacks every dw (columns of a
+// dy window with a halo on the left, LBO = one pixel).  Entries whose s = 2 dw + pw + pl falls outside the kernel
+// are structural zeros and are not stored.
+struct WS2Tile {
+    short ph, dh0, nvalid, pad;
+};
+struct WS2Params {
+    int kh, kw, pt, pl, BH, pitch_b, ndw, dw_lo, dw_hi;
+    int Cs, row_bytes_b;                     // small tensor channels (32 | 64) = one MMA N span
+    int m_tiles, tiles_per_group, groups;
+    int dhlo[2], halo_h;                     // first row shift of each plane's window; window height (common)
+    int tiles_w, tiles_h, chunks, slices, chunks_per_slice, stages;
+    int plane_bytes, b_stage;                // 1024-aligned slot sizes
+    long long out_elems;
+    float* out;
+    WS2Tile tile[8];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_s2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                const __grid_constant__ WS2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int stage_bytes = 2 * p.plane_bytes + p.b_stage;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + 2048);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* done_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slice = blockIdx.x % p.slices, grp = blockIdx.x / p.slices;
+    const int mt0 = grp * p.tiles_per_group;
+    const int n_mt = min(p.m_tiles, mt0 + p.tiles_per_group) - mt0;
+    const int ch0 = slice * p.chunks_per_slice;
+    const int ch1 = min(p.chunks, ch0 + p.chunks_per_slice);
+    const int N = p.Cs * p.ndw;
+    int plane_mask = 0;
+    for (int i = 0; i < n_mt; ++i) plane_mask |= 1 << p.tile[mt0 + i].ph;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(p.tiles_per_group * N)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t a_real = (uint32_t)(p.halo_h * 8 * 128);
+            const uint32_t tx = a_real * (uint32_t)__popc(plane_mask) + (uint32_t)(p.BH * p.pitch_b * p.row_bytes_b);
+            for (int ch = ch0; ch < ch1; ++ch) {
+                int t = ch;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], tx);
+                for (int ph = 0; ph < 2; ++ph)
+                    if (plane_mask & (1 << ph))
+                        tma_load_5d(sa + ph * p.plane_bytes, &map_a, &full_bar[stage], 0, tw * 8 + p.dw_lo, ph, th * p.BH + p.dhlo[ph], t);
+                tma_load_5d(sa + 2 * p.plane_bytes, &map_b, &full_bar[stage], 0, tw * 8 - (p.ndw - 1), 0, th * p.BH, t);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            // A: 128-byte rows (SWIZZLE_128B); spans = dh (LBO one 8-pixel window row = 1024 B), K groups = tile rows (SBO 1024 B)
+            uint64_t a_hi = 0;
+            a_hi |= (uint64_t)(1024u >> 4) << 16;
+            a_hi |= (uint64_t)(1024u >> 4) << 32;
+            a_hi |= (uint64_t)1 << 46;
+            a_hi |= (uint64_t)2 << 61;
+            // B: spans = dw descending (LBO one pixel), K groups = window rows (SBO pitch_b pixels)
+            const uint32_t b_row = (uint32_t)(p.pitch_b * p.row_bytes_b);
+            uint64_t b_hi = 0;
+            b_hi |= (uint64_t)(((uint32_t)p.row_bytes_b >> 4) & 0x3FFF) << 16;
+            b_hi |= (uint64_t)((b_row >> 4) & 0x3FFF) << 32;
+            b_hi |= (uint64_t)1 << 46;
+            b_hi |= (uint64_t)(p.row_bytes_b == 128 ? 2 : 4) << 61;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = ch0; ch < ch1; ++ch) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + 2u * (uint32_t)p.plane_bytes;
+                for (int i = 0; i < n_mt; ++i) {
+                    const WS2Tile& t = p.tile[mt0 + i];
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(i * N);
+                    const uint32_t a0 = sa + (uint32_t)(t.ph * p.plane_bytes) + (uint32_t)(t.dh0 - p.dhlo[t.ph]) * 1024u;
+                    for (int k = 0; k < p.BH / 2; ++k) {
+                        const uint64_t adesc = a_hi | (uint64_t)(((a0 + (uint32_t)(2 * k) * 1024u) & 0x3FFFF) >> 4);
+                        const uint64_t bdesc = b_hi | (uint64_t)(((sb + (uint32_t)(2 * k) * b_row) & 0x3FFFF) >> 4);
+                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (ch > ch0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(done_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        float* outp = p.out + (long long)slice * p.out_elems;
+        const bool have = ch1 > ch0;
+        const int j = m >> 6, pw = (m >> 5) & 1, ci = m & 31;
+        for (int i = 0; i < n_mt; ++i) {
+            const WS2Tile& t = p.tile[mt0 + i];
+            const int r = 2 * (t.dh0 + j) + t.ph + p.pt;
+            const bool row_ok = (j < t.nvalid) && r >= 0 && r < p.kh;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * N);
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                const int jj = c0 / p.Cs, co = c0 - jj * p.Cs;
+                const int s2 = 2 * (p.dw_hi - jj) + pw + p.pl;
+                if (row_ok && s2 >= 0 && s2 < p.kw) {
+                    float* o = outp + ((long long)(r * p.kw + s2) * 32 + ci) * p.Cs + co;
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4)
+                        *reinterpret_cast<float4*>(o + k) =
+                            have ? make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // pixel chunk box: rows = BW*BH*NB a multiple of 16, <= max_rows, maximising the useful fraction
 void choose_chunk(int Jh, int Jw, int N, int max_rows, int& BW, int& BH, int& NB) {
     double best = -1.0;
@@ -725,7 +883,103 @@ int run_wgrad_halo2d(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t 
     return rc;
 }
 
+// ---- stride-2, 32-channel big tensor: 2-D stacking on the parity view
+static int wfdiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+bool ws2_eligible(const WProblem& q) {
+    if (getenv("DMV_NO_WS2")) return false;
+    if (q.stride != 2 || q.Cb != 32 || !(q.Cs == 32 || q.Cs == 64)) return false;
+    if ((q.Hb & 1) || (q.Wb & 1) || q.Hs * 2 != q.Hb || q.Ws * 2 != q.Wb) return false;
+    if (q.Hs * q.Ws < 256 || q.kh > 5 || q.kw > 5) return false;
+    const int ndw = wfdiv2(q.kw - 1 - q.pl) - wfdiv2(-q.pl) + 1;
+    return q.Cs * ndw <= 256;
+}
+
+int run_wgrad_s2(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
+    WS2Params p;
+    memset(&p, 0, sizeof(p));
+    p.kh = q.kh; p.kw = q.kw; p.pt = q.pt; p.pl = q.pl;
+    p.Cs = q.Cs; p.row_bytes_b = q.Cs * 2;
+    p.dw_lo = wfdiv2(-q.pl); p.dw_hi = wfdiv2(q.kw - 1 - q.pl); p.ndw = p.dw_hi - p.dw_lo + 1;
+    int span = 0, n = 0;
+    for (int ph = 0; ph < 2; ++ph) {
+        // dh values of the rows r with (r - pt) mod 2 == ph
+        int lo = 1 << 20, hi = -(1 << 20);
+        for (int r = 0; r < q.kh; ++r) {
+            const int dy = r - q.pt;
+            if ((((dy % 2) + 2) % 2) != ph) continue;
+            const int dh = (dy - ph) / 2;
+            lo = dh < lo ? dh : lo; hi = dh > hi ? dh : hi;
+        }
+        if (lo > hi) { p.dhlo[ph] = 0; continue; }
+        p.dhlo[ph] = lo;
+        span = (hi - lo) > span ? (hi - lo) : span;
+        for (int dh = lo; dh <= hi; dh += 2) p.tile[n++] = WS2Tile{(short)ph, (short)dh, (short)((dh + 1 <= hi) ? 2 : 1), 0};
+    }
+    p.m_tiles = n;
+    const int N = p.Cs * p.ndw;
+    p.tiles_per_group = 512 / N;
+    if (p.tiles_per_group > n) p.tiles_per_group = n;
+    p.groups = ceil_div(n, p.tiles_per_group);
+    int best_bh = 16; double best = -1.0;
+    for (int bh = 16; bh >= 8; bh -= 2) {
+        const double eff = (double)q.Hs / (ceil_div(q.Hs, bh) * bh);
+        if (eff > best + 1e-9) { best = eff; best_bh = bh; }
+    }
+    p.BH = best_bh;
+    p.halo_h = p.BH + span + 1;                      // + 1: the absent second dh of a ragged M tile stays inside the slot
+    p.pitch_b = 8 + p.ndw - 1;
+    p.tiles_w = ceil_div(q.Ws + p.ndw - 1, 8);
+    p.tiles_h = ceil_div(q.Hs, p.BH);
+    p.chunks = p.tiles_w * p.tiles_h * q.N;
+    int slices = ceil_div(num_sms(), p.groups);
+    if (slices > p.chunks) slices = p.chunks;
+    p.chunks_per_slice = ceil_div(p.chunks, slices);
+    p.slices = ceil_div(p.chunks, p.chunks_per_slice);
+    p.out_elems = (long long)q.kh * q.kw * 32 * q.Cs;
+    p.plane_bytes = (p.halo_h * 8 * 128 + 1023) & ~1023;
+    p.b_stage = (p.BH * p.pitch_b * p.row_bytes_b + 1023) & ~1023;
+    const size_t need = p.slices > 1 ? (size_t)p.slices * p.out_elems * sizeof(float) : 0;
+    if (need > 0 && (!ws || ws_bytes < need)) return fail(DMV_E_WORKSPACE, "tc wgrad s2: workspace too small");
+    p.out = p.slices > 1 ? reinterpret_cast<float*>(ws) : q.dw;
+    CUtensorMap map_a, map_b;
+    int rc;
+    {
+        cuuint64_t dims[5] = {64, (cuuint64_t)q.Ws, 2, (cuuint64_t)q.Hs, (cuuint64_t)q.N};
+        cuuint64_t strides[4] = {128, (cuuint64_t)q.Wb * 64, (cuuint64_t)q.Wb * 128, (cuuint64_t)q.Hb * q.Wb * 64};
+        cuuint32_t box[5] = {64u, 8u, 1u, (cuuint32_t)p.halo_h, 1u};
+        rc = encode_map(&map_a, q.big, 5, dims, strides, box, 128);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t pix = (cuuint64_t)q.Cs * 2;
+        cuuint64_t dims[5] = {(cuuint64_t)q.Cs, (cuuint64_t)q.Ws, 1, (cuuint64_t)q.Hs, (cuuint64_t)q.N};
+        cuuint64_t strides[4] = {pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Ws * pix, (cuuint64_t)q.Hs * q.Ws * pix};
+        cuuint32_t box[5] = {(cuuint32_t)q.Cs, (cuuint32_t)p.pitch_b, 1u, (cuuint32_t)p.BH, 1u};
+        rc = encode_map(&map_b, q.small, 5, dims, strides, box, p.row_bytes_b);
+        if (rc) return rc;
+    }
+    const int stage_bytes = 2 * p.plane_bytes + p.b_stage;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad s2: stage does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 2048 + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("tc wgrad s2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return DMV_E_CUDA;
+    }
+    wgrad_s2_kernel<<<p.groups * p.slices, kThreads, smem, st>>>(map_a, map_b, p);
+    count_tc_launch();
+    rc = check_launch("wgrad_s2_tc");
+    if (rc) return rc;
+    if (p.slices > 1) rc = reduce_partials(reinterpret_cast<const float*>(ws), q.dw, p.out_elems, p.slices, st);
+    return rc;
+}
+
 int run_wgrad(const WProblem& q, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws2_eligible(q)) return run_wgrad_s2(q, ws, ws_bytes, st);
     if (whalo2d_eligible(q)) return run_wgrad_halo2d(q, ws, ws_bytes, st);
     if (whalo_eligible(q)) return run_wgrad_halo(q, ws, ws_bytes, st);
     if (!wgrad_eligible(q.Cb, q.Cs, q.kh * q.kw)) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc wgrad: channel counts not covered");
