@@ -153,6 +153,12 @@ class AppearanceFlowModel(object):
         self.optimizer.step()
         return loss.detach()
 
+    def visualize(self, image0, image1, disp, iter_num=None):
+        """appearance_flow_model.py:132-179: output / ground-truth / input grids, the flow image and the
+        correspondence probes (visualize.py).  The TF session argument becomes the batch itself."""
+        from .visualize import visualize
+        return visualize(self, image0, image1, disp, iter_num)
+
     # -- checkpoint surface (tf.train.Saver over global variables, train.py:70-71) -----------
     def state_dict(self):
         if hasattr(self, "_dp") and hasattr(self._dp, "gather_full_state"):

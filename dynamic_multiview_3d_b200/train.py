@@ -35,6 +35,8 @@ class GraphedTrainStep:
         self.loss = None
         self.warmup = warmup
         self.launches_per_step = 0
+        self._stage = None
+        self._pending = False
 
     def capture(self):
         from . import _lib
@@ -53,15 +55,50 @@ class GraphedTrainStep:
         self.launches_per_step = _lib.launch_count() - n0
         return self
 
-    def __call__(self, image0, image1, disp):
-        if self.graph is None:
-            self.image0.copy_(image0, non_blocking=True)
-            self.image1.copy_(image1, non_blocking=True)
-            self.disp.copy_(disp, non_blocking=True)
-            self.capture()
+    def _copy_in(self, image0, image1, disp):
         self.image0.copy_(image0, non_blocking=True)
         self.image1.copy_(image1, non_blocking=True)
         self.disp.copy_(disp, non_blocking=True)
+
+    def prefetch(self, image0, image1, disp):
+        """Start the host->device copy of the NEXT step's batch on a copy stream into staging buffers; it overlaps
+        the step that is replayed meanwhile.  The following __call__ with ``staged=True`` consumes it."""
+        dev = self.model.device
+        if self._stage is None:
+            self._stage = [torch.empty_like(self.image0), torch.empty_like(self.image1), torch.empty_like(self.disp)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged_ev = torch.cuda.Event()
+            self._consumed_ev = torch.cuda.Event()
+            self._consumed_ev.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._consumed_ev)          # the previous staged batch has been moved out
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage, (image0, image1, disp)):
+                dst.copy_(src, non_blocking=True)
+            self._staged_ev.record(self._copy_stream)
+        self._pending = True
+
+    def __call__(self, image0=None, image1=None, disp=None, staged=False, prefetch_next=None):
+        """One train step.  ``staged=True``: take the batch handed to prefetch() (a 25 us device-side move instead
+        of a PCIe copy in front of the step).  ``prefetch_next=(image0, image1, disp)``: start copying the next
+        step's batch before this step is replayed, so the PCIe transfer overlaps it."""
+        if self.graph is None:
+            if staged:
+                torch.cuda.current_stream(self.model.device).wait_event(self._staged_ev)
+                image0, image1, disp = self._stage
+            self._copy_in(image0, image1, disp)
+            self.capture()
+        if staged:
+            main = torch.cuda.current_stream(self.model.device)
+            main.wait_event(self._staged_ev)
+            self._copy_in(*self._stage)
+            self._consumed_ev.record(main)
+            self._pending = False
+        else:
+            self._copy_in(image0, image1, disp)
+            if self._stage is not None:
+                self._consumed_ev.record(torch.cuda.current_stream(self.model.device))
+        if prefetch_next is not None:
+            self.prefetch(*prefetch_next)
         self.graph.replay()
         return self.loss
 
@@ -130,8 +167,18 @@ def main(argv=None):
     if args.pretrained:
         model.load_state_dict(torch.load(args.pretrained, map_location="cpu"))
         itr_0 = checkpoint_iteration(args.pretrained) + 1
-    step = GraphedTrainStep(model)
     V = "onehot19" if model.viewpoint_dim == 19 else "disp2"
+    if args.visualize:                       # train.py:60-65, 86-93: restore <output_dir>/<visualize> and write the figures
+        conf["visualize"] = args.visualize
+        ck = os.path.join(out_dir, args.visualize)
+        if os.path.exists(ck):
+            model.load_state_dict(torch.load(ck, map_location="cpu"))
+        b = make_batch(model.batch_size, model.image_shape[0], V, seed=99)
+        info = model.visualize(*(torch.from_numpy(b[k]).to(model.device) for k in ("image0", "image1", "disp")))
+        print("loss", info["loss"])
+        print("max resample coord:", info["max_resample_coord"])
+        return
+    step = GraphedTrainStep(model)
     t_iter = []
     reader = None
     if args.tfrecords:                       # train.py:57 load_tfrec=True -> read_tf_records.build_tfrecord_input

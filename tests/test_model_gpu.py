@@ -216,3 +216,16 @@ def test_multiview_fusion_model_parity_and_training():
     for _ in range(6):
         l1 = float(model.train_step(*args))
     assert np.isfinite(l1) and l1 < l0
+
+
+def test_visualize_writes_the_reference_outputs(tmp_path):
+    """appearance_flow_model.py:132-179: output_/tr_gt_/tr_input_ grids + flow image + correspondence probes."""
+    import dynamic_multiview_3d_b200 as pkg
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "output_dir": str(tmp_path), "visualize": "model120"}
+    m = pkg.AppearanceFlowModel(conf, build_loss=False)
+    b = _batch(B, H, V)
+    info = m.visualize(*(torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")))
+    for name in ("output_120.png", "tr_gt_120.png", "tr_input_120.png", "flow_120.png"):
+        assert os.path.getsize(os.path.join(str(tmp_path), name)) > 100
+    assert np.isfinite(info["loss"]) and len(info["correspondences"]) == 6 and info["max_resample_coord"] < H + 5
