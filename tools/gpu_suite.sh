@@ -29,9 +29,9 @@ if [[ $what == all || $what == ncu ]]; then
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro --eager > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?" | tee -a gpurun_out/summary.txt
   # dominant kernel of the step (Adam) + the tensor-core kernels, one --set full capture each
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:adam_multi -c 1 -f -o gpurun_out/adam_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-micro --eager > gpurun_out/ncu_adam.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:adam_multi -c 1 -f -o gpurun_out/adam_prof env DMV_OVERLAP_ADAM=0 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-micro --eager > gpurun_out/ncu_adam.log 2>&1
   echo "ncu adam exit $?" | tee -a gpurun_out/summary.txt
   timeout 300 python tools/prof_conv.py > gpurun_out/prof_conv_plain.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"halo_kernel|wgrad_kernel|igemm_kernel" -c 8 -f -o gpurun_out/conv_prof python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"halo|wgrad|igemm" -c 8 -f -o gpurun_out/conv_prof python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1
   echo "ncu conv exit $?" | tee -a gpurun_out/summary.txt
 fi
