@@ -662,6 +662,18 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         }
     }
     if ((p.d2s || p.planes == 2) && !halo_ok) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc: shape not covered by the halo kernel");
+    // Deep, spatially small layers (14^2 / 7^2 at 128-256 channels) have fewer M tiles than SMs: cut N into narrower
+    // tiles until the launch fills the persistent grid (the A boxes are then re-read per N tile from L2, which is cheap).
+    if (!halo_ok && q.n_tile == 0 && !p.d2s && p.planes != 2 && !getenv("DMV_NO_NSPLIT")) {
+        const int m_tiles = p.num_classes * p.tiles_per_class;
+        int nt = p.n_pad;
+        while (nt > 64 && (nt % 32) == 0 && 2 * m_tiles * ceil_div(q.n_real, nt) <= num_sms() && q.n_real % (nt / 2) == 0) nt /= 2;
+        if (nt != p.n_pad) {
+            p.n_pad = nt;
+            p.n_tiles = ceil_div(q.n_real, nt);
+        }
+    }
+
     // ---- A map: 5-D (C', W', P, H', N)
     CUtensorMap map_a, map_b;
     {
