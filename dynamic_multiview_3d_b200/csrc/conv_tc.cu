@@ -197,6 +197,70 @@ __device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t 
     }
 }
 
+// Sub-pixel epilogue for C = 32 (bf16 out): the two column-parity classes of one output row are 128 contiguous bytes
+// per tile pixel, and the 8 pixels of a tile row are 1 KB contiguous.  Stored lane by lane that is 32 scattered 16-byte
+// pieces per instruction (the kernel was bound by L1 -> L2 write requests); instead each warp stages its 32 x 128 B in an
+// XOR-swizzled shared tile and writes it back with four full 128-byte lines per instruction.
+__device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t taddr, int n, int th, int tw, int quarter, int lane,
+                                                 uint4* __restrict__ s_epi) {
+    bf16* outp = reinterpret_cast<bf16*>(p.out);
+#pragma unroll 1
+    for (int py = 0; py < 2; ++py) {
+        uint4 ch[8];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)(py * 64 + q4 * 16), v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+            switch (p.act) {
+                case DMV_ACT_LRELU:
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) f[k] = 0.6f * f[k] + 0.4f * fabsf(f[k]);
+                    break;
+                case DMV_ACT_RELU:
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) f[k] = 0.5f * f[k] + 0.5f * fabsf(f[k]);
+                    break;
+                case DMV_ACT_TANH:
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) f[k] = tanhf(f[k]);
+                    break;
+                default: break;
+            }
+            __nv_bfloat162 h;
+            uint4 a, b;
+            h = __floats2bfloat162_rn(f[0], f[1]); a.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[2], f[3]); a.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[4], f[5]); a.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[6], f[7]); a.w = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[8], f[9]); b.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[10], f[11]); b.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[12], f[13]); b.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[14], f[15]); b.w = *reinterpret_cast<uint32_t*>(&h);
+            ch[2 * q4] = a;
+            ch[2 * q4 + 1] = b;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s_epi[lane * 8 + (c ^ (lane & 7))] = ch[c];
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int rr = t * 4 + (lane >> 3), cc = lane & 7;
+            const int m = quarter * 32 + rr;
+            const int jh = th * 16 + (m >> 3), jw = tw * 8 + (m & 7);
+            const int oy = 2 * jh + py, ox = 2 * jw + (cc >> 2);
+            if (jh < p.Jh && jw < p.Jw && oy < p.out_H && ox < p.out_W) {
+                const uint4 q = s_epi[rr * 8 + (cc ^ (rr & 7))];
+                *reinterpret_cast<uint4*>(outp + (((long long)n * p.out_H + oy) * p.out_W + 2 * jw) * 32 + cc * 8) = q;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int KC>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
@@ -394,6 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     uint32_t* s_aoff = reinterpret_cast<uint32_t*>(s_bdesc + kMaxTaps);   // [ntaps] tap offsets (16-byte units)
     uint32_t* tmem_slot = s_aoff + kMaxTaps;
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+    // [4 epilogue warps][32 x 128 B] transpose tiles of the sub-pixel C = 32 epilogue (allocated only then)
+    uint4* s_epi_all = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_bias + 256) + 127) & ~(uintptr_t)127);
     for (int i = threadIdx.x; i < p.n_pad; i += kThreads) s_bias[i] = (p.bias && i < p.n_real) ? __ldg(p.bias + i) : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -515,7 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            if (p.d2s) epilogue_row_d2s(p, taddr, (oy < p.Jh) && (ox < p.Jw), n, oy, ox);
+            if (p.d2s == 2) epilogue_d2s_c32(p, taddr, n, th, tw, quarter, lane, s_epi_all + (warp - 2) * 256);
+            else if (p.d2s) epilogue_row_d2s(p, taddr, (oy < p.Jh) && (ox < p.Jw), n, oy, ox);
             else epilogue_row(p, taddr, ok, opix, 0, 0, s_bias);
             tc_fence_before();
             __syncwarp();
@@ -651,7 +718,16 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
                 halo_stages = (int)((220 * 1024 - wbytes) / a_stage);
             }
             if (halo_stages > 6) halo_stages = 6;
-            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8 + kMaxTaps) * sizeof(uint64_t) + kMaxTaps * 4 + 32 + 256 * sizeof(float) + 1024;
+            // sub-pixel layers with 32 bf16 output channels: coalescing epilogue through 16 KB of transpose tiles
+            size_t epi = 0;
+            if (p.d2s && p.d2s_c == 32 && !q.out_f32 && !getenv("DMV_NO_D2S_EPI")) {
+                while (halo_stages > 2 && wbytes + (size_t)halo_stages * a_stage + 16 * 1024 + 4096 > (halo_ctas_per_sm == 2 ? 112 : 226) * 1024) --halo_stages;
+                if (wbytes + (size_t)halo_stages * a_stage + 16 * 1024 + 4096 <= (halo_ctas_per_sm == 2 ? 112 : 226) * 1024) {
+                    p.d2s = 2;
+                    epi = 16 * 1024 + 128;
+                }
+            }
+            halo_smem = wbytes + (size_t)halo_stages * a_stage + (2 * halo_stages + 8 + kMaxTaps) * sizeof(uint64_t) + kMaxTaps * 4 + 32 + 256 * sizeof(float) + 1024 + epi;
             halo_ok = true;
             // the halo kernel tiles the image 8 wide x 16 tall, one image per tile
             p.BW = 8; p.BH = 16; p.NB = 1; p.rows = 128;
