@@ -206,7 +206,6 @@ __device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t 
     bf16* outp = reinterpret_cast<bf16*>(p.out);
 #pragma unroll 1
     for (int py = 0; py < 2; ++py) {
-        uint4 ch[8];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
             uint32_t v[16];
@@ -240,11 +239,9 @@ __device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t 
             h = __floats2bfloat162_rn(f[10], f[11]); b.y = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2bfloat162_rn(f[12], f[13]); b.z = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2bfloat162_rn(f[14], f[15]); b.w = *reinterpret_cast<uint32_t*>(&h);
-            ch[2 * q4] = a;
-            ch[2 * q4 + 1] = b;
+            s_epi[lane * 8 + ((2 * q4) ^ (lane & 7))] = a;
+            s_epi[lane * 8 + ((2 * q4 + 1) ^ (lane & 7))] = b;
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) s_epi[lane * 8 + (c ^ (lane & 7))] = ch[c];
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -435,8 +432,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 // pixel rows further and strides one window row per 8-row core group.  This works because the
 // shared-memory swizzle is a pure function of the address (established with tools/probe), and it cuts
 // the L2 -> SM traffic of a 5x5 layer by ~13x.  All kh*kw weight tiles are loaded once per CTA.
-template <int KC, int NT>
-__global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant__ CUtensorMap map_a,
+template <int KC, int NT, int EPI>      // EPI 1: coalescing sub-pixel epilogue (its own instantiation: it needs more registers)
+__global__ void __launch_bounds__(kThreads, EPI ? 1 : 2) halo_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_b,
                                                             const __grid_constant__ IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -581,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            if (p.d2s == 2) epilogue_d2s_c32(p, taddr, n, th, tw, quarter, lane, s_epi_all + (warp - 2) * 256);
+            if (EPI == 1) epilogue_d2s_c32(p, taddr, n, th, tw, quarter, lane, s_epi_all + (warp - 2) * 256);
             else if (p.d2s) epilogue_row_d2s(p, taddr, (oy < p.Jh) && (ox < p.Jw), n, oy, ox);
             else epilogue_row(p, taddr, ok, opix, 0, 0, s_bias);
             tc_fence_before();
@@ -817,8 +814,13 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         const int nt = p.cls[0].tap_count;
 #define DMV_LAUNCH_HALO(KCV, NTV)                                                                                          \
     do {                                                                                                                   \
-        e = cudaFuncSetAttribute(halo_kernel<KCV, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem);      \
-        if (e == cudaSuccess) halo_kernel<KCV, NTV><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);                  \
+        if (p.d2s == 2) {                                                                                                  \
+            e = cudaFuncSetAttribute(halo_kernel<KCV, NTV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem); \
+            if (e == cudaSuccess) halo_kernel<KCV, NTV, 1><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);            \
+        } else {                                                                                                           \
+            e = cudaFuncSetAttribute(halo_kernel<KCV, NTV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem); \
+            if (e == cudaSuccess) halo_kernel<KCV, NTV, 0><<<grid, kThreads, halo_smem, st>>>(map_h, map_b, p);            \
+        }                                                                                                                  \
     } while (0)
         if (KC == 64) {
             if (nt == 25) DMV_LAUNCH_HALO(64, 25); else if (nt == 15) DMV_LAUNCH_HALO(64, 15); else if (nt == 9) DMV_LAUNCH_HALO(64, 9); else DMV_LAUNCH_HALO(64, 0);
