@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdmv3d.so")
 OK = 0
 ACT = {None: 0, "none": 0, "lrelu": 1, "relu": 2, "tanh": 3}
 LOSS = {"l2": 0, "l1": 1}
-DT_BF16, DT_F32 = 0, 1
+DT_BF16, DT_F32, DT_S2D = 0, 1, 2
 ALGO = {"auto": 0, "simt": 1, "tcgen05": 2}
 SAMPLER_ADD_GRID, SAMPLER_GRID_XY = 1, 2
 
@@ -32,6 +32,8 @@ SIGNATURES = {
     "dmv_loss_fused_fwd_bwd": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_f), _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _vp, _sz, _vp]),
     "dmv_scale_by_device_scalar": (_i, [_vp, _vp, _ll, _vp]),
     "dmv_conv_workspace_size": (_sz, [_i] * 8),
+    "dmv_thin_s2d_size": (_sz, [_i] * 8),
+    "dmv_thin_s2d_prep": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "dmv_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
     "dmv_conv2d_dgrad": (_i, [_vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_wgrad_workspace_size": (_sz, [_i] * 8),

@@ -19,6 +19,18 @@ int dmv_act_bwd_bias(const void* dy_bf16, const void* y_bf16, void* dpre_bf16, f
     return act_bwd_bias(dy_bf16, y_bf16, dpre_bf16, db, rows, C, act, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t dmv_thin_s2d_size(int N, int H, int W, int C_thin, int C_wide, int kh, int kw, int stride) {
+    if (N <= 0 || H <= 0 || W <= 0 || C_thin <= 0 || !thin_s2d_eligible(H, W, C_thin, C_wide, kh, kw, stride)) return 0;
+    return (size_t)N * (H / 2) * (W / 2) * 64;
+}
+
+int dmv_thin_s2d_prep(const void* thin, int thin_dtype, void* x2, int N, int H, int W, int C_thin, void* stream) {
+    DMV_REQUIRE(thin && x2 && N > 0 && H > 0 && W > 0 && C_thin > 0 && 4 * C_thin <= 32 && !(H & 1) && !(W & 1), DMV_E_INVALID_ARG, "thin_s2d_prep: bad argument");
+    DMV_REQUIRE(thin_dtype == DMV_DT_F32 || thin_dtype == DMV_DT_BF16, DMV_E_INVALID_ARG, "thin_s2d_prep: dtype");
+    DMV_REQUIRE(((uintptr_t)x2 & 15) == 0, DMV_E_ALIGN, "thin_s2d_prep: x2 must be 16-byte aligned");
+    return thin_s2d_prep(thin, thin_dtype, x2, N, H, W, C_thin, (cudaStream_t)stream);
+}
+
 // layers with fewer than 8 channels on the image side (e0: 3, flow head: 2) go through a patch matrix
 static bool thin_side(int c) { return c < 8; }
 
@@ -61,6 +73,10 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias,
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "conv2d_fwd: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == DMV_DT_S2D) {        // caller-kept space-to-depth tensor: only the tensor-core thin path understands it
+        DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cin), DMV_E_INVALID_ARG, "conv2d_fwd: DMV_DT_S2D needs the tensor-core thin path");
+        return tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
+    }
     if (algo != DMV_ALGO_SIMT && thin_side(Cin)) {
         int rc = tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
@@ -89,6 +105,15 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, floa
     DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "conv2d_wgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == DMV_DT_S2D) {
+        DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cin), DMV_E_INVALID_ARG, "conv2d_wgrad: DMV_DT_S2D needs the tensor-core thin path");
+        int rc = tc_thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc == DMV_OK && db) {
+            const SamePad ph = same_pad(H, kh, stride), pw = same_pad(W, kw, stride);
+            rc = simt_bias_grad(dy, db, (long long)B * ph.out * pw.out, Cout, workspace, workspace_bytes, st);
+        }
+        return rc;
+    }
     if (algo != DMV_ALGO_SIMT && thin_side(Cin)) {   // e0: 3-channel image side
         int rc = tc_thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc == DMV_E_UNSUPPORTED_SHAPE || rc == DMV_E_WORKSPACE) {
@@ -130,6 +155,10 @@ int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, in
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "deconv2d_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dy_dtype == DMV_DT_S2D) {
+        DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cout), DMV_E_INVALID_ARG, "deconv2d_dgrad: DMV_DT_S2D needs the tensor-core thin path");
+        return tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace, workspace_bytes, st);
+    }
     if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {   // flow head: dx = conv of the 2-channel gradient with w[r,s,c,ci]
         int rc = tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
                              workspace_bytes, st);
@@ -147,6 +176,10 @@ int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, i
     DMV_REQUIRE(x && dy && dw, DMV_E_INVALID_ARG, "deconv2d_wgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dy_dtype == DMV_DT_S2D) {
+        DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cout), DMV_E_INVALID_ARG, "deconv2d_wgrad: DMV_DT_S2D needs the tensor-core thin path");
+        return tc_thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+    }
     if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {      // flow head: 2-channel output side
         int rc = tc_thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;

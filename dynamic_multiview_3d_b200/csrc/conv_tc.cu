@@ -1300,14 +1300,18 @@ int tc_thin_fwd(const void* thin, int thin_dtype, const void* w, const float* bi
                 int Cw, int kh, int kw, int stride, int act, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (Cw % 8 || Cw > 256) return fail(DMV_E_UNSUPPORTED_SHAPE, "tc_thin_fwd: output channels");
     const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
+    if (thin_dtype == DMV_DT_S2D && !thin_s2d_eligible(Hb, Wb, Ct, Cw, kh, kw, stride))
+        return fail(DMV_E_INVALID_ARG, "DMV_DT_S2D input for a layer that does not take the space-to-depth path");
     if (thin_s2d_eligible(Hb, Wb, Ct, Cw, kh, kw, stride)) {
         // space-to-depth: stride-1 conv over X2[n][Hb/2][Wb/2][32] with kh2 x kw2 shifts on the halo kernel -- no patch matrix
         const S2dGeom g2 = thin_s2d_geom(Hb, Wb, kh, kw);
         const int S = g2.kh2 * g2.kw2;
-        const size_t Xb = align256((size_t)N * (Hb / 2) * (Wb / 2) * 64), Wp = align256((size_t)Cw * S * 64);
+        const bool given = thin_dtype == DMV_DT_S2D;          // the caller keeps X2 (dmv_thin_s2d_prep)
+        const size_t Xb = given ? 0 : align256((size_t)N * (Hb / 2) * (Wb / 2) * 64), Wp = align256((size_t)Cw * S * 64);
         if (!ws || ws_bytes < Xb + Wp || ((uintptr_t)ws & 255)) return fail(DMV_E_WORKSPACE, "tc_thin_fwd: workspace too small or unaligned");
         uint8_t* base = reinterpret_cast<uint8_t*>(ws);
-        int rc = thin_s2d_prep(thin, thin_dtype, base, N, Hb, Wb, Ct, st);
+        const void* x2 = given ? thin : base;
+        int rc = given ? DMV_OK : thin_s2d_prep(thin, thin_dtype, base, N, Hb, Wb, Ct, st);
         if (rc) return rc;
         rc = thin_s2d_pack_weights(w, base + Xb, Ct, Cw, kh, kw, ph.before, pw.before, g2, st);
         if (rc) return rc;
@@ -1320,7 +1324,7 @@ int tc_thin_fwd(const void* thin, int thin_dtype, const void* w, const float* bi
             p.taps[j].ph = 0; p.taps[j].pw = 0; p.taps[j].id = j;
         }
         Problem q;
-        q.src = base; q.N = N; q.Hs = Hb / 2; q.Ws = Wb / 2; q.Cs = 32; q.src_stride = 1;
+        q.src = x2; q.N = N; q.Hs = Hb / 2; q.Ws = Wb / 2; q.Cs = 32; q.src_stride = 1;
         q.w_hwio = base + Xb; q.kh = 1; q.kw = S; q.w_ci = S * 32; q.w_co = Cw; q.g_form = false; q.n_tile = 0; q.b_mode_override = 3; q.k_splits = 1;
         q.out = out; q.out_f32 = (out_dtype == DMV_DT_F32); q.out_H = ph.out; q.out_W = pw.out; q.n_real = Cw; q.out_mul = 1;
         q.Jh = ph.out; q.Jw = pw.out; q.bias = bias; q.act = act;

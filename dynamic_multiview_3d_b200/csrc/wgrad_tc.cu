@@ -1108,18 +1108,21 @@ int tc_thin_wgrad(const void* thin, int thin_dtype, const void* wide, float* dw,
     const SamePad ph = same_pad(Hb, kh, stride), pw = same_pad(Wb, kw, stride);
     const int rows = kh * kw * Ct, Kp = thin_patch_cols(kh * kw, Ct);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    if (thin_dtype == DMV_DT_S2D && !thin_s2d_eligible(Hb, Wb, Ct, Cw, kh, kw, stride))
+        return fail(DMV_E_INVALID_ARG, "DMV_DT_S2D input for a layer that does not take the space-to-depth path");
     if (thin_s2d_eligible(Hb, Wb, Ct, Cw, kh, kw, stride)) {
         // space-to-depth: stride-1 weight gradient over X2 (halo kernel), then the (shift, block) entries are gathered into dW
         const S2dGeom g2 = thin_s2d_geom(Hb, Wb, kh, kw);
         const int S = g2.kh2 * g2.kw2;
-        const size_t Xb = al((size_t)N * (Hb / 2) * (Wb / 2) * 64), Db = al((size_t)S * 32 * Cw * 4);
+        const bool given = thin_dtype == DMV_DT_S2D;          // the caller keeps X2 (dmv_thin_s2d_prep)
+        const size_t Xb = given ? 0 : al((size_t)N * (Hb / 2) * (Wb / 2) * 64), Db = al((size_t)S * 32 * Cw * 4);
         if (!ws || ws_bytes < Xb + Db || ((uintptr_t)ws & 255)) return fail(DMV_E_WORKSPACE, "tc_thin_wgrad: workspace too small or unaligned");
         uint8_t* base = reinterpret_cast<uint8_t*>(ws);
-        int rc = thin_s2d_prep(thin, thin_dtype, base, N, Hb, Wb, Ct, st);
+        int rc = given ? DMV_OK : thin_s2d_prep(thin, thin_dtype, base, N, Hb, Wb, Ct, st);
         if (rc) return rc;
         float* dw2 = reinterpret_cast<float*>(base + Xb);
         WProblem q;
-        q.big = base; q.N = N; q.Hb = Hb / 2; q.Wb = Wb / 2; q.Cb = 32; q.stride = 1;
+        q.big = given ? thin : base; q.N = N; q.Hb = Hb / 2; q.Wb = Wb / 2; q.Cb = 32; q.stride = 1;
         q.small = wide; q.Hs = ph.out; q.Ws = pw.out; q.Cs = Cw;
         q.kh = g2.kh2; q.kw = g2.kw2; q.pt = -g2.dh0; q.pl = -g2.dw0; q.dw = dw2;
         rc = run_wgrad(q, base + Xb + Db, ws_bytes - Xb - Db, st);

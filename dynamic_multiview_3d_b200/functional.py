@@ -14,7 +14,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT, ALGO, DT_BF16, DT_F32, LOSS, SAMPLER_ADD_GRID, SAMPLER_GRID_XY
+from ._lib import ACT, ALGO, DT_BF16, DT_F32, DT_S2D, LOSS, SAMPLER_ADD_GRID, SAMPLER_GRID_XY
 from ._lib import call as _real_call
 
 _workspaces = {}
@@ -140,19 +140,27 @@ class _Conv2d(torch.autograd.Function):
         y = torch.empty((B, same_out(H, stride), same_out(W, stride), Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
         ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), x.device)
-        call("dmv_conv2d_fwd", _p(x), _dt(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
+        # thin stride-2 layer (e0): build the space-to-depth tensor once and keep it for the weight gradient
+        xs, xs_dt = x, _dt(x)
+        n2 = _lib.load().dmv_thin_s2d_size(B, H, W, Cin, Cout, kh, kw, stride) if (Cin < 8 and algo != ALGO["simt"] and not _meta_depth[0]) else 0
+        if n2:
+            xs = torch.empty(n2, dtype=torch.uint8, device=x.device)
+            call("dmv_thin_s2d_prep", _p(x), _dt(x), _p(xs), B, H, W, Cin, _stream(x))
+            xs_dt = DT_S2D
+        call("dmv_conv2d_fwd", _p(xs), xs_dt, _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
              B, H, W, Cin, Cout, kh, kw, stride, ACT[act], _p(ws), ws.numel(), algo, _stream(x))
-        ctx.save_for_backward(x, y)
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] or not n2 else xs, y, xs)
+        ctx.xshape, ctx.xdtype, ctx.xs_dt = tuple(x.shape), x.dtype, xs_dt
         ctx.cfg = (wvar, bvar, stride, act, algo)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
+        x, y, xs = ctx.saved_tensors
         wvar, bvar, stride, act, algo = ctx.cfg
-        B, H, W, Cin = x.shape
+        B, H, W, Cin = ctx.xshape
         kh, kw, _, Cout = wvar.shape
-        st = _stream(x)
+        st = _stream(y)
         _tag[0] = wvar.name
         dy = dy.contiguous()
         bias_done = False
@@ -173,17 +181,17 @@ class _Conv2d(torch.autograd.Function):
             dpre = dy
         dx = None
         if ctx.needs_input_grad[1]:
-            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), x.device)
+            dx = torch.empty(ctx.xshape, dtype=torch.bfloat16, device=y.device)
+            ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), y.device)
             call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
-            if x.dtype != torch.bfloat16:
-                dxf = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+            if ctx.xdtype != torch.bfloat16:
+                dxf = torch.empty(ctx.xshape, dtype=ctx.xdtype, device=y.device)
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
                 dx = dxf
         pixels = B * y.shape[1] * y.shape[2]
         nws = _lib.load().dmv_wgrad_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
-        ws = workspace(nws, x.device)
-        call("dmv_conv2d_wgrad", _p(x), _dt(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None,
+        ws = workspace(nws, y.device)
+        call("dmv_conv2d_wgrad", _p(xs), ctx.xs_dt, _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None,
              B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
         store = wvar.store
         if bvar is not None:
@@ -228,15 +236,22 @@ class _Deconv2d(torch.autograd.Function):
         else:
             dpre = dy
         dx = None
+        # thin stride-2 head (flow field): one space-to-depth pass of the gradient serves dgrad and wgrad
+        dps, dps_dt = dpre, _dt(dpre)
+        n2 = _lib.load().dmv_thin_s2d_size(B, Ho, Wo, Cout, Cin, kh, kw, stride) if (Cout < 8 and algo != ALGO["simt"] and not _meta_depth[0]) else 0
+        if n2:
+            dps = torch.empty(n2, dtype=torch.uint8, device=x.device)
+            call("dmv_thin_s2d_prep", _p(dpre), _dt(dpre), _p(dps), B, Ho, Wo, Cout, st)
+            dps_dt = DT_S2D
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
             ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
-            call("dmv_deconv2d_dgrad", _p(dpre), _dt(dpre), _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
+            call("dmv_deconv2d_dgrad", _p(dps), dps_dt, _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
                  ws.numel(), algo, st)
         pixels = B * x.shape[1] * x.shape[2]
         nws = _lib.load().dmv_wgrad_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
         ws = workspace(nws, x.device)
-        call("dmv_deconv2d_wgrad", _p(x), _p(dpre), _dt(dpre), _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
+        call("dmv_deconv2d_wgrad", _p(x), _p(dps), dps_dt, _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
              ws.numel(), algo, st)
         wvar.store.notify_grad(wvar)
         return None, dx, None, None, None, None, None, None

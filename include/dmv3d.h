@@ -54,6 +54,8 @@ extern "C" {
 /* element types of activation tensors at the conv/linear boundary */
 #define DMV_DT_BF16 0
 #define DMV_DT_F32 1
+#define DMV_DT_S2D 2 /* the pointer is the space-to-depth bf16 tensor written by dmv_thin_s2d_prep (thin stride-2
+                        layers only: e0's image, the flow head's gradient); shapes still describe the ORIGINAL tensor */
 
 /* implementation selector for conv/deconv/linear entry points */
 #define DMV_ALGO_AUTO 0    /* tcgen05/TMEM/TMA implicit GEMM where the shape allows, else SIMT */
@@ -184,6 +186,13 @@ int dmv_act_bwd(const void* dy, const void* y, void* dpre, int dtype, long long 
 size_t dmv_act_bwd_bias_workspace_size(long long rows, int C);
 int dmv_act_bwd_bias(const void* dy_bf16, const void* y_bf16, void* dpre_bf16, float* db, long long rows,
                      int C, int act, void* workspace, size_t workspace_bytes, void* stream);
+/* Thin stride-2 layers (image side of e0, appearance_flow_model.py:88; 2-channel side of the flow head, :125) run on
+ * X2[n][H/2][W/2][32] = the 2x2 pixel block as channels (ph, pw, c), zero padded, bf16.  The conv / deconv entry
+ * points build X2 themselves from a DMV_DT_F32 / DMV_DT_BF16 tensor; a caller that keeps X2 between the forward
+ * and the weight-gradient call (or between dgrad and wgrad of the flow head) passes it with DMV_DT_S2D instead.
+ * dmv_thin_s2d_size returns the bytes of X2, or 0 when the layer shape does not take this path.                    */
+size_t dmv_thin_s2d_size(int N, int H, int W, int C_thin, int C_wide, int kh, int kw, int stride);
+int dmv_thin_s2d_prep(const void* thin, int thin_dtype, void* x2, int N, int H, int W, int C_thin, void* stream);
 int dmv_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int dmv_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, void* stream);
 
