@@ -182,10 +182,68 @@ def sampler_microbench(torch, pk, iters=20):
         gbs = nbytes / (us * 1e-6) / 1e9
         return {"us": round(us, 2), "gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 4), "bytes": nbytes}
 
-    return {"fwd": timeit(fwd, px * (8 + 8 * 3)),                    # 8 + 8C B/px
-            "bwd_grad_flow": timeit(bwd_flow, px * (16 + 8 * 3)),    # 16 + 8C (source is a network input)
-            "bwd_both": timeit(bwd_both, px * (16 + 12 * 3)),        # 16 + 12C
-            "shape": "64x224x224x3 fp32, flow U(-3,3), reference (Y,X) grid fused", "l2_policy": "4 rotating input sets (412 MB)"}
+    res = {"fwd": timeit(fwd, px * (8 + 8 * 3)),                    # 8 + 8C B/px
+           "bwd_grad_flow": timeit(bwd_flow, px * (16 + 8 * 3)),    # 16 + 8C (source is a network input)
+           "bwd_both": timeit(bwd_both, px * (16 + 12 * 3)),        # 16 + 12C
+           "shape": "64x224x224x3 fp32, flow U(-3,3), reference (Y,X) grid fused", "l2_policy": "4 rotating input sets (412 MB)"}
+    # second regime: smooth flows (rotation by 8..11 degrees about the centre), the shape of a trained network's output;
+    # U(-3,3) jitter is the worst case for shared-memory bank conflicts in the tap gathers
+    import math
+    ii, jj = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32), torch.arange(H, device=dev, dtype=torch.float32), indexing="ij")
+    c0 = (H - 1) / 2
+    for k in range(4):
+        a = math.radians(8.0 + k)
+        u = math.cos(a) * (ii - c0) - math.sin(a) * (jj - c0) + c0
+        v = math.sin(a) * (ii - c0) + math.cos(a) * (jj - c0) + c0
+        sets[k] = (sets[k][0], torch.stack([u - ii, v - jj], -1).unsqueeze(0).repeat(BATCH, 1, 1, 1).contiguous(), sets[k][2])
+    res["smooth"] = {"fwd": timeit(fwd, px * (8 + 8 * 3)), "bwd_grad_flow": timeit(bwd_flow, px * (16 + 8 * 3)),
+                     "shape": "same tensors, flow = rotation field of 8..11 degrees"}
+    return res
+
+
+def conv_microbench(torch, pk, iters=20):
+    """The heaviest conv layer of the graph (e0_0 / d1_0: 5x5, 32->32 at 112^2, B=64: 41.1 GFLOP) through the C ABI:
+    forward, input gradient and weight gradient against the measured sustained bf16 peak (tensor-pipe roofline)."""
+    from dynamic_multiview_3d_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    L = _lib.load()
+    B, Hc, C, k = BATCH, 112, 32, 5
+    bf = torch.bfloat16
+    x = torch.randn((B, Hc, Hc, C), device=dev).to(bf)
+    w = (torch.randn((k, k, C, C), device=dev) * 0.05).to(bf)
+    b = torch.zeros(C, device=dev)
+    y = torch.empty((B, Hc, Hc, C), device=dev, dtype=bf)
+    dy = torch.randn((B, Hc, Hc, C), device=dev).to(bf)
+    dx = torch.empty_like(x)
+    dw = torch.empty((k, k, C, C), device=dev)
+    ws = torch.empty(max(L.dmv_conv_workspace_size(B, Hc, Hc, C, C, k, k, 1), L.dmv_wgrad_workspace_size(B, Hc, Hc, C, C, k, k, 1), 256),
+                     dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    flop = 2.0 * B * Hc * Hc * k * k * C * C
+    calls = {
+        "fwd": lambda: _lib.call("dmv_conv2d_fwd", x.data_ptr(), 0, w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, B, Hc, Hc, C, C, k, k, 1, 1,
+                                 ws.data_ptr(), ws.numel(), 0, st),
+        "dgrad": lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, Hc, Hc, C, C, k, k, 1, ws.data_ptr(),
+                                   ws.numel(), 0, st),
+        "wgrad": lambda: _lib.call("dmv_conv2d_wgrad", x.data_ptr(), 0, dy.data_ptr(), dw.data_ptr(), None, B, Hc, Hc, C, C, k, k, 1,
+                                   ws.data_ptr(), ws.numel(), 0, st),
+    }
+    out = {"layer": "e0_0 / d1_0: conv 5x5 stride 1, 32->32, 64x112x112 (bf16 in, fp32 accumulate)", "flop_per_launch": flop,
+           "peak_tflops": pk["bf16_tflops_sustained"], "peak_src": pk["src"] + " (sustained)"}
+    for name, fn in calls.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / iters
+        tf = flop / us / 1e6
+        out[name] = {"us": round(us, 2), "tflops": round(tf, 1), "frac": round(tf / pk["bf16_tflops_sustained"], 4)}
+    return out
 
 
 def layer_gflop(B):
@@ -368,6 +426,12 @@ def main():
             micro = sampler_microbench(torch, pk)
         except Exception as ex:
             micro = {"error": repr(ex)[:200]}
+    conv = None
+    if not args.no_micro:
+        try:
+            conv = conv_microbench(torch, pk)
+        except Exception as ex:
+            conv = {"error": repr(ex)[:200]}
     if roof is None and micro and "fwd" in micro:
         roof = {"bound": "hbm", "kernel": "sampler_fwd", "achieved": micro["fwd"]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": micro["fwd"]["frac"], "traffic": None, "peak_src": pk["src"]}
@@ -391,7 +455,7 @@ def main():
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e, 4)},
             "gpu_launches": int(launches * K), "launches_per_step": int(launches),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sampler": micro, "top_kernels": top,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sampler": micro, "conv": conv, "top_kernels": top,
             "step_tflops_per_gpu": round(step_tflops, 2), "final_loss": last}
     emit(line)
     finish(world, rank)
