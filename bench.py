@@ -313,8 +313,21 @@ def main():
     if world > 1 or os.environ.get("DMV_OVERLAP_ADAM", "1") == "1":
         data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128" if world > 1 else "32")))
     b = make_batch(BATCH, H, "onehot19", seed=1234, rank=rank)
-    host = {k: torch.from_numpy(b[k]).pin_memory() for k in ("image0", "image1", "disp")}
-    devb = {k: v.to(dev) for k, v in host.items()}
+    # The host batch is held in the reference's storage format: uint8 pixels (read_tf_records.py:104-111, images are
+    # tf.decode_raw(..., tf.uint8) / 255).  The same quantised images, converted on the device, are the HBM-resident batch.
+    u8 = not args.eager and os.environ.get("DMV_BENCH_F32_INPUT", "0") != "1"
+    if u8:
+        import numpy as np
+        host = {k: torch.from_numpy(np.clip(np.rint(b[k] * 255.0), 0, 255).astype(np.uint8)).pin_memory() for k in ("image0", "image1")}
+        host["disp"] = torch.from_numpy(b["disp"]).pin_memory()
+        devb = {"disp": host["disp"].to(dev)}
+        for k in ("image0", "image1"):
+            t8 = host[k].to(dev)
+            devb[k] = torch.empty(t8.shape, dtype=torch.float32, device=dev)
+            _lib.call("dmv_u8_to_f32", t8.data_ptr(), devb[k].data_ptr(), t8.numel(), 255.0, torch.cuda.current_stream().cuda_stream)
+    else:
+        host = {k: torch.from_numpy(b[k]).pin_memory() for k in ("image0", "image1", "disp")}
+        devb = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     if args.eager:
@@ -450,7 +463,8 @@ def main():
             "config": {"workload": "single-view appearance-flow train step (fwd+bwd+Adam), 224x224 synthetic car renders, "
                                    "one-hot azimuth V=19, batch 64 per GPU (configs[1]; N>1 = batch-sharded data parallel)",
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": H, "loss": "l2 (reference)",
-                       "parallelism": "dp%d" % world, "cuda_graph": not args.eager, "algo": args.algo or F.get_default_algo(),
+                       "parallelism": "dp%d" % world, "cuda_graph": not args.eager,
+                       "host_input": "uint8 pixels (reference TFRecord format), /255 on the device" if u8 else "float32", "algo": args.algo or F.get_default_algo(),
                        "l2_policy": "per-step working set (parameters, Adam state, activations: several GB) >> 126 MB L2"},
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e, 4)},

@@ -120,6 +120,15 @@ __global__ void cast_b2f_kernel(const __nv_bfloat16* s, float* d, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = __bfloat162float(s[i]);
 }
 
+// uint8 pixels -> float32 / 255 (read_tf_records.py:111), four pixels per thread
+__global__ void u8_to_f32_kernel(const uchar4* __restrict__ s, float4* __restrict__ d, long long n4, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uchar4 v = __ldg(s + i);
+        d[i] = make_float4(__fdiv_rn((float)v.x, scale), __fdiv_rn((float)v.y, scale), __fdiv_rn((float)v.z, scale), __fdiv_rn((float)v.w, scale));
+    }
+}
+
 inline int grid_for(long long n, int per_block) {
     long long b = dmv::ceil_div_ll(n, per_block);
     if (b > 148 * 16) b = 148 * 16;
@@ -207,6 +216,13 @@ int dmv_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream)
     if (n == 0) return DMV_OK;
     cast_f2b_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
     return dmv::check_launch("cast_f32_to_bf16");
+}
+int dmv_u8_to_f32(const unsigned char* src, float* dst, long long n, float divisor, void* stream) {
+    DMV_REQUIRE(src && dst && n >= 0 && divisor != 0.f, DMV_E_INVALID_ARG, "u8_to_f32: bad argument");
+    DMV_REQUIRE((n & 3) == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 15) == 0, DMV_E_ALIGN, "u8_to_f32: n % 4 and 4/16-byte alignment");
+    if (n == 0) return DMV_OK;
+    u8_to_f32_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const uchar4*)src, (float4*)dst, n / 4, divisor);
+    return dmv::check_launch("u8_to_f32");
 }
 int dmv_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
     DMV_REQUIRE(src && dst && n >= 0, DMV_E_INVALID_ARG, "cast: bad argument");

@@ -37,6 +37,7 @@ class GraphedTrainStep:
         self.launches_per_step = 0
         self._stage = None
         self._pending = False
+        self._u8 = None
 
     def capture(self):
         from . import _lib
@@ -56,8 +57,23 @@ class GraphedTrainStep:
         return self
 
     def _copy_in(self, image0, image1, disp):
-        self.image0.copy_(image0, non_blocking=True)
-        self.image1.copy_(image1, non_blocking=True)
+        """Bring a batch into the graph's static fp32 buffers.  uint8 images (the reference's TFRecord pixel format,
+        a quarter of the PCIe bytes) are converted on the device: float32(pixel) / 255 (read_tf_records.py:111)."""
+        from . import _lib
+        st = torch.cuda.current_stream(self.model.device).cuda_stream
+        for dst, src in ((self.image0, image0), (self.image1, image1)):
+            if src.dtype == torch.uint8:
+                if not src.is_cuda:
+                    if self._u8 is None:
+                        self._u8 = {}
+                    buf = self._u8.get(id(dst))
+                    if buf is None:
+                        buf = self._u8[id(dst)] = torch.empty(dst.shape, dtype=torch.uint8, device=dst.device)
+                    buf.copy_(src, non_blocking=True)
+                    src = buf
+                _lib.call("dmv_u8_to_f32", src.data_ptr(), dst.data_ptr(), dst.numel(), 255.0, st)
+            else:
+                dst.copy_(src, non_blocking=True)
         self.disp.copy_(disp, non_blocking=True)
 
     def prefetch(self, image0, image1, disp):
@@ -65,7 +81,8 @@ class GraphedTrainStep:
         the step that is replayed meanwhile.  The following __call__ with ``staged=True`` consumes it."""
         dev = self.model.device
         if self._stage is None:
-            self._stage = [torch.empty_like(self.image0), torch.empty_like(self.image1), torch.empty_like(self.disp)]
+            self._stage = [torch.empty(self.image0.shape, dtype=image0.dtype, device=dev), torch.empty(self.image1.shape, dtype=image1.dtype, device=dev),
+                           torch.empty_like(self.disp)]
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._staged_ev = torch.cuda.Event()
             self._consumed_ev = torch.cuda.Event()
@@ -186,8 +203,8 @@ def main(argv=None):
         reader = build_tfrecord_input(dict(conf, image_size=model.image_shape[0]), training=True)
     for itr in range(itr_0, conf["num_iterations"] + 1):
         t0 = time.time()
-        if reader is not None:
-            fb = reader.float_batch()
+        if reader is not None:               # uint8 pixels go over PCIe as stored; /255 happens on the device (_copy_in)
+            fb = reader.next_batch()
             batch = {"image0": fb["image0"], "image1": fb["image1"], "disp": fb["displacement"]}
         else:
             batch = make_batch(model.batch_size, model.image_shape[0], V, seed=1234 + itr)

@@ -193,6 +193,9 @@ int dmv_act_bwd_bias(const void* dy_bf16, const void* y_bf16, void* dpre_bf16, f
  * dmv_thin_s2d_size returns the bytes of X2, or 0 when the layer shape does not take this path.                    */
 size_t dmv_thin_s2d_size(int N, int H, int W, int C_thin, int C_wide, int kh, int kw, int stride);
 int dmv_thin_s2d_prep(const void* thin, int thin_dtype, void* x2, int N, int H, int W, int C_thin, void* stream);
+/* uint8 pixels -> float32, dst = src / divisor in IEEE division (tf.cast(image, tf.float32) / 255.0,
+ * utils/read_tf_records.py:111): lets the input pipeline ship the reference's uint8 pixel format over PCIe. */
+int dmv_u8_to_f32(const unsigned char* src, float* dst, long long n, float divisor, void* stream);
 int dmv_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int dmv_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, void* stream);
 

@@ -254,3 +254,13 @@ def test_adam_matches_tf_oracle():
         assert np.allclose(v.m.cpu().numpy(), m, rtol=1e-5, atol=1e-12)       # fp32 FMA contraction vs NumPy
         assert np.allclose(v.v.cpu().numpy(), vv, rtol=1e-5, atol=1e-15)
         assert torch.equal(v.half, v.master.to(torch.bfloat16))          # bf16 compute copy refreshed in the same pass
+
+
+def test_u8_to_f32_matches_reference_division():
+    """dmv_u8_to_f32: float32(pixel) / 255 in IEEE division, bit for bit (read_tf_records.py:111)."""
+    from dynamic_multiview_3d_b200 import _lib
+    src = torch.arange(256, dtype=torch.uint8).repeat(64).cuda()
+    dst = torch.empty(src.numel(), dtype=torch.float32, device="cuda")
+    _lib.call("dmv_u8_to_f32", src.data_ptr(), dst.data_ptr(), src.numel(), 255.0, torch.cuda.current_stream().cuda_stream)
+    ref = (np.arange(256, dtype=np.uint8).astype(np.float32) / np.float32(255.0))
+    assert np.array_equal(dst.cpu().numpy().reshape(64, 256), np.tile(ref, (64, 1)))
