@@ -58,7 +58,6 @@ struct IgemmParams {
     int halo_pitch, halo_h, min_dh, min_dw;   // halo kernel: window rows x pitch pixels, origin offset of the window
     int planes, plane_bytes;      // halo kernel over a stride-2 source: the two row-parity planes of the parity view are separate
                                   // windows (tap.ph selects one); the column parity is folded into the 2C channels of a row
-    int a_slot;                   // igemm: bytes reserved for the A tile of a stage
     int d2s, d2s_c;               // sub-pixel form: column (class, c) of a tile row goes to output pixel (2*jh + py, 2*jw + px), channel c
     TapClass cls[4];
     Tap taps[kMaxTaps];
@@ -265,9 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                                                              const __grid_constant__ IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int kRowBytes = KC * 2;
-    // A slot of a stage: 128 rows, or only the loaded rows when the tile has <= 64 of them (linear layers, M = 64 samples):
-    // the MMA still reads 128 rows, the upper ones alias the B tile and land in accumulator rows that are never stored
-    const int kABytes = p.a_slot;
+    constexpr int kABytes = 128 * kRowBytes;
     const int b_bytes = p.n_pad * kRowBytes;     // mode 2: (n_pad/64) boxes of KC rows x 128 B -- the same size
     const int stage_bytes = kABytes + b_bytes;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -858,12 +855,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         }
     }
     // ---- shared memory / grid
-    p.a_slot = 128 * row_bytes;
-    if (p.rows <= 64 && !getenv("DMV_NO_ASLOT")) {
-        const int need = ((p.rows * row_bytes + 1023) / 1024) * 1024;
-        if (p.n_pad * row_bytes >= 128 * row_bytes - need) p.a_slot = need;     // the aliased rows stay inside the stage
-    }
-    const int stage_bytes = p.a_slot + p.n_pad * row_bytes;
+    const int stage_bytes = 128 * row_bytes + p.n_pad * row_bytes;
     // The pipeline is latency-bound (one TMA box per tap): keep as many bytes in flight per SM as
     // possible.  Narrow layers (N <= 64) run two CTAs per SM, each with half of the shared memory.
     const bool two_per_sm = p.n_pad <= 64;
