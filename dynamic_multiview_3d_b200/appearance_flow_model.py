@@ -17,6 +17,8 @@ Extra conf keys (all optional): image_size (128), viewpoint_dim (2), loss ('l2' 
 'l1' = north-star), grid_order ('ref_yx' = the reference's transposing (Y,X) grid, 'xy'),
 algo ('auto'|'simt'|'tcgen05'), seed (0).
 """
+import os
+
 import torch
 
 from . import functional as F
@@ -143,10 +145,30 @@ class AppearanceFlowModel(object):
         self.loss = F.reconstruction_loss(self.gen, image1, self.loss_mode, inv_count=1.0 / n, unit_upstream=True)
         return self.loss
 
+    def forward_and_loss(self, image0, image1, disp):
+        """forward + build_loss with the warp, the loss and the flow gradient fused into one kernel (the training
+        path).  Falls back to the separate calls for shapes the fused kernel does not cover."""
+        if type(self).forward is not AppearanceFlowModel.forward or type(self).build_loss is not AppearanceFlowModel.build_loss \
+                or self.device.type == "meta":
+            self.forward(image0, disp)
+            return self.build_loss(image1)
+        self.flow_field = self.gen = self.loss = None
+        self.store.new_anchor()
+        self.image0, self.disp, self.image1 = image0, disp, image1
+        with use_store(self.store):
+            self.flow_field = self.buildModel(image0, F.to_bf16(disp))
+        if not F.warp_loss_supported(image0, self.flow_field) or os.environ.get("DMV_NO_WARP_LOSS"):
+            with use_store(self.store):
+                self.gen = flow_resample_layer(image0, self.flow_field, self.grid_order)
+            return self.build_loss(image1)
+        n = image1.shape[0] * image1.shape[1] * image1.shape[2] * self.world_size
+        self.loss, self.gen = F.flow_resample_loss(image0, self.flow_field, image1, self.loss_mode, inv_count=1.0 / n,
+                                                   grid_order=self.grid_order, unit_upstream=True)
+        return self.loss
+
     def train_step(self, image0, image1, disp):
         """One sess.run([loss, train_op]) of train.py:122: forward, backward, Adam."""
-        self.forward(image0, disp)
-        loss = self.build_loss(image1)
+        loss = self.forward_and_loss(image0, image1, disp)
         loss.backward()
         if self.store.grad_ready_hook is not None and hasattr(self, "_dp"):
             self._dp.finish()

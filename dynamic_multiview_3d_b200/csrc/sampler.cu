@@ -291,14 +291,30 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_MINBLOCKS) sampler_tile_kern
 //     smooth flows, flow loads / grad_flow stores are coalesced 8-byte accesses.
 constexpr int kBoxS = SAMPLER_BOX, kBoxL = SAMPLER_BOX_L;   // source window box (pixels); tap boxes beyond the larger one fall back to global gathers
 
+// MODE 2 (training step): forward + reconstruction loss + grad wrt flow in ONE pass -- the warped tile never leaves
+// the SM between the three: gen is stored for the caller, d = gen - target feeds the loss partial and, through
+// dL/dgen = inv_count * w_c * (2 d | sign d), the flow gradient from the taps that are still in shared memory.
+// Per-CTA loss partials (double) are summed in index order by the last CTA (all its threads, fixed tree).
+struct FuseArgs {
+    float w[4];
+    float inv_count;
+    int mode;
+    double* partials;
+    unsigned* counter;
+    float* loss_out;
+    float* grad_wf;
+};
+
 template <int C, int MODE>
 __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_kernel(
     const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_src_l,
-    const __grid_constant__ CUtensorMap map_io, const float* __restrict__ data, const float* __restrict__ wf, float* __restrict__ out,
-    int32_t* __restrict__ dbg_idx, uint8_t* __restrict__ dbg_mask, Geom g) {
+    const __grid_constant__ CUtensorMap map_io, const __grid_constant__ CUtensorMap map_tgt, const float* __restrict__ data,
+    const float* __restrict__ wf, float* __restrict__ out, int32_t* __restrict__ dbg_idx, uint8_t* __restrict__ dbg_mask, Geom g,
+    const FuseArgs fa) {
     extern __shared__ __align__(128) float s_dyn[];
     float* s_win = s_dyn;                              // [box][box * C], box = kBoxS or kBoxL
-    float* s_io = s_dyn + kBoxL * kBoxL * C;           // [32][32 * C]: MODE 0 results, MODE 1 grad_out
+    float* s_io = s_dyn + kBoxL * kBoxL * C;           // [32][32 * C]: MODE 0/2 results, MODE 1 grad_out
+    float* s_tgt = s_io + 32 * 32 * C;                 // MODE 2: target tile
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_box[4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -314,10 +330,15 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_k
             tc::mbar_expect_tx(&s_bar[1], 32 * 32 * C * 4);
             tc::tma_load_3d(s_io, &map_io, &s_bar[1], j0 * C, i0, b);
         }
+        if (MODE == 2) {
+            tc::mbar_expect_tx(&s_bar[1], 32 * 32 * C * 4);
+            tc::tma_load_3d(s_tgt, &map_tgt, &s_bar[1], j0 * C, i0, b);
+        }
     }
     __syncthreads();
 
     const int j = j0 + lane;
+    float loss_acc = 0.f;
     float sx[kPPT], sy[kPPT];
     bool valid[kPPT];
     int fx[kPPT], fy[kPPT];
@@ -371,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_k
         }
         tc::mbar_wait(&s_bar[0], 0);
     }
-    if (MODE == 1) tc::mbar_wait(&s_bar[1], 0);
+    if (MODE >= 1) tc::mbar_wait(&s_bar[1], 0);
 
 #pragma unroll
     for (int k = 0; k < kPPT; ++k) {
@@ -424,6 +445,36 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_k
                 v = __fadd_rn(v, __fmul_rn(w_cf, p_cf[c]));
                 io[c] = valid[k] ? v : 0.f;
             }
+        } else if (MODE == 2) {
+            const float w_ff = __fmul_rn(dx, dy), w_cc = __fmul_rn(omdx, omdy), w_fc = __fmul_rn(dx, omdy),
+                        w_cf = __fmul_rn(omdx, dy);
+            const float* tg = s_tgt + (r * 32 + lane) * C;
+            float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float v = __fmul_rn(w_ff, p_ff[c]);
+                v = __fadd_rn(v, __fmul_rn(w_cc, p_cc[c]));
+                v = __fadd_rn(v, __fmul_rn(w_fc, p_fc[c]));
+                v = __fadd_rn(v, __fmul_rn(w_cf, p_cf[c]));
+                v = valid[k] ? v : 0.f;
+                io[c] = v;
+                // loss and dL/dgen exactly as loss_flat_kernel (loss.cu): out-of-image pixels have gen = target = 0
+                const float d = __fsub_rn(v, tg[c]);
+                float gq;
+                if (fa.mode == DMV_LOSS_L2) {
+                    loss_acc = __fadd_rn(loss_acc, __fmul_rn(__fmul_rn(fa.w[c], d), d));
+                    gq = __fmul_rn(2.0f, d);
+                } else {
+                    loss_acc = __fadd_rn(loss_acc, __fmul_rn(fa.w[c], fabsf(d)));
+                    gq = (d > 0.f) ? 1.0f : (d < 0.f ? -1.0f : 0.0f);
+                }
+                const float gc = __fmul_rn(__fmul_rn(gq, fa.w[c]), fa.inv_count);
+                const float a0 = __fadd_rn(__fmul_rn(omdy, __fsub_rn(p_cc[c], p_fc[c])), __fmul_rn(dy, __fsub_rn(p_cf[c], p_ff[c])));
+                const float a1 = __fadd_rn(__fmul_rn(omdx, __fsub_rn(p_cc[c], p_cf[c])), __fmul_rn(dx, __fsub_rn(p_fc[c], p_ff[c])));
+                g0 = __fadd_rn(g0, __fmul_rn(gc, a0));
+                g1 = __fadd_rn(g1, __fmul_rn(gc, a1));
+            }
+            if (inb) reinterpret_cast<float2*>(fa.grad_wf)[img_pix + (long long)i * g.Wo + j] = valid[k] ? make_float2(g0, g1) : make_float2(0.f, 0.f);
         } else {
             float g0 = 0.f, g1 = 0.f;
 #pragma unroll
@@ -437,14 +488,44 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_k
             if (inb) reinterpret_cast<float2*>(out)[img_pix + (long long)i * g.Wo + j] = valid[k] ? make_float2(g0, g1) : make_float2(0.f, 0.f);
         }
     }
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
         tc::fence_proxy_async();          // generic-proxy writes of s_io -> visible to the bulk store
         __syncthreads();
+        if (tid == 0) tc::tma_store_3d(&map_io, s_io, j0 * C, i0, b);
+    }
+    if (MODE == 2) {
+        // deterministic loss: fixed tree inside the CTA, per-CTA partials, ordered sum by the last CTA to finish
+        __shared__ double s_red[kWarps];
+        __shared__ bool s_last;
+        double local = (double)loss_acc;
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if (lane == 0) s_red[warp] = local;
+        __syncthreads();
         if (tid == 0) {
-            tc::tma_store_3d(&map_io, s_io, j0 * C, i0, b);
-            tc::bulk_commit_wait_read();  // the tile must stay in shared memory until the store has read it
+            double t = 0.0;
+            for (int w = 0; w < kWarps; ++w) t += s_red[w];
+            fa.partials[blockIdx.x] = t;
+            __threadfence();
+            s_last = (atomicAdd(fa.counter, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double t = 0.0;
+            for (unsigned q = tid; q < gridDim.x; q += kThreads) t += __ldcg(fa.partials + q);   // thread-strided, fixed order
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            __syncthreads();
+            if (lane == 0) s_red[warp] = t;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < kWarps; ++w) tot += s_red[w];
+                *fa.loss_out = (float)(tot * (double)fa.inv_count);
+                *fa.counter = 0;          // ready for the next launch (stream-ordered)
+            }
         }
     }
+    if ((MODE == 0 || MODE == 2) && tid == 0) tc::bulk_commit_wait_read();   // the tile stays in shared memory until the store has read it
 }
 
 int encode_f32_map(CUtensorMap* map, const float* base, int inner, int rows, int batch, int box_inner, int box_rows) {
@@ -615,7 +696,7 @@ int launch_tile(const float* data, const float* wf, const float* go, float* out,
             cudaFuncSetAttribute(sampler_tma_kernel<CT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm); \
             attr_done = true;                                                                            \
         }                                                                                                \
-        sampler_tma_kernel<CT, MODE><<<grid, kThreads, wsm, st>>>(map_src, map_src_l, map_io, data, wf, out, di, dm, g); \
+        sampler_tma_kernel<CT, MODE><<<grid, kThreads, wsm, st>>>(map_src, map_src_l, map_io, map_io, data, wf, out, di, dm, g, FuseArgs()); \
     } while (0)
         if (g.C == 1) DMV_LAUNCH_TMA(1);
         else if (g.C == 3) DMV_LAUNCH_TMA(3);
@@ -709,6 +790,55 @@ int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out, f
         if (rc) return rc;
     }
     return DMV_OK;
+}
+
+size_t dmv_sampler_loss_workspace_size(int B, int Hout, int Wout) {
+    if (B <= 0 || Hout <= 0 || Wout <= 0) return 0;
+    return (size_t)B * ceil_div(Wout, 32) * ceil_div(Hout, 32) * sizeof(double) + 16;
+}
+
+int dmv_sampler_loss_fused(const float* data, const float* wf, const float* target, const float* chan_weight, int mode, float inv_count,
+                           float* gen_out, float* grad_wf, float* loss_out, int B, int H, int W, int C, int Hout, int Wout,
+                           unsigned flags, void* workspace, size_t workspace_bytes, void* stream) {
+    DMV_REQUIRE(data && wf && target && chan_weight && gen_out && grad_wf && loss_out, DMV_E_INVALID_ARG, "sampler_loss_fused: null pointer");
+    DMV_REQUIRE(mode == DMV_LOSS_L2 || mode == DMV_LOSS_L1, DMV_E_INVALID_ARG, "sampler_loss_fused: unknown loss mode");
+    Geom g;
+    int rc = make_geom(g, B, H, W, C, Hout, Wout, flags);
+    if (rc) return rc;
+    const bool aligned = (((uintptr_t)data | (uintptr_t)wf | (uintptr_t)target | (uintptr_t)gen_out | (uintptr_t)grad_wf) & 15) == 0;
+    if (!(g.tw_shift == 5 && (C == 1 || C == 3 || C == 4) && ((W * C) & 3) == 0 && ((Wout * C) & 3) == 0 && aligned))
+        return fail(DMV_E_UNSUPPORTED_SHAPE, "sampler_loss_fused: needs C in {1,3,4}, 16-byte aligned rows and buffers, image-shaped output");
+    const int grid = g.B * g.tiles_x * g.tiles_y;
+    DMV_REQUIRE(workspace && workspace_bytes >= dmv_sampler_loss_workspace_size(B, Hout, Wout) && ((uintptr_t)workspace & 7) == 0, DMV_E_WORKSPACE,
+                "sampler_loss_fused: workspace too small or unaligned (it must be zeroed once and not shared)");
+    CUtensorMap map_src, map_src_l, map_io, map_tgt;
+    rc = encode_f32_map(&map_src, data, W * C, H, B, kBoxS * C, kBoxS);
+    if (!rc) rc = encode_f32_map(&map_src_l, data, W * C, H, B, kBoxL * C, kBoxL);
+    if (!rc) rc = encode_f32_map(&map_io, gen_out, Wout * C, Hout, B, 32 * C, 32);
+    if (!rc) rc = encode_f32_map(&map_tgt, target, Wout * C, Hout, B, 32 * C, 32);
+    if (rc) return rc;
+    FuseArgs fa;
+    for (int c = 0; c < 4; ++c) fa.w[c] = c < C ? chan_weight[c] : 0.f;
+    fa.inv_count = inv_count; fa.mode = mode;
+    fa.counter = reinterpret_cast<unsigned*>(workspace);                 // fixed place: survives calls with other grid sizes
+    fa.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
+    fa.loss_out = loss_out; fa.grad_wf = grad_wf;
+    const size_t wsm = (size_t)(kBoxL * kBoxL + 2 * 32 * 32) * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DMV_LAUNCH_FUSED(CT)                                                                                  \
+    do {                                                                                                      \
+        static bool attr_done = false;                                                                        \
+        if (!attr_done) {                                                                                     \
+            cudaFuncSetAttribute(sampler_tma_kernel<CT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm); \
+            attr_done = true;                                                                                 \
+        }                                                                                                     \
+        sampler_tma_kernel<CT, 2><<<grid, kThreads, wsm, st>>>(map_src, map_src_l, map_io, map_tgt, data, wf, gen_out, nullptr, nullptr, g, fa); \
+    } while (0)
+    if (C == 1) DMV_LAUNCH_FUSED(1);
+    else if (C == 3) DMV_LAUNCH_FUSED(3);
+    else DMV_LAUNCH_FUSED(4);
+#undef DMV_LAUNCH_FUSED
+    return check_launch("sampler_loss_fused");
 }
 
 }  // extern "C"

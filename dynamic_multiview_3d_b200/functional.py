@@ -402,6 +402,63 @@ def flow_resampler(data, flow, grid_order="ref_yx"):
     return _Resampler.apply(data, flow, flags)
 
 
+_loss_wss = {}
+
+
+class _WarpLoss(torch.autograd.Function):
+    """flow -> (loss, gen): resample_layer(src, warp_pts_layer(flow)), the reconstruction loss against the target and
+    d loss / d flow in one kernel (dmv_sampler_loss_fused).  The source and the target are network inputs."""
+
+    @staticmethod
+    def forward(ctx, data, flow, target, flags, weights, mode, inv_count, unit_upstream):
+        _need_cuda(data, flow, target)
+        data, flow, target = data.contiguous(), flow.contiguous(), target.contiguous()
+        B, H, W, Cc = data.shape
+        Ho, Wo = flow.shape[1], flow.shape[2]
+        gen = torch.empty((B, Ho, Wo, Cc), dtype=torch.float32, device=data.device)
+        gflow = torch.empty_like(flow)
+        loss = torch.empty((), dtype=torch.float32, device=data.device)
+        w = (C.c_float * Cc)(*[float(x) for x in weights])
+        nws = _lib.load().dmv_sampler_loss_workspace_size(B, Ho, Wo)
+        key = ("warp_loss", data.device.type, data.device.index)
+        ws = _loss_wss.get(key)
+        if ws is None or ws.numel() < nws:             # zeroed once: holds a self-resetting counter
+            ws = _loss_wss[key] = torch.zeros(int(nws), dtype=torch.uint8, device=data.device)
+        _tag[0] = "warp_loss"
+        call("dmv_sampler_loss_fused", _p(data), _p(flow), _p(target), w, LOSS[mode], float(inv_count), _p(gen), _p(gflow), _p(loss),
+             B, H, W, Cc, Ho, Wo, flags, _p(ws), ws.numel(), _stream(data))
+        ctx.gflow, ctx.unit_upstream = gflow, unit_upstream
+        ctx.mark_non_differentiable(gen)
+        return loss, gen
+
+    @staticmethod
+    def backward(ctx, gloss, _ggen):
+        gflow = ctx.gflow
+        if not ctx.unit_upstream:
+            _tag[0] = "warp_loss"
+            call("dmv_scale_by_device_scalar", _p(gflow), _p(gloss.contiguous().to(torch.float32)), gflow.numel(), _stream(gflow))
+        return None, gflow, None, None, None, None, None, None
+
+
+def warp_loss_supported(data, flow):
+    """Shapes the fused kernel covers (the C ABI returns DMV_E_UNSUPPORTED_SHAPE otherwise)."""
+    Cc, W, Wo = data.shape[-1], data.shape[2], flow.shape[2]
+    return flow.dim() == 4 and flow.shape[1] > 1 and Cc in (1, 3, 4) and (W * Cc) % 4 == 0 and (Wo * Cc) % 4 == 0
+
+
+def flow_resample_loss(data, flow, target, mode="l2", weights=None, inv_count=None, grid_order="ref_yx", unit_upstream=False):
+    """(loss, gen) of the training step's tail: warp ``data`` by ``flow`` (grid formed in the kernel), compare with
+    ``target``.  One launch instead of sampler forward + loss + sampler backward."""
+    if grid_order not in ("ref_yx", "xy"):
+        raise ValueError(grid_order)
+    flags = SAMPLER_ADD_GRID | (SAMPLER_GRID_XY if grid_order == "xy" else 0)
+    Cc = data.shape[-1]
+    weights = [1.0] * Cc if weights is None else list(weights)
+    if inv_count is None:
+        inv_count = 1.0 / (target.numel() // Cc)
+    return _WarpLoss.apply(data, flow, target, flags, tuple(weights), mode, inv_count, unit_upstream)
+
+
 def resampler_debug(data, wf, flags=0):
     """Forward plus the bit-exact targets: corner indices [.,4] int32 and predicate mask uint8."""
     _need_cuda(data, wf)
@@ -462,9 +519,6 @@ class _FusedLoss(torch.autograd.Function):
         if gl is not None:
             call("dmv_scale_by_device_scalar", _p(gl), _p(gloss), gl.numel(), st)
         return gg, gl, None, None, None, None, None, None, None
-
-
-_loss_wss = {}
 
 
 def _loss_ws(device, nbytes):

@@ -95,6 +95,21 @@ int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out,
                     int Wout, unsigned flags, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Training-step fusion of the three calls above: resample_layer(src, warp_pts_layer(flow)) (tf_utils.py:35-42,
+ * appearance_flow_model.py:126-127), euclidean_loss / l1_loss against the target (tf_utils.py:18-23,
+ * appearance_flow_model.py:73) and the gradient wrt the flow (ResamplerGrad through the loss gradient) in ONE kernel:
+ *   gen_out [B,Hout,Wout,C] = the warped image (as dmv_sampler_fwd, same bits)
+ *   loss_out = inv_count * sum_pixels sum_c w_c * ((gen - target)^2 | |gen - target|)
+ *   grad_wf [B,Hout,Wout,2] = d loss / d flow                     (as dmv_loss_fused_fwd_bwd + dmv_sampler_bwd)
+ * Needs C in {1,3,4}, W*C and Wout*C multiples of 4, 16-byte aligned buffers; otherwise DMV_E_UNSUPPORTED_SHAPE
+ * (use the three separate calls).  workspace: dmv_sampler_loss_workspace_size bytes, zeroed ONCE by the caller and
+ * not shared with other calls (it holds a self-resetting counter).                                                */
+size_t dmv_sampler_loss_workspace_size(int B, int Hout, int Wout);
+int dmv_sampler_loss_fused(const float* data, const float* wf, const float* target, const float* chan_weight,
+                           int mode, float inv_count, float* gen_out, float* grad_wf, float* loss_out, int B, int H,
+                           int W, int C, int Hout, int Wout, unsigned flags, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- fused loss (+ multi-view confidence fusion) forward and backward ----------------- *
  * replaces euclidean_loss / l1_loss (tf_utils.py:18-23) and the weighted sums of
  * main_model.py:144-154, multiobject_appflow.py:223-283, plus their gradients.

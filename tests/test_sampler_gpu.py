@@ -196,3 +196,37 @@ def test_rectangle_fixture_on_gpu(golden_dir):
     assert hashlib.sha256(out8.tobytes()).digest() == g["sha256"].tobytes()
     rect = np.all(out8 == g["fg"], axis=-1)
     assert abs(mg.principal_angle(rect) % 180.0 - 10.0) < 0.5
+
+
+@pytest.mark.parametrize("C,mode,order", [(3, "l2", "ref_yx"), (3, "l1", "xy"), (4, "l2", "xy"), (1, "l2", "ref_yx")])
+def test_fused_warp_loss_matches_the_three_separate_calls(C, mode, order):
+    """dmv_sampler_loss_fused == sampler forward + fused loss + sampler backward: gen and d loss / d flow bit for bit
+    (same arithmetic), the loss to summation-order accuracy; and all three against the NumPy oracle."""
+    from dynamic_multiview_3d_b200 import functional as F
+    rng = np.random.default_rng(C * 10 + len(mode))
+    B, H = 3, 72                                             # 72 = ragged 32x32 tiling, rows 16-byte aligned for C = 3
+    data = rng.random((B, H, H, C), dtype=np.float32)
+    target = rng.random((B, H, H, C), dtype=np.float32)
+    flow = rng.uniform(-3, 3, (B, H, H, 2)).astype(np.float32)
+    flow[0, :4, :4] = 500.0                                  # invalid samples: gen = 0, no flow gradient
+    wts = [1.0, 0.5, 2.0, 0.1][:C]
+    inv = 1.0 / (B * H * H)
+    d, t = torch.from_numpy(data).cuda(), torch.from_numpy(target).cuda()
+    f1 = torch.from_numpy(flow).cuda().requires_grad_(True)
+    gen1 = F.flow_resampler(d, f1, order)
+    l1 = F.reconstruction_loss(gen1, t, mode, weights=wts, inv_count=inv)
+    l1.backward()
+    f2 = torch.from_numpy(flow).cuda().requires_grad_(True)
+    assert F.warp_loss_supported(d, f2)
+    l2, gen2 = F.flow_resample_loss(d, f2, t, mode, weights=wts, inv_count=inv, grid_order=order)
+    l2.backward()
+    assert torch.equal(gen1.detach(), gen2)
+    assert torch.equal(f1.grad, f2.grad)
+    assert float(l2) == pytest.approx(float(l1), rel=1e-6)
+    grid = T.coords(H, H, B) if order == "ref_yx" else T.coords(H, H, B)[..., ::-1]
+    ref = T.resampler(data, (flow + grid).astype(np.float32))
+    assert np.array_equal(gen2.cpu().numpy(), ref)
+    dd = ref.astype(np.float64) - target
+    w = np.asarray(wts, np.float64)
+    rl = ((dd * dd if mode == "l2" else np.abs(dd)) * w).sum() * inv
+    assert float(l2) == pytest.approx(rl, rel=1e-5)
