@@ -33,6 +33,24 @@ struct LossParams {
     float w[kMaxC];
 };
 
+// Last CTA: ordered sum of the per-CTA partials by all its threads (thread t takes partials t, t + 256, ... in order,
+// then a fixed tree) -- deterministic, and not one thread walking a thousand dependent loads.
+__device__ __forceinline__ void final_sum(const LossParams& p, double* s_red) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) t += __ldcg(p.partials + i);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) tot += s_red[w];
+        *p.loss_out = (float)(tot * (double)p.inv_count);
+        *p.counter = 0;  // ready for the next launch (stream-ordered)
+    }
+}
+
 template <int CT>
 __global__ void __launch_bounds__(kThreads) loss_kernel(LossParams p) {
     const int C = CT ? CT : p.C;
@@ -106,13 +124,7 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(LossParams p) {
         s_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        double t = 0.0;
-        for (unsigned i = 0; i < gridDim.x; ++i) t += ((volatile double*)p.partials)[i];
-        *p.loss_out = (float)(t * (double)p.inv_count);
-        *p.counter = 0;  // ready for the next launch (stream-ordered)
-    }
+    if (s_last) final_sum(p, s_red);
 }
 
 // Plain (single view, unmasked) loss over the flat [pixels*C] arrays: float4 loads/stores, channel = index % C.
@@ -155,13 +167,7 @@ __global__ void __launch_bounds__(kThreads) loss_flat_kernel(LossParams p) {
         s_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        double t = 0.0;
-        for (unsigned i = 0; i < gridDim.x; ++i) t += ((volatile double*)p.partials)[i];
-        *p.loss_out = (float)(t * (double)p.inv_count);
-        *p.counter = 0;
-    }
+    if (s_last) final_sum(p, s_red);
 }
 
 __global__ void scale_kernel(float* x, const float* s, long long n) {
