@@ -347,7 +347,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing
+    # ---------------- device-resident timing: the batch sits in the captured step's static input buffers
+    resident = (lambda: step.replay()) if not args.eager else (lambda: step_fn(devb["image0"], devb["image1"], devb["disp"]))
     for _ in range(W):
         step_fn(devb["image0"], devb["image1"], devb["disp"])
     sampler = ClockSampler(local) if rank == 0 else None
@@ -357,7 +358,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        loss = step_fn(devb["image0"], devb["image1"], devb["disp"])
+        loss = resident()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / K

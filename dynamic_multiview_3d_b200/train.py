@@ -76,6 +76,11 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         self.disp.copy_(disp, non_blocking=True)
 
+    def replay(self):
+        """One more step on the batch that already sits in the static buffers (no copy at all)."""
+        self.graph.replay()
+        return self.loss
+
     def prefetch(self, image0, image1, disp):
         """Start the host->device copy of the NEXT step's batch on a copy stream into staging buffers; it overlaps
         the step that is replayed meanwhile.  The following __call__ with ``staged=True`` consumes it."""
