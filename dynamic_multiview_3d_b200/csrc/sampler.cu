@@ -2,11 +2,16 @@
 //
 //   forward / grad_warp : one CTA per 1024-pixel OUTPUT tile.  The CTA loads its flow
 //     vectors (coalesced float2), forms warp = flow + grid in registers, reduces the
-//     bounding box of the taps it needs, stages that SOURCE window into shared memory with
-//     coalesced row-segment loads, then gathers the four taps from shared memory.  When the
-//     window does not fit (arbitrary warps) it gathers straight from global (L1/L2).
-//     The arithmetic uses non-contracted fp32 ops in the reference's summation order, so
-//     the forward values and grad_warp are bit-equal to the NumPy oracle.
+//     bounding box of the taps it needs, stages that SOURCE window into shared memory, then
+//     gathers the four taps from shared memory.  When the window does not fit (arbitrary
+//     warps) it gathers straight from global (L1/L2).  The arithmetic uses non-contracted
+//     fp32 ops in the reference's summation order, so the forward values and grad_warp are
+//     bit-equal to the NumPy oracle.  Two forms:
+//       sampler_tma_kernel  (C in {1,3,4}, 16-byte aligned rows -- the training path): window,
+//         grad_out / target tiles and the output tile move by TMA; MODE 2 fuses forward, the
+//         reconstruction loss and grad_warp into one pass (dmv_sampler_loss_fused);
+//       sampler_tile_kernel (any C <= 16, any alignment, 1-D sample lists): cp.async staging,
+//         predicated taps.
 //   grad_data : owner-computes scatter.  One CTA owns a 32x16 SOURCE tile; it visits every
 //     output tile whose tap box intersects it (box table from a pre-pass), and each warp
 //     accumulates into a warp-private shared-memory copy of the tile.  Lanes that hit the
