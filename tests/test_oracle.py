@@ -297,3 +297,61 @@ def test_fusion_definition():
     f = G.fuse_views(G.NumpyOps(), gens, logits)
     w = np.exp(logits) / np.exp(logits).sum(0, keepdims=True)
     assert np.allclose(f, (w * gens).sum(0))
+
+
+MO_CONFS = [{"use_color": "", "use_depth": 0.1, "combination_image": "", "gen_sep_images": "", "predict_target_masks": 0.1,
+             "masked_image_loss": ""},
+            {"use_color": "", "combination_image": "", "fully_conv": ""}]
+
+
+def _mo_batch(rng, B, H):
+    names = ["image0", "image0_mask0", "image0_mask1", "image1", "image1_only0", "image1_only1", "image1_mask0", "image1_mask1",
+             "depth0", "depth1", "depth1_only0", "depth1_only1"]
+    b = {n: rng.random((B, H, H, 3 if (n.startswith("image") and "mask" not in n) else 1), dtype=np.float32) for n in names}
+    b["displacement"] = rng.standard_normal((B, 2)).astype(np.float32)
+    return b
+
+
+@pytest.mark.parametrize("conf", MO_CONFS)
+def test_multiobject_graph_numpy_vs_torch_cpu(conf):
+    """The two backends of the oracle agree on the restatement of multiobject_appflow.py:123-283, the heads come out in
+    the reference's pop() order, and a masked loss ignores pixels outside the mask."""
+    rng = np.random.default_rng(3)
+    B, H, V = 1, 32, 2
+    P = G.init_params(G.multiobject_param_shapes(H, V, conf), 0)
+    b = _mo_batch(rng, B, H)
+    o = G.multiobject_forward(G.NumpyOps(), P, conf, b)
+    t = G.multiobject_forward(G.TorchCpuOps(), P, conf, b)
+    assert list(o) == [h[0] for h in G._mo_heads(conf)]
+    for k in o:
+        assert o[k].shape == (B, H, H, 3 if k.startswith("gen_image1") and "mask" not in k else 1)
+        assert np.allclose(o[k], np.asarray(t[k]), rtol=1e-3, atol=1e-4), k
+    l_np = float(G.multiobject_loss(G.NumpyOps(), o, conf, b))
+    l_t = float(G.multiobject_loss(G.TorchCpuOps(), t, conf, b))
+    assert l_np == pytest.approx(l_t, rel=1e-3)
+    if "masked_image_loss" in conf:
+        b2 = dict(b)
+        b2["image1_only0"] = b["image1_only0"] + 5.0 * (1.0 - np.round(b["image1_mask0"]))     # change pixels where mask < 0.5 only
+        b2["image1_mask0"] = np.round(b["image1_mask0"])
+        b1 = dict(b, image1_mask0=np.round(b["image1_mask0"]))
+        assert float(G.multiobject_loss(G.NumpyOps(), o, conf, b1)) == pytest.approx(float(G.multiobject_loss(G.NumpyOps(), o, conf, b2)), rel=1e-12)
+
+
+def test_multiview_graph_numpy_vs_torch_cpu_and_single_view_limit():
+    """Config 5's definition: backends agree; with ONE view the fusion is the identity (softmax of one logit = 1), so the
+    model reduces to the single-view appearance-flow graph."""
+    rng = np.random.default_rng(4)
+    B, H, V, Vw = 1, 32, 2, 3
+    P = G.init_params(G.multiview_param_shapes(H, V), 0)
+    im = rng.random((Vw, B, H, H, 3), dtype=np.float32)
+    d = rng.standard_normal((Vw, B, V)).astype(np.float32)
+    o = G.multiview_forward(G.NumpyOps(), P, im, d)
+    t = G.multiview_forward(G.TorchCpuOps(), P, im, d)
+    assert np.allclose(o["fused"], np.asarray(t["fused"]), rtol=1e-3, atol=1e-4)
+    assert np.allclose(o["logits"], np.asarray(t["logits"]), rtol=1e-3, atol=1e-4)
+    w = np.exp(o["logits"] - o["logits"].max(0, keepdims=True))
+    w /= w.sum(0, keepdims=True)
+    assert np.allclose(o["fused"], (w * o["gens"]).sum(0), atol=1e-6) and np.allclose(w.sum(0), 1.0)
+    one = G.multiview_forward(G.NumpyOps(), P, im[:1], d[:1])
+    single = G.appearance_flow_forward(G.NumpyOps(), {k: v for k, v in P.items() if not k.startswith("conf_field")}, im[0], d[0], "base")
+    assert np.array_equal(one["fused"], single["gen"])
