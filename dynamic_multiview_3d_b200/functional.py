@@ -109,6 +109,84 @@ def _p(t):
     return None if (t is None or t.is_meta) else t.data_ptr()
 
 
+# --- weight gradients on a side stream -----------------------------------------------------------------------
+# dgrad is the critical chain of backward; every wgrad only needs (input, dPre) and can run next to it.  The side
+# stream forks behind an event after dPre is ready and is joined before the optimizer (join_side_stream).  It has its
+# own scratch buffer, and the tensors it reads are kept alive until the join (the caching allocator does not know that
+# another stream still uses them).
+_side = {}
+_held = []
+_join_queued = [False]
+
+
+def side_stream_enabled():
+    import os
+    return os.environ.get("DMV_SIDE_WGRAD", "1") == "1" and not _meta_depth[0] and _profile[0] is None
+
+
+class side_stream:
+    """Context: run the enclosed launches on the device's side stream, ordered after everything enqueued so far on
+    the current stream.  ``keep`` are tensors the side work reads."""
+
+    def __init__(self, device, *keep):
+        key = (device.type, device.index)
+        st = _side.get(key)
+        if st is None:
+            st = _side[key] = torch.cuda.Stream(device=device)
+        self.stream, self.device = st, device
+        _held.extend(t for t in keep if t is not None)
+
+    def __enter__(self):
+        main = torch.cuda.current_stream(self.device)
+        if not _join_queued[0]:
+            # join when this backward pass ends (engine callback, as DDP does): after loss.backward() returns, every
+            # gradient is ordered on the stream that called it
+            _join_queued[0] = True
+            dev = self.device
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: _auto_join(dev, main))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        self.ctx = torch.cuda.stream(self.stream)
+        self.ctx.__enter__()
+        return self.stream
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a)
+
+
+def _auto_join(device, main):
+    _join_queued[0] = False
+    st = _side.get((device.type, device.index))
+    if st is not None:
+        main.wait_stream(st)
+    del _held[:]
+
+
+def side_workspace(nbytes, device):
+    key = ("side", device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+class _main_stream_ctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+def _wgrad_ctx(device, *keep):
+    """(context manager, workspace function) for a weight-gradient launch."""
+    if side_stream_enabled():
+        return side_stream(device, *keep), side_workspace
+    return _main_stream_ctx(), workspace
+
+
 def workspace(nbytes, device):
     """One growable scratch buffer per device (all launches are stream-ordered on one stream)."""
     key = (device.type, device.index)
@@ -188,15 +266,16 @@ class _Conv2d(torch.autograd.Function):
                 dxf = torch.empty(ctx.xshape, dtype=ctx.xdtype, device=y.device)
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
                 dx = dxf
-        pixels = B * y.shape[1] * y.shape[2]
         nws = _lib.load().dmv_wgrad_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
-        ws = workspace(nws, y.device)
-        call("dmv_conv2d_wgrad", _p(xs), ctx.xs_dt, _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None,
-             B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
-        store = wvar.store
-        if bvar is not None:
-            store.notify_grad(bvar)
-        store.notify_grad(wvar)
+        wctx, wsf = _wgrad_ctx(y.device, xs, dpre)
+        with wctx:
+            ws = wsf(nws, y.device)
+            call("dmv_conv2d_wgrad", _p(xs), ctx.xs_dt, _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None,
+                 B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, _stream(y))
+            store = wvar.store
+            if bvar is not None:
+                store.notify_grad(bvar)
+            store.notify_grad(wvar)
         return None, dx, None, None, None, None, None, None
 
 
@@ -248,12 +327,13 @@ class _Deconv2d(torch.autograd.Function):
             ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
             call("dmv_deconv2d_dgrad", _p(dps), dps_dt, _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
                  ws.numel(), algo, st)
-        pixels = B * x.shape[1] * x.shape[2]
         nws = _lib.load().dmv_wgrad_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
-        ws = workspace(nws, x.device)
-        call("dmv_deconv2d_wgrad", _p(x), _p(dps), dps_dt, _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
-             ws.numel(), algo, st)
-        wvar.store.notify_grad(wvar)
+        wctx, wsf = _wgrad_ctx(x.device, x, dps)
+        with wctx:
+            ws = wsf(nws, x.device)
+            call("dmv_deconv2d_wgrad", _p(x), _p(dps), dps_dt, _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
+                 ws.numel(), algo, _stream(x))
+            wvar.store.notify_grad(wvar)
         return None, dx, None, None, None, None, None, None
 
 
@@ -302,12 +382,14 @@ class _Linear(torch.autograd.Function):
             ws = workspace(_lib.load().dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), x.device)
             call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
-        ws = workspace(nws, x.device)
-        call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,
-             _p(ws), ws.numel(), algo, st)
-        if bvar is not None:
-            wvar.store.notify_grad(bvar)
-        wvar.store.notify_grad(wvar)
+        wctx, wsf = _wgrad_ctx(x.device, x, dpre)
+        with wctx:
+            ws = wsf(nws, x.device)
+            call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,
+                 _p(ws), ws.numel(), algo, _stream(x))
+            if bvar is not None:
+                wvar.store.notify_grad(bvar)
+            wvar.store.notify_grad(wvar)
         return None, dx, None, None, None, None
 
 
