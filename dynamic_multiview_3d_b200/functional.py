@@ -155,6 +155,15 @@ class side_stream:
         return self.ctx.__exit__(*a)
 
 
+def reset_side_stream_state():
+    """Start of a forward pass: forget a join that a failed backward pass left queued."""
+    if _join_queued[0]:
+        _join_queued[0] = False
+        for (kind, idx), st in list(_side.items()):
+            torch.cuda.current_stream(torch.device(kind, idx)).wait_stream(st)
+        del _held[:]
+
+
 def _auto_join(device, main):
     _join_queued[0] = False
     st = _side.get((device.type, device.index))

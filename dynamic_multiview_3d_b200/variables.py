@@ -55,6 +55,9 @@ class VariableStore:
         of backward; a leaf that outlives a step would tie a CUDA-graph capture to the
         (uncaptured) warm-up stream -- cudaErrorStreamCaptureIsolation."""
         self.anchor = torch.empty(1, device=self.device, requires_grad=True)
+        if self.device.type == "cuda":
+            from . import functional          # a backward pass that died mid-way never ran its side-stream join callback
+            functional.reset_side_stream_state()
         return self.anchor
 
     # -- scopes -------------------------------------------------------------------------
