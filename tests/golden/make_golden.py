@@ -8,6 +8,9 @@ rectangle fixture; nothing else reads the reference).  The GPU box only reads th
                       test_resampler.py:20-44): rectangle bounds, SHA-256 of the oracle's uint8
                       output, and the rotated rectangle's principal-axis angle
   layers.npz          oracle conv / deconv / linear outputs on seeded bf16-representable inputs
+  graphs.npz          oracle outputs of the whole model graphs at 32x32 (single-view app-flow, colour+depth,
+                      multi-object, 3-view fusion) on seeded inputs and seed-0 parameters: flow / generated images
+                      (float16-rounded to keep the file small) and the losses -- a regression pin of oracle/graph.py
 """
 import hashlib
 import os
@@ -146,7 +149,64 @@ def layer_cases():
     np.savez(os.path.join(HERE, "layers.npz"), **d)
 
 
+def graph_inputs(H=32, B=1, V=2, Vw=3):
+    """Seeded inputs shared by graph_cases() and tests/test_oracle.py::test_graph_golden_vectors."""
+    rng = np.random.default_rng(77)
+    names = ["image0", "image0_mask0", "image0_mask1", "image1", "image1_only0", "image1_only1", "image1_mask0", "image1_mask1",
+             "depth0", "depth1", "depth1_only0", "depth1_only1"]
+    mo = {n: rng.random((B, H, H, 3 if (n.startswith("image") and "mask" not in n) else 1), dtype=np.float32) for n in names}
+    mo["displacement"] = rng.standard_normal((B, V)).astype(np.float32)
+    views = rng.random((Vw, B, H, H, 3), dtype=np.float32)
+    disps = rng.standard_normal((Vw, B, V)).astype(np.float32)
+    return mo, views, disps
+
+
+GRAPH_CONFS = {
+    "colordepth": {"use_color": "", "use_depth": "", "depth_lr_factor": 0.1},
+    "multiobject": {"use_color": "", "use_depth": 0.1, "combination_image": "", "gen_sep_images": "", "predict_target_masks": 0.1,
+                    "masked_image_loss": ""},
+    "multiobject_fc": {"use_color": "", "combination_image": "", "fully_conv": ""},
+}
+
+
+def graph_outputs():
+    from oracle import graph as G
+    H, B, V = 32, 1, 2
+    mo, views, disps = graph_inputs(H, B, V)
+    ops = G.NumpyOps()
+    out = {}
+    P = G.init_params(G.appflow_param_shapes(H, V, "base"), 0)
+    o = G.appearance_flow_forward(ops, P, mo["image0"], mo["displacement"], "base")
+    out["appflow_flow"], out["appflow_gen"] = o["flow_field"], o["gen"]
+    out["appflow_loss"] = np.float64(G.appearance_flow_loss(ops, o, mo["image1"]))
+    c = GRAPH_CONFS["colordepth"]
+    P = G.init_params(G.colordepth_param_shapes(H, V, c), 0)
+    o = G.colordepth_forward(ops, P, c, mo["image0"], mo["depth0"], mo["displacement"])
+    out["colordepth_gen_image1"], out["colordepth_gen_dimage1"] = o["gen_image1"], o["gen_dimage1"]
+    out["colordepth_loss"] = np.float64(G.colordepth_loss(ops, o, c, mo["image1"], mo["depth1"]))
+    for key in ("multiobject", "multiobject_fc"):
+        c = GRAPH_CONFS[key]
+        P = G.init_params(G.multiobject_param_shapes(H, V, c), 0)
+        o = G.multiobject_forward(ops, P, c, mo)
+        for k, v in o.items():
+            out["%s_%s" % (key, k)] = v
+        out[key + "_loss"] = np.float64(G.multiobject_loss(ops, o, c, mo))
+    P = G.init_params(G.multiview_param_shapes(H, V), 0)
+    o = G.multiview_forward(ops, P, views, disps)
+    out["multiview_fused"], out["multiview_logits"] = o["fused"], o["logits"]
+    out["multiview_loss"] = np.float64(G.multiview_loss(ops, o, mo["image1"]))
+    return out
+
+
+def graph_cases():
+    out = graph_outputs()
+    np.savez_compressed(os.path.join(HERE, "graphs.npz"),
+                        **{k: (v.astype(np.float16) if getattr(v, "ndim", 0) > 0 else v) for k, v in out.items()})
+    print("graphs:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     sampler_cases()
     layer_cases()
+    graph_cases()
     rectangle_case()
