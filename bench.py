@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the appearance-flow training hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
 
 Own arm: one "step" = forward + backward + Adam of the single-view appearance-flow model on a
 synthetic 224x224 car-render batch of 64 per GPU (BASELINE configs[1]; data parallel over N
@@ -13,6 +13,9 @@ GPUs = weak scaling, configs[2] shape of work per GPU), replayed from a captured
            against MEASURED_PEAKS.json
   cpu_baseline : the oracle's torch-CPU port of the same step on the host cores (rank 0, N=1)
 Reference arm (--impl reference): that CPU port alone, on a bounded batch-8 sample.
+--config selects the BASELINE.json workload (default 2 = configs[1], the one the metric is quoted on; 3 = high-dim
+viewpoint variant, 4 = cars_colordepth RGB+depth with per-channel L1, 5 = 4 source frames + confidence fusion on the
+multi-object trunk); every one is 64 samples per GPU at 224x224, V=19, captured into one CUDA graph.
 """
 import argparse
 import json
@@ -28,6 +31,20 @@ sys.path.insert(0, ROOT)
 H, V, BATCH = 224, 19, 64
 FWD_GFLOP_PER_SAMPLE = 3.39
 METRIC = "train samples/s @224^2 appflow"
+
+
+WORKLOADS = {
+    2: ("AppearanceFlowModel", {}, "single-view appearance-flow train step (fwd+bwd+Adam), 224x224 synthetic car renders, "
+        "one-hot azimuth V=19, batch 64 per GPU (configs[1]; N>1 = batch-sharded data parallel)", "l2 (reference)"),
+    3: ("AppFlowHighDimAngle", {}, "appearance flow + offset head with the high-dim viewpoint encoding (highdim_angle.py), 224x224, "
+        "one-hot azimuth V=19, batch 64 per GPU = 512 on 8 GPUs (configs[2])", "l2 (reference)"),
+    4: ("Base_Prediction_Model", {"use_color": "", "use_depth": "", "depth_lr_factor": 0.1, "loss": "l1"},
+        "cars_colordepth: joint RGB+depth decoder (two pre-encoders, split trunk, tanh heads), per-channel L1 with weights "
+        "(1,1,1,0.1), 224x224, batch 64 per GPU (configs[3])", "l1 per channel"),
+    5: ("MultiViewFusionAppFlow", {"num_views": 4, "use_depth": 0.1},
+        "4 source frames per sample of a two-object scene on the multi-object trunk (colour, depth, 2 masks), one 3-channel "
+        "flow + confidence head per frame, softmax fusion, 224x224, 64 samples (256 frames) per GPU (configs[4])", "l2"),
+}
 
 
 def peaks():
@@ -119,20 +136,22 @@ class ClockSampler(threading.Thread):
 
 
 def reference_arm(args, rank):
-    """The reference path's CPU implementation (oracle torch-CPU port), bounded sample."""
+    """The reference path's CPU implementation (oracle torch-CPU port) of the selected config, bounded sample,
+    every host thread (oracle/cpu_step.py sets the count itself: torchrun exports OMP_NUM_THREADS=1)."""
     if rank != 0:
         return
     from oracle import cpu_step
     b = 8
     wu = max(1, min(args.warmup, 2))
-    sps, ts, cores = cpu_step.time_steps(b, H, V, steps=max(1, min(args.steps, 10)), warmup=wu)
+    sps, ts, cores = cpu_step.time_steps(b, H, V, steps=max(1, min(args.steps, 10)), warmup=wu, config=args.config)
     ms = 1e3 * sorted(ts)[len(ts) // 2]
-    sample = "batch %d of the 224^2 single-view app-flow step, fp32 fwd+bwd+Adam, torch-CPU port of the oracle graph" % b
+    what = cpu_step.make_config_step(args.config, 32, V)[2]
+    sample = "batch %d of the 224^2 step of config %d (%s), fp32 fwd+bwd+Adam, torch-CPU port of the oracle graph" % (b, args.config, what)
     line = {"impl": "reference", "metric": METRIC, "value": round(sps, 3), "unit": "samples/s", "n_gpus": args.gpus, "steps": len(ts),
             "warmup": wu, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "single-view appearance-flow train step, 224x224, one-hot azimuth V=19, batch 8 (configs[0])",
-                       "per_gpu_batch": b, "image": H, "threads": cores},
+            "config": {"workload": "CPU reference arm: " + WORKLOADS[args.config][2] + " -- timed at batch %d" % b,
+                       "bench_config": args.config, "per_gpu_batch": b, "image": H, "threads": cores},
             "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -203,7 +222,8 @@ def sampler_microbench(torch, pk, iters=20):
 
 def conv_microbench(torch, pk, iters=20):
     """The heaviest conv layer of the graph (e0_0 / d1_0: 5x5, 32->32 at 112^2, B=64: 41.1 GFLOP) through the C ABI:
-    forward, input gradient and weight gradient against the measured sustained bf16 peak (tensor-pipe roofline)."""
+    forward, input gradient and weight gradient against the measured BURST bf16 peak -- the figure that applies to a
+    kernel timed alone (20 back-to-back launches); the fraction of the sustained peak is reported beside it."""
     from dynamic_multiview_3d_b200 import _lib
     dev = torch.device("cuda", torch.cuda.current_device())
     L = _lib.load()
@@ -229,7 +249,7 @@ def conv_microbench(torch, pk, iters=20):
                                    ws.data_ptr(), ws.numel(), 0, st),
     }
     out = {"layer": "e0_0 / d1_0: conv 5x5 stride 1, 32->32, 64x112x112 (bf16 in, fp32 accumulate)", "flop_per_launch": flop,
-           "peak_tflops": pk["bf16_tflops_sustained"], "peak_src": pk["src"] + " (sustained)"}
+           "peak_tflops": pk["bf16_tflops"], "peak_src": pk["src"] + " (burst)", "peak_tflops_sustained": pk["bf16_tflops_sustained"]}
     for name, fn in calls.items():
         for _ in range(3):
             fn()
@@ -242,7 +262,8 @@ def conv_microbench(torch, pk, iters=20):
         torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / iters
         tf = flop / us / 1e6
-        out[name] = {"us": round(us, 2), "tflops": round(tf, 1), "frac": round(tf / pk["bf16_tflops_sustained"], 4)}
+        out[name] = {"us": round(us, 2), "tflops": round(tf, 1), "frac": round(tf / pk["bf16_tflops"], 4),
+                     "frac_of_sustained": round(tf / pk["bf16_tflops_sustained"], 4)}
     return out
 
 
@@ -270,6 +291,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json workload (see WORKLOADS)")
+    ap.add_argument("--loss", default=None, help="override the workload's loss mode (l1|l2)")
     ap.add_argument("--algo", default=None, help="auto|simt|tcgen05 (default: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
@@ -292,8 +315,7 @@ def main():
     import torch.distributed as dist
     import dynamic_multiview_3d_b200 as pkg
     from dynamic_multiview_3d_b200 import _lib, data_parallel, functional as F
-    from dynamic_multiview_3d_b200.synthetic import make_batch
-    from dynamic_multiview_3d_b200.train import GraphedTrainStep
+    from dynamic_multiview_3d_b200.train import GraphedTrainStep, synthetic_batch
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
     torch.cuda.set_device(local)
@@ -304,41 +326,46 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
+    cls_name, extra, workload, loss_name = WORKLOADS[args.config]
     conf = {"batch_size": BATCH, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "loss": "l2", "seed": 0}
+    conf.update(extra)
+    if args.loss:
+        conf["loss"] = args.loss
+        loss_name = args.loss
     if args.algo:
         conf["algo"] = args.algo
-    model = pkg.AppearanceFlowModel(conf)
+    Model = getattr(pkg, cls_name)
+    model = Model(conf)
     # N > 1: sharded data parallelism.  N == 1: the same chunk pipeline without the exchange -- Adam runs chunk by chunk on a
     # side stream as soon as a chunk's gradients are complete, so the HBM-bound update overlaps the rest of backward.
     if world > 1 or os.environ.get("DMV_OVERLAP_ADAM", "1") == "1":
         data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128" if world > 1 else "32")))
-    b = make_batch(BATCH, H, "onehot19", seed=1234, rank=rank)
+    b = synthetic_batch(model, seed=1234, rank=rank)
     # The host batch is held in the reference's storage format: uint8 pixels (read_tf_records.py:104-111, images are
     # tf.decode_raw(..., tf.uint8) / 255).  The same quantised images, converted on the device, are the HBM-resident batch.
     u8 = not args.eager and os.environ.get("DMV_BENCH_F32_INPUT", "0") != "1"
-    if u8:
-        import numpy as np
-        host = {k: torch.from_numpy(np.clip(np.rint(b[k] * 255.0), 0, 255).astype(np.uint8)).pin_memory() for k in ("image0", "image1")}
-        host["disp"] = torch.from_numpy(b["disp"]).pin_memory()
-        devb = {"disp": host["disp"].to(dev)}
-        for k in ("image0", "image1"):
+    import numpy as np
+    host, devb = {}, {}
+    for k, v in b.items():
+        if u8 and v.ndim >= 4:
+            host[k] = torch.from_numpy(np.clip(np.rint(v * 255.0), 0, 255).astype(np.uint8)).pin_memory()
             t8 = host[k].to(dev)
             devb[k] = torch.empty(t8.shape, dtype=torch.float32, device=dev)
             _lib.call("dmv_u8_to_f32", t8.data_ptr(), devb[k].data_ptr(), t8.numel(), 255.0, torch.cuda.current_stream().cuda_stream)
-    else:
-        host = {k: torch.from_numpy(b[k]).pin_memory() for k in ("image0", "image1", "disp")}
-        devb = {k: v.to(dev) for k, v in host.items()}
+        else:
+            host[k] = torch.from_numpy(v).pin_memory()
+            devb[k] = host[k].to(dev)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     if args.eager:
-        def step_fn(i0, i1, d):
-            return model.train_step(i0.to(dev, non_blocking=True), i1.to(dev, non_blocking=True), d.to(dev, non_blocking=True))
+        def step_fn(batch):
+            return model.train_step({k: v.to(dev, non_blocking=True) for k, v in batch.items()})
         n0 = _lib.launch_count()
-        step_fn(devb["image0"], devb["image1"], devb["disp"])
+        step_fn(devb)
         launches = _lib.launch_count() - n0
     else:
         step = GraphedTrainStep(model, warmup=2)
-        step(devb["image0"], devb["image1"], devb["disp"])
+        step(devb)
         step_fn = step
         launches = step.launches_per_step
 
@@ -348,9 +375,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing: the batch sits in the captured step's static input buffers
-    resident = (lambda: step.replay()) if not args.eager else (lambda: step_fn(devb["image0"], devb["image1"], devb["disp"]))
+    resident = (lambda: step.replay()) if not args.eager else (lambda: step_fn(devb))
     for _ in range(W):
-        step_fn(devb["image0"], devb["image1"], devb["disp"])
+        step_fn(devb)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
@@ -372,14 +399,14 @@ def main():
     # step k+1 is issued on a copy stream before step k is replayed (GraphedTrainStep.prefetch), so PCIe overlaps compute;
     # step 0's copy is not hidden.  K copies and K loss reads lie inside the timed region.
     pipelined = not args.eager
-    hb = (host["image0"], host["image1"], host["disp"])
+    hb = host
     if pipelined:
-        step.prefetch(*hb)
+        step.prefetch(hb)
     for k in range(K):
         if pipelined:
             loss = step(staged=True, prefetch_next=hb if k + 1 < K else None)
         else:
-            loss = step_fn(*hb)
+            loss = step_fn(hb)
         last = float(loss)                       # D2H read of the step's result
     ee1.record()
     barrier()
@@ -405,11 +432,11 @@ def main():
         try:
             # a second, un-pipelined model: every call runs alone on the current stream, so its CUDA-event time is the
             # kernel's own duration (the timed model overlaps Adam chunks with backward on a side stream)
-            pmodel = pkg.AppearanceFlowModel(conf)
+            pmodel = Model(conf)
             for _ in range(2):
-                pmodel.train_step(devb["image0"], devb["image1"], devb["disp"])
+                pmodel.train_step(devb)
             with F.profile_calls() as prof:
-                pmodel.train_step(devb["image0"], devb["image1"], devb["disp"])
+                pmodel.train_step(devb)
             agg = {}
             for name, tag, t_ms in prof.records:
                 agg[(name, tag)] = agg.get((name, tag), 0.0) + t_ms
@@ -417,7 +444,7 @@ def main():
             ranked = sorted(agg.items(), key=lambda kv: -kv[1])
             top = [{"call": k[0], "var": k[1], "ms": round(v, 4), "share": round(v / total, 4)} for k, v in ranked[:8]]
             (dname, dtag), dms = ranked[0]
-            gf = layer_gflop(BATCH)
+            gf = layer_gflop(BATCH) if args.config in (2, 3) else {}
             lname = dtag.split("/")[0]
             if lname in gf:
                 tf = gf[lname] / dms          # GFLOP / ms == TFLOP/s
@@ -426,15 +453,19 @@ def main():
                         "unit": "TFLOP/s", "frac": round(tf / peak, 5), "traffic": None, "peak_src": pk["src"] + " (sustained)",
                         "flops_per_launch": gf[lname] * 1e9, "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
             elif dtag == "adam":
-                nbytes = 30.0 * pmodel.store.total      # read theta, g, m, v (16 B) + write theta, m, v (12 B) + bf16 copy (2 B)
+                # 28 B/param (read theta, g, m, v; write theta, m, v).  The kernel also writes the bf16 compute
+                # copy (2 B/param), reported separately as bytes_moved_per_launch; `achieved` uses the 8(d) figure.
+                nbytes = 28.0 * pmodel.store.total
                 gbs = nbytes / (dms * 1e-3) / 1e9
                 roof = {"bound": "hbm", "kernel": "dmv_adam_multi", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": ncu_traffic("adam_multi_kernel"), "peak_src": pk["src"],
-                        "bytes_per_launch": nbytes,
+                        "bytes_per_launch": nbytes, "bytes_moved_per_launch": 30.0 * pmodel.store.total,
                         "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
         except Exception as ex:      # the profile is explanatory; never lose the bench line over it
             roof = {"error": repr(ex)[:200]}
     micro = None
+    if args.config != 2:
+        args.no_micro = True          # the standalone sampler / conv microbenchmarks belong to the headline config's line
     if not args.no_micro:
         try:
             micro = sampler_microbench(torch, pk)
@@ -453,17 +484,16 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_step
-        sps, ts, cores = cpu_step.time_steps(8, H, V, steps=3, warmup=1)
+        sps, ts, cores = cpu_step.time_steps(8, H, V, steps=3, warmup=1, config=args.config)
         cpu = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "batch 8 of the same 224^2 step (configs[0]): fp32 fwd+bwd+Adam, torch-CPU port of the oracle graph, 3 timed steps"}
+               "sample": "batch 8 of the same 224^2 step (config %d): fp32 fwd+bwd+Adam, torch-CPU port of the oracle graph, 3 timed steps" % args.config}
 
-    step_tflops = 3 * FWD_GFLOP_PER_SAMPLE * BATCH / ms       # GFLOP/ms = TFLOP/s per GPU
+    step_tflops = 3 * FWD_GFLOP_PER_SAMPLE * BATCH / ms if args.config in (2, 3) else None     # GFLOP/ms = TFLOP/s per GPU
     line = {"metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "single-view appearance-flow train step (fwd+bwd+Adam), 224x224 synthetic car renders, "
-                                   "one-hot azimuth V=19, batch 64 per GPU (configs[1]; N>1 = batch-sharded data parallel)",
-                       "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": H, "loss": "l2 (reference)",
+            "config": {"workload": workload, "bench_config": args.config, "model_class": cls_name,
+                       "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": H, "loss": loss_name,
                        "parallelism": "dp%d" % world, "cuda_graph": not args.eager,
                        "host_input": "uint8 pixels (reference TFRecord format), /255 on the device" if u8 else "float32", "algo": args.algo or F.get_default_algo(),
                        "l2_policy": "per-step working set (parameters, Adam state, activations: several GB) >> 126 MB L2"},
@@ -471,7 +501,7 @@ def main():
                     "ms_per_step": round(ms_e2e, 4)},
             "gpu_launches": int(launches * K), "launches_per_step": int(launches),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sampler": micro, "conv": conv, "top_kernels": top,
-            "step_tflops_per_gpu": round(step_tflops, 2), "final_loss": last}
+            "step_tflops_per_gpu": round(step_tflops, 2) if step_tflops else None, "final_loss": last}
     emit(line)
     finish(world, rank)
     return 0

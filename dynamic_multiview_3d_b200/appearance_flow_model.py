@@ -22,13 +22,15 @@ import os
 import torch
 
 from . import functional as F
+from .model_base import ModelBase
 from .optimizer import TFAdam
 from .tf_utils import conv2d_msra, coords, deconv2d_msra, flow_resample_layer, linear_msra, warp_pts_layer
 from .variables import VariableStore, use_store
 
 
-class AppearanceFlowModel(object):
+class AppearanceFlowModel(ModelBase):
     ACT = "lrelu"
+    INPUT_KEYS = ("image0", "image1", "disp")
 
     def __init__(self, conf, load_tfrec=True, build_loss=True, device=None):
         self.conf = conf
@@ -67,6 +69,10 @@ class AppearanceFlowModel(object):
         B = self.batch_size
         return (torch.zeros([B] + self.image_shape, dtype=torch.float32, device=self.device),
                 torch.zeros([B, self.viewpoint_dim], dtype=torch.float32, device=self.device))
+
+    def input_spec(self):
+        B = self.batch_size
+        return {"image0": tuple([B] + self.image_shape), "image1": tuple([B] + self.image_shape), "disp": (B, self.viewpoint_dim)}
 
     # dead variables of the high-dim viewpoint encoder receive no gradient (TF skips None grads)
     def _trainable(self, name):
@@ -166,44 +172,14 @@ class AppearanceFlowModel(object):
                                                    grid_order=self.grid_order, unit_upstream=True)
         return self.loss
 
-    def train_step(self, image0, image1, disp):
-        """One sess.run([loss, train_op]) of train.py:122: forward, backward, Adam."""
-        loss = self.forward_and_loss(image0, image1, disp)
-        loss.backward()
-        if self.store.grad_ready_hook is not None and hasattr(self, "_dp"):
-            self._dp.finish()
-        self.optimizer.step()
-        return loss.detach()
+    def step_loss(self, batch):
+        return self.forward_and_loss(batch["image0"], batch["image1"], batch["disp"])
 
     def visualize(self, image0, image1, disp, iter_num=None):
         """appearance_flow_model.py:132-179: output / ground-truth / input grids, the flow image and the
         correspondence probes (visualize.py).  The TF session argument becomes the batch itself."""
         from .visualize import visualize
         return visualize(self, image0, image1, disp, iter_num)
-
-    # -- checkpoint surface (tf.train.Saver over global variables, train.py:70-71) -----------
-    def state_dict(self):
-        if hasattr(self, "_dp") and hasattr(self._dp, "gather_full_state"):
-            self._dp.gather_full_state()        # sharded data parallelism: masters and moments live with their owners
-        sd = self.store.state_dict()
-        if self.optimizer is not None:
-            for k, v in self.store.vars.items():
-                if v.trainable:
-                    sd[k + "/Adam"] = v.m.detach().cpu().clone()
-                    sd[k + "/Adam_1"] = v.v.detach().cpu().clone()
-            sd["__adam_state__"] = self.optimizer.state.detach().cpu().clone()
-        return sd
-
-    def load_state_dict(self, sd):
-        params = {k: v for k, v in sd.items() if k in self.store.vars}
-        self.store.load_state_dict(params)
-        if self.optimizer is not None:
-            for k, v in self.store.vars.items():
-                if k + "/Adam" in sd:
-                    v.m.copy_(sd[k + "/Adam"].to(self.device))
-                    v.v.copy_(sd[k + "/Adam_1"].to(self.device))
-            if "__adam_state__" in sd:
-                self.optimizer.state.copy_(sd["__adam_state__"].to(self.device))
 
 
 class AppFlowHighDimAngle(AppearanceFlowModel):

@@ -16,12 +16,15 @@ grid_order, algo, seed.  The reference ignores conf['batch_size'] (main_model.py
 import torch
 
 from . import functional as F
+from .model_base import ModelBase
 from .optimizer import TFAdam
 from .tf_utils import conv2d_msra, deconv2d_msra, flow_resample_layer, linear_msra
 from .variables import VariableStore, use_store
 
 
-class Base_Prediction_Model(object):
+class Base_Prediction_Model(ModelBase):
+    INPUT_KEYS = ("image0", "depth0", "image1", "depth1", "disp")      # train_step(image0, dimage0, image1, dimage1, disp)
+
     def __init__(self, conf, load_tfrec=True, build_loss=True, device=None):
         self.conf = conf
         self.batch_size = int(conf.get("batch_size", 64))
@@ -149,11 +152,11 @@ class Base_Prediction_Model(object):
         self.image1, self.dimage1, self.loss = image1, dimage1, loss
         return loss
 
-    def train_step(self, image0, dimage0, image1, dimage1, disp):
-        self.forward(image0, dimage0, disp)
-        loss = self.build_loss(image1, dimage1)
-        loss.backward()
-        if hasattr(self, "_dp"):
-            self._dp.finish()
-        self.optimizer.step()
-        return loss.detach()
+    def input_spec(self):
+        B, H = self.batch_size, self.image_shape[0]
+        return {"image0": (B, H, H, 3), "depth0": (B, H, H, 1), "image1": (B, H, H, 3), "depth1": (B, H, H, 1),
+                "disp": (B, self.viewpoint_dim)}
+
+    def step_loss(self, batch):
+        self.forward(batch["image0"], batch["depth0"], batch["disp"])
+        return self.build_loss(batch["image1"], batch["depth1"])

@@ -8,16 +8,19 @@ all sample ``image0`` (:89-102, 193-198), tanh decoders for depth and masks (:10
 (euclidean terms, ``masked_image_loss``, ``use_depth`` / ``predict_target_masks`` factors).  Feature switches are
 key-presence tests on ``conf`` as in the reference.
 
-``MultiViewFusionAppFlow`` is BASELINE config 5, which the reference does not contain: every one of
-``num_views`` source frames runs the single-view appearance-flow network (shared weights, its own viewpoint change to
-the target), emitting a flow and a per-pixel confidence logit (head ``conf_field`` next to ``flow_field``); the
-prediction is  sum_v softmax_v(logit)_v * warp(src_v, flow_v)  (after Zhou et al. 2016), and the fusion, the loss and
-both gradients are one fused kernel (dmv_loss_fused_fwd_bwd).  The views are a batch dimension for every layer.
+``MultiViewFusionAppFlow`` is BASELINE config 5, which the reference does not contain (definition
+8(f)-3): ``num_views`` source frames of a multi-object scene per sample.  Every source frame runs the MULTI-OBJECT trunk
+above (its colour image, its depth map when ``use_depth`` is set, its two object masks -- the pre-encoders of
+multiobject_appflow.py:123-134 -- and its own viewpoint change to the target; shared weights), and ONE decoder
+(``dec_image1``) ends in a single 3-channel head ``d0``: channels 0-1 are the flow that warps that frame's colour image,
+channel 2 is its per-pixel confidence logit.  The prediction is  sum_v softmax_v(logit)_v * warp(src_v, flow_v)  (after
+Zhou et al. 2016); the fusion, the loss and both gradients are one fused kernel (dmv_loss_fused_fwd_bwd).  The views are
+a batch dimension for every layer.
 """
 import torch
 
 from . import functional as F
-from .appearance_flow_model import AppearanceFlowModel
+from .model_base import ModelBase
 from .optimizer import TFAdam
 from .tf_utils import conv2d_msra, deconv2d_msra, flow_resample_layer, linear_msra
 from .variables import VariableStore, use_store
@@ -46,7 +49,9 @@ def decoder_heads(conf):
     return heads
 
 
-class MultiObjectAppFlow(object):
+class MultiObjectAppFlow(ModelBase):
+    INPUT_KEYS = tuple(BATCH_KEYS)
+
     def __init__(self, conf, load_tfrec=True, build_loss=True, device=None):
         self.conf = conf
         self.batch_size = int(conf["batch_size"])
@@ -59,7 +64,7 @@ class MultiObjectAppFlow(object):
         self.grid_order = conf.get("grid_order", "ref_yx")
         self.algo = conf.get("algo", None)
         self.max_iter, self.start_iter = 1000000, 0
-        self.heads = decoder_heads(conf)
+        self.heads = self._heads(conf)
         if not self.heads:
             raise ValueError("conf selects no decoder output")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -67,10 +72,7 @@ class MultiObjectAppFlow(object):
         self.world_size = 1
         self.loss = None
         self.optimizer = None
-        B = self.batch_size
-        zeros = {k: torch.zeros((B, H, H, 3 if (k.startswith("image") and "mask" not in k) else 1), dtype=torch.float32, device=self.device)
-                 for k in BATCH_KEYS if k != "displacement"}
-        zeros["displacement"] = torch.zeros((B, self.viewpoint_dim), dtype=torch.float32, device=self.device)
+        zeros = {k: torch.zeros(shp, dtype=torch.float32, device=self.device) for k, shp in self.input_spec().items()}
         if self.device.type == "meta":
             with torch.no_grad(), F.meta_mode():
                 self.forward(zeros)
@@ -81,6 +83,19 @@ class MultiObjectAppFlow(object):
         self.t_vars = self.store.trainable_vars()
         if build_loss and self.device.type != "meta":
             self.optimizer = TFAdam(self.store, conf["learning_rate"])
+
+    def _heads(self, conf):
+        return decoder_heads(conf)
+
+    def input_spec(self):
+        B, H = self.batch_size, self.image_shape[0]
+        spec = {k: (B, H, H, 3 if (k.startswith("image") and "mask" not in k) else 1) for k in BATCH_KEYS if k != "displacement"}
+        spec["displacement"] = (B, self.viewpoint_dim)
+        return spec
+
+    def step_loss(self, batch):
+        self.forward(batch)
+        return self.build_loss(batch)
 
     # -- graph ---------------------------------------------------------------------------------
     def image_preprocessing(self, x, scope):
@@ -153,7 +168,12 @@ class MultiObjectAppFlow(object):
         out = {}
         for attr, scope, kind in self.heads:
             x = split_list.pop()
-            out[attr] = self.decode_flow(batch["image0"], x, scope) if kind == "flow" else self.decode_direct(x, scope)
+            if kind == "flow":
+                out[attr] = self.decode_flow(batch["image0"], x, scope)
+            elif kind == "flowconf":
+                out[attr] = self.decode_flowconf(batch["image0"], x, scope)
+            else:
+                out[attr] = self.decode_direct(x, scope)
         assert split_list == []
         return out
 
@@ -204,55 +224,65 @@ class MultiObjectAppFlow(object):
         self.loss = loss
         return loss
 
-    def train_step(self, batch):
-        self.forward(batch)
-        loss = self.build_loss(batch)
-        loss.backward()
-        if hasattr(self, "_dp"):
-            self._dp.finish()
-        self.optimizer.step()
-        return loss.detach()
 
-    def state_dict(self):
-        return self.store.state_dict()
-
-    def load_state_dict(self, sd):
-        self.store.load_state_dict({k: v for k, v in sd.items() if k in self.store.vars})
-
-
-class MultiViewFusionAppFlow(AppearanceFlowModel):
-    """BASELINE config 5: ``num_views`` source frames per sample, per-view flow + confidence, softmax fusion."""
+class MultiViewFusionAppFlow(MultiObjectAppFlow):
+    """BASELINE config 5: ``num_views`` source frames per sample on the multi-object trunk, one 3-channel
+    flow + confidence head per frame, softmax fusion (module docstring)."""
+    SRC_KEYS = ("image0", "depth0", "image0_mask0", "image0_mask1")
 
     def __init__(self, conf, load_tfrec=True, build_loss=True, device=None):
         self.num_views = int(conf.get("num_views", 4))
-        self.gens = self.logits = self.fused = None
+        self.loss_mode = conf.get("loss", "l2")
+        self.gens = self.logits = self.fused = self.flow_field = None
+        conf = dict(conf)
+        conf.setdefault("use_color", "")
         super().__init__(conf, load_tfrec, build_loss, device)
 
-    def _zeros_for_build(self):
-        B, Vw = self.batch_size, self.num_views
-        return (torch.zeros([Vw, B] + self.image_shape, dtype=torch.float32, device=self.device),
-                torch.zeros([Vw, B, self.viewpoint_dim], dtype=torch.float32, device=self.device))
+    def _heads(self, conf):
+        return [("gen_image1", "dec_image1", "flowconf")]
 
-    def forward(self, images0, disps, keep=None):
-        """images0 [Vw,B,H,H,3] fp32 in [0,1], disps [Vw,B,V] -> dict(flow_field [Vw,B,H,H,2], gens, logits)."""
-        self.flow_field = self.gen = self.loss = self.gens = self.logits = self.fused = None
+    @property
+    def INPUT_KEYS(self):
+        return tuple(k for k in self.SRC_KEYS if k != "depth0" or "use_depth" in self.conf) + ("displacement", "image1")
+
+    def input_spec(self):
+        B, H, Vw = self.batch_size, self.image_shape[0], self.num_views
+        spec = {"image0": (Vw, B, H, H, 3)}
+        if "use_depth" in self.conf:
+            spec["depth0"] = (Vw, B, H, H, 1)
+        spec.update(image0_mask0=(Vw, B, H, H, 1), image0_mask1=(Vw, B, H, H, 1), displacement=(Vw, B, self.viewpoint_dim),
+                    image1=(B, H, H, 3))
+        return spec
+
+    def decode_flowconf(self, src_img, x, scope):
+        """One 3-channel head: flow (channels 0-1) + confidence logit (channel 2), SURVEY 8(f)-3."""
+        B, H = x.shape[0], self.image_shape[0]
+        with self.store.scope(scope):
+            d1_0 = self._decode_trunk(x)
+            head = deconv2d_msra(d1_0, [B, H, H, 3], 5, 5, 2, 2, "d0", act=None, algo=self.algo, out_dtype=torch.float32)
+        flow, logit = head[..., :2].contiguous(), head[..., 2].contiguous()
+        return flow_resample_layer(src_img, flow, self.grid_order), flow, logit
+
+    def forward(self, batch):
+        """batch: image0 [Vw,B,H,H,3], (depth0,) image0_mask0/1 [Vw,B,H,H,1], displacement [Vw,B,V] (each frame's
+        viewpoint change to the target), image1 [B,H,H,3] -> dict(flow_field [Vw,B,H,H,2], gens, logits)."""
+        self.loss = self.gens = self.logits = self.fused = self.flow_field = None
         self.store.new_anchor()
-        Vw, B, H = images0.shape[0], images0.shape[1], images0.shape[2]
-        flat = images0.reshape(Vw * B, H, H, 3)
-        self.image0, self.disp = images0, disps
+        self.batch = batch
+        Vw, B, H = batch["image0"].shape[0], batch["image0"].shape[1], batch["image0"].shape[2]
+        flat = {k: batch[k].reshape((Vw * B,) + tuple(batch[k].shape[2:])) for k in self.SRC_KEYS + ("displacement",) if k in batch}
         with use_store(self.store):
-            flow = self.buildModel(flat, F.to_bf16(disps.reshape(Vw * B, -1)))
-            logit = deconv2d_msra(self._last_decoder, [Vw * B, H, H, 1], 5, 5, 2, 2, "conf_field", act=None, algo=self.algo,
-                                  out_dtype=torch.float32)
-            gen = flow_resample_layer(flat, flow, self.grid_order)
+            out = self.buildModel(flat)
+        gen, flow, logit = out["gen_image1"]
         self.flow_field = flow.reshape(Vw, B, H, H, 2)
         self.gens = gen.reshape(Vw, B, H, H, 3)
         self.logits = logit.reshape(Vw, B, H, H)
-        return {"flow_field": self.flow_field, "gens": self.gens, "logits": self.logits}
+        self.out = {"flow_field": self.flow_field, "gens": self.gens, "logits": self.logits}
+        return self.out
 
-    def build_loss(self, image1):
-        self.image1 = image1
+    def build_loss(self, batch=None):
+        image1 = (batch or self.batch)["image1"]
         n = image1.shape[0] * image1.shape[1] * image1.shape[2] * self.world_size
         self.loss, self.fused = F.fused_views_loss(self.gens, self.logits, image1, self.loss_mode, inv_count=1.0 / n)
-        self.gen = self.fused
+        self.gen_image1 = self.fused
         return self.loss

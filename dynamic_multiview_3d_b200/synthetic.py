@@ -98,3 +98,43 @@ def make_multiobject_batch(batch, size=128, seed=1234, rank=0):
         out[k] = np.clip(out[k] + rng.normal(0, 0.02, out[k].shape).astype(np.float32), 0, 1)
     out["displacement"] = disp
     return out
+
+
+def make_multiview_multiobject_batch(batch, size=224, views=4, seed=1234, rank=0, viewpoint="disp2"):
+    """BASELINE config 5 inputs: ``views`` source frames of a two-object scene per sample, each with its
+    object masks and depth map (tensor names of read_tf_records_multobj.py:65-80, leading axis = source frame), the
+    viewpoint change of every frame to the target (``displacement`` [views, B, V]) and the target render ``image1``."""
+    rng = np.random.default_rng(seed + rank)
+    H = W = size
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    Vd = 19 if viewpoint == "onehot19" else 2
+    out = {"image0": np.full((views, batch, H, W, 3), 0.5, np.float32), "depth0": np.ones((views, batch, H, W, 1), np.float32),
+           "image0_mask0": np.zeros((views, batch, H, W, 1), np.float32), "image0_mask1": np.zeros((views, batch, H, W, 1), np.float32),
+           "displacement": np.zeros((views, batch, Vd), np.float32), "image1": np.full((batch, H, W, 3), 0.5, np.float32)}
+
+    def ell(cx, cy, yaw, a, b):
+        c, s = np.cos(yaw), np.sin(yaw)
+        u = ((xx - cx) * c + (yy - cy) * s) / a
+        v = (-(xx - cx) * s + (yy - cy) * c) / b
+        return (u * u + v * v) <= 1.0
+
+    for n in range(batch):
+        bins = rng.integers(1, 5, size=views)                     # each frame 20..80 degrees away from the target
+        objs = [(rng.uniform(0.1, 0.9, size=3).astype(np.float32), rng.uniform(0.3, 0.7) * W, rng.uniform(0.3, 0.7) * H,
+                 rng.uniform(0, np.pi), rng.uniform(0.3, 0.6)) for _ in range(2)]
+        for ob, (col, cx, cy, yaw, dval) in enumerate(objs):
+            out["image1"][n][ell(cx, cy, yaw, 0.18 * W, 0.09 * H)] = col
+        for v in range(views):
+            daz = np.deg2rad(20.0 * bins[v]) * (1 if v % 2 == 0 else -1)
+            if viewpoint == "onehot19":
+                out["displacement"][v, n, (bins[v] * (1 if v % 2 == 0 else -1)) % 19] = 1.0
+            else:
+                out["displacement"][v, n] = (0.0, daz)
+            for ob, (col, cx, cy, yaw, dval) in enumerate(objs):
+                m = ell(cx, cy, yaw - daz, 0.18 * W, 0.09 * H)
+                out["image0"][v, n][m] = col
+                out["image0_mask%d" % ob][v, n][m] = 1.0
+                out["depth0"][v, n][m] = dval
+    for k in ("image0", "image1"):
+        out[k] = np.clip(out[k] + rng.normal(0, 0.02, out[k].shape).astype(np.float32), 0, 1)
+    return out

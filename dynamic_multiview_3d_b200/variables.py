@@ -47,6 +47,7 @@ class VariableStore:
         # dummy differentiable leaf: keeps the autograd tape alive for layers whose only
         # differentiable inputs are parameters (gradients of parameters bypass autograd)
         self.anchor = None
+        self._pass_uses = set()
         self.new_anchor()
 
     def new_anchor(self):
@@ -55,6 +56,7 @@ class VariableStore:
         of backward; a leaf that outlives a step would tie a CUDA-graph capture to the
         (uncaptured) warm-up stream -- cudaErrorStreamCaptureIsolation."""
         self.anchor = torch.empty(1, device=self.device, requires_grad=True)
+        self._pass_uses = set()
         if self.device.type == "cuda":
             from . import functional          # a backward pass that died mid-way never ran its side-stream join callback
             functional.reset_side_stream_state()
@@ -79,6 +81,13 @@ class VariableStore:
         if v is not None:
             if tuple(shape) != v.shape:
                 raise ValueError("variable %s exists with shape %s, requested %s" % (full, v.shape, tuple(shape)))
+            # the weight-gradient kernels OVERWRITE the variable's slot of the flat gradient buffer and report it to
+            # the data-parallel hook once: a second use of a name within one forward pass (TF-style reuse) would keep
+            # only the last use's gradient -- refuse it instead of training on a wrong gradient
+            if full in self._pass_uses:
+                raise RuntimeError("variable %s is used twice in one forward pass; weight sharing across calls is not "
+                                   "supported (fold the shared applications into the batch dimension)" % full)
+            self._pass_uses.add(full)
             v.used = True
             return v
         if self.finalized:
@@ -90,6 +99,7 @@ class VariableStore:
             v.grad = torch.empty(shape, dtype=torch.float32, device="meta")
             v.half = torch.empty(shape, dtype=torch.bfloat16, device="meta")
             self.vars[full] = v
+            self._pass_uses.add(full)
             return v
         if init == "zeros":
             t = torch.zeros(shape, dtype=torch.float32)
@@ -112,6 +122,7 @@ class VariableStore:
         v.half = torch.empty(shape, dtype=torch.bfloat16, device=self.device)
         self._cast(v.master, v.half, v.numel)
         self.vars[full] = v
+        self._pass_uses.add(full)
         return v
 
     def _cast(self, src, dst, n):

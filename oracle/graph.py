@@ -210,6 +210,75 @@ class TorchCpuOps:
         return self.t.softmax(logits, dim=0)
 
 
+def _bf16_round_fns(torch):
+    """(round_fwd, round_bwd, round_both): straight-through bf16 rounding points for Bf16TorchCpuOps."""
+    def r(x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    class RoundF(torch.autograd.Function):       # value is stored as bf16; gradient passes untouched
+        @staticmethod
+        def forward(ctx, x):
+            return r(x)
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    class RoundB(torch.autograd.Function):       # value untouched; the gradient arriving here is stored as bf16
+        @staticmethod
+        def forward(ctx, x):
+            return x.view_as(x)
+
+        @staticmethod
+        def backward(ctx, g):
+            return r(g)
+
+    class RoundFB(torch.autograd.Function):      # both the value and its gradient are stored as bf16
+        @staticmethod
+        def forward(ctx, x):
+            return r(x)
+
+        @staticmethod
+        def backward(ctx, g):
+            return r(g)
+
+    return RoundF.apply, RoundB.apply, RoundFB.apply
+
+
+class Bf16TorchCpuOps(TorchCpuOps):
+    """The torch-CPU backend with bf16 rounding exactly where the CUDA path STORES bf16, fp32
+    arithmetic everywhere else -- so that a comparison against it isolates kernel error from the quantisation that the
+    bf16 data layout itself introduces (against the plain fp32 backends the two are mixed).  Rounding points:
+      * the bf16 compute copy of every conv / deconv / FC weight (biases stay fp32 masters);
+      * the input of every conv / deconv / FC (network inputs are cast: thin_s2d_prep, dmv_cast_f32_to_bf16; hidden
+        activations are already bf16, the rounding is idempotent);
+      * the output of every lrelu / relu epilogue (stored bf16); tanh / linear heads write fp32 and are NOT rounded;
+      * backward: the gradient arriving at a bf16 activation (the next layer's dX is written as bf16) and the gradient
+        leaving the activation derivative (dPre = dY * act'(Y) is written as bf16: dmv_act_bwd_bias / dmv_act_bwd,
+        and thin_s2d_prep for the fp32 heads) -- both dgrad and wgrad consume that rounded dPre.
+    Weight gradients, the sampler, the losses and Adam are fp32 on both sides."""
+    name = "torch-cpu"
+
+    def __init__(self):
+        super().__init__()
+        self.rf, self.rb, self.rfb = _bf16_round_fns(self.t)
+
+    def conv(self, x, w, b, s):
+        return self.rb(super().conv(self.rf(x), self.rf(w), b, s))
+
+    def deconv(self, x, w, out_shape, s):
+        return self.rb(super().deconv(self.rf(x), self.rf(w), out_shape, s))
+
+    def linear(self, x, m, b):
+        return self.rb(super().linear(self.rf(x), self.rf(m), b))
+
+    def lrelu(self, x):
+        return self.rfb(super().lrelu(x))
+
+    def relu(self, x):
+        return self.rfb(super().relu(x))
+
+
 # --------------------------------------------------------------------------- #
 # parameter shapes (TF variable names) -- shared by oracle users
 # --------------------------------------------------------------------------- #
@@ -308,7 +377,7 @@ def _decode_angle(ops, P, disp, kind):
     raise ValueError(kind)
 
 
-def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False, extra_heads=None):
+def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False):
     """appearance_flow_model.py:83-127 (kind base/highdim/lowdim) or
     appearance_flow_tinghui.py:13-46 (kind tinghui).  image0 NHWC [B,H,H,3], disp [B,V].
     Returns dict with flow_field, warp_pts, gen (NHWC) and, if keep, every activation."""
@@ -362,13 +431,9 @@ def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False, 
         d = D("d2", d, 8 * h5, 32); d = C("d2_0", d, 1)
         d = D("d1", d, 16 * h5, 32); d = C("d1_0", d, 1)
         flow = D("flow_field", d, H, 2, 2, None)
-        # further linear heads on the last decoder activation (config 5's confidence logit)
-        extra = {n: ops.nhwc(ops.deconv(d, P[n + "/w"], (B, H, H, c), 2)) for n, c in (extra_heads or [])}
     warp = ops.warp_pts(flow)
     gen = ops.resample(x, warp)
     out = {"flow_field": ops.nhwc(flow), "warp_pts": warp, "gen": ops.nhwc(gen)}
-    if extra_heads:
-        out["heads"] = extra
     if keep:
         out["acts"] = {k: (ops.nhwc(v) if getattr(v, "ndim", 0) == 4 else v) for k, v in acts.items()}
     return out
@@ -602,26 +667,53 @@ def multiobject_loss(ops, out, conf, batch):
 
 
 # --- config 5 : multi-view appearance flow with confidence fusion (NOT in the reference) ---------- #
-def multiview_param_shapes(H, V):
-    """The single-view graph (appearance_flow_model.py:83-127) plus a 1-channel confidence head `conf_field`
-    next to `flow_field`; the same weights serve every source view."""
-    s = appflow_param_shapes(H, V, "base")
-    _deconv(s, "conf_field", 5, 1, 32)
+_MV_CONF_KEYS = ("use_color", "use_depth", "fully_conv")
+
+
+def _mv_conf(conf):
+    c = {k: conf[k] for k in _MV_CONF_KEYS if k in conf}
+    c.setdefault("use_color", "")
+    return c
+
+
+def multiview_param_shapes(H, V, conf=None):
+    """SURVEY 8(f)-3 on the multi-object trunk (multiobject_appflow.py:123-187): the pre-encoders of the inputs the conf
+    selects (colour, depth, the two object masks), the shared trunk, ONE decoder `dec_image1` whose last layer `d0` has 3
+    channels (flow x, flow y, confidence logit).  The same weights serve every source frame."""
+    conf = _mv_conf(conf or {})
+    s = {}
+    n_in = 0
+    for key, _, scope, cin in _MO_INPUTS:
+        if key is None or key in conf:
+            _pre_encoder_shapes(s, scope, cin); n_in += 1
+    _trunk_shapes(s, H, V, n_in, 1, fully_conv="fully_conv" in conf)
+    _decoder_shapes(s, "dec_image1", 3)
     return s
 
 
-def multiview_forward(ops, params, images0, disps):
-    """images0 [Vw,B,H,H,3] source views, disps [Vw,B,V] their viewpoint change to the target.  Every view runs
-    the single-view network (shared weights); view v yields gen_v = warp(src_v, flow_v) and a confidence logit;
+def multiview_forward(ops, params, conf, batch):
+    """batch: image0 [Vw,B,H,H,3] source frames, (depth0,) image0_mask0/1 [Vw,B,H,H,1], displacement [Vw,B,V] (each
+    frame's viewpoint change to the target).  Frame v runs the multi-object trunk (shared weights) and one 3-channel
+    head: flow_v = head[...,0:2], logit_v = head[...,2]; gen_v = warp(image0_v, flow_v);
     fused = sum_v softmax_v(logit)_v * gen_v   (after Zhou et al. 2016)."""
-    Vw = images0.shape[0]
+    conf = _mv_conf(conf or {})
+    P = {k: ops.asarray(v) for k, v in params.items()}
+    Vw, B, H = batch["image0"].shape[0], batch["image0"].shape[1], batch["image0"].shape[2]
     gens, logits, flows = [], [], []
     for v in range(Vw):
-        o = appearance_flow_forward(ops, params, images0[v], disps[v], "base", extra_heads=[("conf_field", 1)])
-        gens.append(o["gen"]); logits.append(o["heads"]["conf_field"]); flows.append(o["flow_field"])
+        feats = []
+        for key, attr, scope, _ in _MO_INPUTS:
+            if key is None or key in conf:
+                feats.append(_pre_encode(ops, P, ops.from_nhwc(batch[attr][v]), scope))
+        d3_0 = _trunk(ops, P, ops.concat(feats, 3), ops.asarray(batch["displacement"][v]), B, H, fully_conv="fully_conv" in conf)
+        head = ops.nhwc(_decode(ops, P, d3_0, "dec_image1", B, H, 3))              # NHWC [B,H,H,3]
+        flow, logit = head[..., 0:2], head[..., 2:3]
+        src = ops.from_nhwc(batch["image0"][v])
+        gen = ops.nhwc(ops.resample(src, flow + ops.asarray(T.coords(H, H, B))))
+        gens.append(gen); logits.append(logit); flows.append(flow)
     stack = (lambda xs: np.stack(xs, 0)) if ops.name == "numpy" else (lambda xs: __import__("torch").stack(xs, 0))
     gens, logits = stack(gens), stack(logits)
-    return {"gens": gens, "logits": logits, "flows": stack(flows), "fused": fuse_views(ops, gens, logits)}
+    return {"gens": gens, "logits": logits[..., 0], "flows": stack(flows), "fused": fuse_views(ops, gens, logits)}
 
 
 def multiview_loss(ops, out, image1, mode="l2"):

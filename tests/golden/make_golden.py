@@ -156,9 +156,10 @@ def graph_inputs(H=32, B=1, V=2, Vw=3):
              "depth0", "depth1", "depth1_only0", "depth1_only1"]
     mo = {n: rng.random((B, H, H, 3 if (n.startswith("image") and "mask" not in n) else 1), dtype=np.float32) for n in names}
     mo["displacement"] = rng.standard_normal((B, V)).astype(np.float32)
-    views = rng.random((Vw, B, H, H, 3), dtype=np.float32)
-    disps = rng.standard_normal((Vw, B, V)).astype(np.float32)
-    return mo, views, disps
+    views = {"image0": rng.random((Vw, B, H, H, 3), dtype=np.float32), "depth0": rng.random((Vw, B, H, H, 1), dtype=np.float32),
+             "image0_mask0": rng.random((Vw, B, H, H, 1), dtype=np.float32), "image0_mask1": rng.random((Vw, B, H, H, 1), dtype=np.float32),
+             "displacement": rng.standard_normal((Vw, B, V)).astype(np.float32), "image1": mo["image1"]}
+    return mo, views
 
 
 GRAPH_CONFS = {
@@ -172,7 +173,7 @@ GRAPH_CONFS = {
 def graph_outputs():
     from oracle import graph as G
     H, B, V = 32, 1, 2
-    mo, views, disps = graph_inputs(H, B, V)
+    mo, views = graph_inputs(H, B, V)
     ops = G.NumpyOps()
     out = {}
     P = G.init_params(G.appflow_param_shapes(H, V, "base"), 0)
@@ -191,10 +192,11 @@ def graph_outputs():
         for k, v in o.items():
             out["%s_%s" % (key, k)] = v
         out[key + "_loss"] = np.float64(G.multiobject_loss(ops, o, c, mo))
-    P = G.init_params(G.multiview_param_shapes(H, V), 0)
-    o = G.multiview_forward(ops, P, views, disps)
+    c = {"use_depth": 0.1}
+    P = G.init_params(G.multiview_param_shapes(H, V, c), 0)
+    o = G.multiview_forward(ops, P, c, views)
     out["multiview_fused"], out["multiview_logits"] = o["fused"], o["logits"]
-    out["multiview_loss"] = np.float64(G.multiview_loss(ops, o, mo["image1"]))
+    out["multiview_loss"] = np.float64(G.multiview_loss(ops, o, views["image1"]))
     return out
 
 

@@ -337,24 +337,72 @@ def test_multiobject_graph_numpy_vs_torch_cpu(conf):
         assert float(G.multiobject_loss(G.NumpyOps(), o, conf, b1)) == pytest.approx(float(G.multiobject_loss(G.NumpyOps(), o, conf, b2)), rel=1e-12)
 
 
+def _mv_batch(rng, Vw, B, H, V, depth=True):
+    b = {"image0": rng.random((Vw, B, H, H, 3), dtype=np.float32), "image0_mask0": rng.random((Vw, B, H, H, 1), dtype=np.float32),
+         "image0_mask1": rng.random((Vw, B, H, H, 1), dtype=np.float32), "displacement": rng.standard_normal((Vw, B, V)).astype(np.float32),
+         "image1": rng.random((B, H, H, 3), dtype=np.float32)}
+    if depth:
+        b["depth0"] = rng.random((Vw, B, H, H, 1), dtype=np.float32)
+    return b
+
+
 def test_multiview_graph_numpy_vs_torch_cpu_and_single_view_limit():
-    """Config 5's definition: backends agree; with ONE view the fusion is the identity (softmax of one logit = 1), so the
-    model reduces to the single-view appearance-flow graph."""
+    """Config 5's definition (SURVEY 8(f)-3 on the multi-object trunk): backends agree; the fusion is a convex
+    combination; with ONE view it is the identity (softmax of one logit = 1), so the model reduces to a multi-object
+    flow decoder whose head ignores its third channel."""
     rng = np.random.default_rng(4)
     B, H, V, Vw = 1, 32, 2, 3
-    P = G.init_params(G.multiview_param_shapes(H, V), 0)
-    im = rng.random((Vw, B, H, H, 3), dtype=np.float32)
-    d = rng.standard_normal((Vw, B, V)).astype(np.float32)
-    o = G.multiview_forward(G.NumpyOps(), P, im, d)
-    t = G.multiview_forward(G.TorchCpuOps(), P, im, d)
+    conf = {"use_depth": 0.1}
+    P = G.init_params(G.multiview_param_shapes(H, V, conf), 0)
+    assert P["dec_image1/d0/w"].shape == (5, 5, 3, 32) and "pre_mask0_ob1/e0/w" in P and "pre_dimage0_f/e0/w" in P
+    b = _mv_batch(rng, Vw, B, H, V)
+    o = G.multiview_forward(G.NumpyOps(), P, conf, b)
+    t = G.multiview_forward(G.TorchCpuOps(), P, conf, b)
     assert np.allclose(o["fused"], np.asarray(t["fused"]), rtol=1e-3, atol=1e-4)
     assert np.allclose(o["logits"], np.asarray(t["logits"]), rtol=1e-3, atol=1e-4)
     w = np.exp(o["logits"] - o["logits"].max(0, keepdims=True))
     w /= w.sum(0, keepdims=True)
-    assert np.allclose(o["fused"], (w * o["gens"]).sum(0), atol=1e-6) and np.allclose(w.sum(0), 1.0)
-    one = G.multiview_forward(G.NumpyOps(), P, im[:1], d[:1])
-    single = G.appearance_flow_forward(G.NumpyOps(), {k: v for k, v in P.items() if not k.startswith("conf_field")}, im[0], d[0], "base")
-    assert np.array_equal(one["fused"], single["gen"])
+    assert np.allclose(o["fused"], (w[..., None] * o["gens"]).sum(0), atol=1e-6) and np.allclose(w.sum(0), 1.0)
+    one = G.multiview_forward(G.NumpyOps(), P, conf, {k: (v[:1] if k != "image1" else v) for k, v in b.items()})
+    assert np.array_equal(one["fused"], one["gens"][0])
+    # the same frame through the multi-object graph with a 2-channel flow head made of the head's first two channels
+    mo_conf = {"use_color": "", "use_depth": 0.1, "combination_image": ""}
+    P2 = {k: v for k, v in P.items()}
+    P2["dec_image1/d0/w"] = P["dec_image1/d0/w"][:, :, :2, :]
+    P2["d3_0/w"] = np.concatenate([P["d3_0/w"], P["d3_0/w"]], axis=3)          # two heads (colour flow, depth tanh): the colour
+    P2["d3_0/b"] = np.concatenate([P["d3_0/b"], P["d3_0/b"]])                  # head pops the LAST group = a copy of ours
+    for k in list(P):
+        if k.startswith("dec_image1/"):
+            P2["dec_dimage1_f/" + k.split("/", 1)[1]] = P[k][:, :, :1, :] if k.endswith("d0/w") else P[k]
+    mo = {"image0": b["image0"][0], "depth0": b["depth0"][0], "image0_mask0": b["image0_mask0"][0], "image0_mask1": b["image0_mask1"][0],
+          "displacement": b["displacement"][0]}
+    single = G.multiobject_forward(G.NumpyOps(), P2, mo_conf, mo)
+    assert np.allclose(one["gens"][0], single["gen_image1"], atol=1e-6)
+
+
+def test_bf16_aware_backend_rounds_where_the_cuda_path_stores_bf16():
+    """Bf16TorchCpuOps: layer outputs are bf16-representable, fp32 heads are not rounded, weight gradients stay fp32,
+    and on bf16-representable data with a single layer it equals the fp32 backend up to the output rounding."""
+    import torch
+    rng = np.random.default_rng(9)
+    ops16, ops32 = G.Bf16TorchCpuOps(), G.TorchCpuOps()
+    r = lambda a: torch.as_tensor(a).to(torch.bfloat16).to(torch.float32)
+    x = r(rng.standard_normal((2, 8, 8, 4)).astype(np.float32))
+    w = r(rng.standard_normal((3, 3, 4, 8)).astype(np.float32)).requires_grad_(True)
+    bias = torch.as_tensor(rng.standard_normal(8).astype(np.float32))
+    y16 = ops16.lrelu(ops16.conv(ops16.from_nhwc(x), w, bias, 1))
+    y32 = ops32.lrelu(ops32.conv(ops32.from_nhwc(x), w, bias, 1))
+    assert torch.equal(y16, r(y16)) and torch.equal(y16, r(y32))
+    head = ops16.conv(ops16.from_nhwc(x), w, bias, 1)                   # no activation: an fp32 head
+    assert torch.equal(head, ops32.conv(ops32.from_nhwc(x), w, bias, 1)) and not torch.equal(head, r(head))
+    g = torch.as_tensor(rng.standard_normal(tuple(y16.shape)).astype(np.float32))
+    (gw,) = torch.autograd.grad(y16, w, g)
+    assert not torch.equal(gw, r(gw))                                   # fp32 weight gradient
+    # the gradient that reaches the conv is dPre = round(round(g) * act'(y)): compare with that fed to the fp32 backend
+    y32b = ops32.conv(ops32.from_nhwc(x), w, bias, 1)
+    slope = torch.where(y32b > 0, torch.ones_like(y32b), torch.full_like(y32b, 0.2))
+    (gw_ref,) = torch.autograd.grad(y32b, w, r(r(g) * slope))
+    assert torch.allclose(gw, gw_ref, rtol=1e-5, atol=1e-6)
 
 
 def test_graph_golden_vectors(golden_dir):
