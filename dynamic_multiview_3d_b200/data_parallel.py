@@ -86,19 +86,37 @@ class GradientAllReducer:
         self.launched = []
 
 
-def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None):
-    """Uniform chunks of the flat buffer for the sharded mode.  Returns (chunks, var2chunks, expected):
-    chunks = [(start, end)] tiling [0, alloc) (every length a multiple of world*256), var2chunks maps a
-    variable name to the chunks it overlaps, expected[c] = number of trainable variables overlapping chunk c."""
+def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None, big=1 << 20):
+    """Chunks of the flat buffer for the sharded mode.  Returns (chunks, var2chunks, expected):
+    chunks = [(start, end)] tiling [0, alloc) (every length a multiple of world*256), var2chunks maps a variable name to
+    the chunks it overlaps, expected[c] = number of trainable variables overlapping chunk c.
+
+    Backward writes gradients from the END of the buffer towards its start, so a chunk is complete when its LOWEST
+    variable has reported.  Chunk groups therefore begin where a big variable (>= ``big`` elements: the FC matrices)
+    begins -- the group is that matrix plus the small variables created after it, whose gradients arrive earlier -- and
+    each group is cut into pieces of at most ``chunk_elems``.  In particular the first group holds only the encoder's
+    convolution weights: the exchange that cannot start before the very last weight gradient of the step is a few MB,
+    not a slice of fc1 (a uniform grid from offset 0 put 100+ MB behind e0's gradient)."""
     unit = world * 256
     chunk_elems = max(unit, (chunk_elems // unit) * unit)
     assert alloc % unit == 0, "flat buffers must be allocated to a multiple of world*256 elements"
-    chunks = [(s, min(alloc, s + chunk_elems)) for s in range(0, alloc, chunk_elems)]
+    cuts = {0, alloc}
+    for name, off, n in var_table:
+        if n >= big and off % unit == 0 and 0 < off < alloc:
+            cuts.add(off)
+    cuts = sorted(cuts)
+    chunks = []
+    for g0, g1 in zip(cuts, cuts[1:]):
+        pieces = -(-(g1 - g0) // chunk_elems)
+        per = -(-(g1 - g0) // (pieces * unit)) * unit
+        chunks += [(s, min(g1, s + per)) for s in range(g0, g1, per)]
+    starts = [c[0] for c in chunks]
+    import bisect
     var2chunks, expected = {}, [0] * len(chunks)
     for name, off, n in var_table:
         if trainable is not None and name not in trainable:
             continue
-        cs = list(range(off // chunk_elems, (off + n - 1) // chunk_elems + 1))
+        cs = list(range(bisect.bisect_right(starts, off) - 1, bisect.bisect_right(starts, off + n - 1)))
         var2chunks[name] = cs
         for c in cs:
             expected[c] += 1

@@ -17,8 +17,14 @@ from .variables import current_store
 
 
 def _rec(store, var, y):
+    """Test hooks: ``store.record`` (dict) receives every layer's output under the layer's name; ``store.record_grad``
+    (dict) the gradient that output receives in backward."""
     if store.record is not None:
-        store.record[var.name.rsplit("/", 1)[0]] = y
+        name = var.name.rsplit("/", 1)[0]
+        store.record[name] = y
+        rg = getattr(store, "record_grad", None)
+        if rg is not None and y.requires_grad:
+            y.register_hook(lambda g, name=name: rg.__setitem__(name, g.detach()))
     return y
 
 

@@ -17,6 +17,7 @@ import math
 import torch
 
 _ALIGN = 64  # elements; keeps every view 128/256-byte aligned for vector and TMA access
+BIG_VARIABLE = 1 << 20   # elements; variables this large (the FC matrices) begin a new exchange / Adam chunk group
 
 
 class Variable:
@@ -147,6 +148,8 @@ class VariableStore:
                 v.trainable = bool(trainable(v.name))
         for v in self.vars.values():
             if not v.name.endswith("/b"):
+                if v.numel >= BIG_VARIABLE:          # big matrices start on a chunk-plan boundary (data_parallel.plan_chunks)
+                    total = -(-total // 16384) * 16384
                 v.offset = total
                 total += int(math.ceil(v.numel / _ALIGN)) * _ALIGN
         self.shard_end = total = -(-total // 16384) * 16384

@@ -362,18 +362,99 @@ def init_params(shapes, seed=0):
 
 
 # --------------------------------------------------------------------------- #
+# teacher forcing: the checked implementation's own stored activations as layer inputs
+# --------------------------------------------------------------------------- #
+_FORCE = [None]
+_FREE = [None]
+_FORCE_GRAD = [None]
+_FREE_GRAD = [None]
+
+
+class forcing:
+    """Context for the torch backends: ``with forcing(record, grad_record) as f:`` runs a graph in which the OUTPUT of
+    every layer named in ``record`` (name -> NHWC / [B,N] activation as the implementation under test stored it) replaces
+    the oracle's own, value and activation slope alike, while the autograd path through the oracle's arithmetic stays;
+    with ``grad_record`` (name -> the gradient the implementation received for that activation) the incoming gradient
+    of every such layer is replaced likewise during backward.
+
+    Why: bf16 rounding is chaotic.  Two correct implementations whose fp32 sums differ in the last bit round a few
+    activations to different bf16 neighbours; the next layer amplifies a perturbation d to sqrt(d * ulp), so after a few
+    layers the two chains differ by the full bf16 quantisation noise (~sqrt(L) * 2^-9), and leaky-relu units near zero
+    take different slopes, which changes bottleneck gradients by 10 % and more -- between ANY two bf16 chains, and
+    between a bf16 chain and the fp32 reference.  With forcing, every layer is checked on identical inputs:
+    ``f.free[name]`` is the oracle's own output of the layer given the implementation's input (forward check),
+    ``f.free_grad[name]`` the oracle's own gradient for that activation given the implementation's downstream gradient
+    (input-gradient check of the NEXT layer), and every parameter gradient is computed from identical activations,
+    slopes and output gradients (weight-gradient check).  A wrong kernel at layer L still fails: its output differs from
+    ``free[L]``, its gradients from the oracle's."""
+
+    def __init__(self, record, grad_record=None):
+        self.record, self.grad_record = record, grad_record
+        self.free, self.free_grad = {}, {}
+
+    def __enter__(self):
+        _FORCE[0], _FREE[0], _FORCE_GRAD[0], _FREE_GRAD[0] = self.record, self.free, self.grad_record, self.free_grad
+        return self
+
+    def __exit__(self, *a):
+        _FORCE[0] = _FREE[0] = _FORCE_GRAD[0] = _FREE_GRAD[0] = None
+
+
+def _force_grad(ops, name, y):
+    gr, free = _FORCE_GRAD[0], _FREE_GRAD[0]
+    if gr is None or name not in gr:
+        return y
+    t = ops.t
+    g_forced = t.as_tensor(gr[name]).detach().to(t.float32)
+    g_forced = ops.from_nhwc(g_forced) if g_forced.dim() == 4 else g_forced
+
+    class ForceGrad(t.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x.view_as(x)
+
+        @staticmethod
+        def backward(ctx, g):
+            free[name] = g.detach()
+            return g_forced.reshape(g.shape)
+
+    return ForceGrad.apply(y)
+
+
+def _finish(ops, name, pre, act, acts=None):
+    """Activation epilogue of layer ``name`` (act in 'lrelu' | 'relu' | 'tanh' | None) + the forcing hook."""
+    fn = {"lrelu": ops.lrelu, "relu": ops.relu, "tanh": ops.tanh, None: (lambda v: v)}[act]
+    y = fn(pre)
+    if acts is not None:
+        acts[name] = y
+    f = _FORCE[0]
+    if f is not None and name in f and act != "tanh":
+        t = ops.t
+        _FREE[0][name] = y.detach()
+        yc = t.as_tensor(f[name]).detach().to(t.float32)
+        yc = ops.from_nhwc(yc) if yc.dim() == 4 else yc
+        if act == "lrelu":                       # invert the activation: the slope then follows the FORCED output's sign
+            pc = t.where(yc > 0, yc, yc * 5.0)
+        elif act == "relu":
+            pc = t.where(yc > 0, yc, -t.ones_like(yc))
+        else:
+            pc = yc
+        y = _force_grad(ops, name, fn(pre + (pc - pre).detach()))
+    return y
+
+
+# --------------------------------------------------------------------------- #
 # graphs
 # --------------------------------------------------------------------------- #
 def _decode_angle(ops, P, disp, kind):
     if kind in ("base", "tinghui"):          # appearance_flow_model.py:63-66 / tinghui :7-11
-        act = ops.lrelu
-        a0 = act(ops.linear(disp, P["a0/Matrix"], P["a0/b"]))
-        a1 = act(ops.linear(a0, P["a1/Matrix"], P["a1/b"]))
-        return act(ops.linear(a1, P["a2/Matrix"], P["a2/b"]))
+        a0 = _finish(ops, "a0", ops.linear(disp, P["a0/Matrix"], P["a0/b"]), "lrelu")
+        a1 = _finish(ops, "a1", ops.linear(a0, P["a1/Matrix"], P["a1/b"]), "lrelu")
+        return _finish(ops, "a2", ops.linear(a1, P["a2/Matrix"], P["a2/b"]), "lrelu")
     if kind == "highdim":                    # highdim_angle.py:8-10 (a0, a1 outputs unused)
-        return ops.lrelu(ops.linear(disp, P["a2/Matrix"], P["a2/b"]))
+        return _finish(ops, "a2", ops.linear(disp, P["a2/Matrix"], P["a2/b"]), "lrelu")
     if kind == "lowdim":                     # lowdim_angle.py:8
-        return ops.lrelu(ops.linear(disp, P["a0/Matrix"], P["a0/b"]))
+        return _finish(ops, "a0", ops.linear(disp, P["a0/Matrix"], P["a0/b"]), "lrelu")
     raise ValueError(kind)
 
 
@@ -387,26 +468,18 @@ def appearance_flow_forward(ops, params, image0, disp, kind="base", keep=False):
     B, H = image0.shape[0], image0.shape[1]
     acts = {}
 
-    def C(name, inp, s, act=ops.lrelu):
-        y = ops.conv(inp, P[name + "/w"], P[name + "/b"], s)
-        y = act(y) if act is not None else y
-        acts[name] = y
-        return y
+    def C(name, inp, s, act="lrelu"):
+        return _finish(ops, name, ops.conv(inp, P[name + "/w"], P[name + "/b"], s), act, acts)
 
-    def D(name, inp, side, cout, s=2, act=ops.lrelu):
-        y = ops.deconv(inp, P[name + "/w"], (B, side, side, cout), s)
-        y = act(y) if act is not None else y
-        acts[name] = y
-        return y
+    def D(name, inp, side, cout, s=2, act="lrelu"):
+        return _finish(ops, name, ops.deconv(inp, P[name + "/w"], (B, side, side, cout), s), act, acts)
 
-    def FC(name, inp, act=ops.lrelu):
-        y = act(ops.linear(inp, P[name + "/Matrix"], P[name + "/b"]))
-        acts[name] = y
-        return y
+    def FC(name, inp, act="lrelu"):
+        return _finish(ops, name, ops.linear(inp, P[name + "/Matrix"], P[name + "/b"]), act, acts)
 
     h5 = H // 32
     if kind == "tinghui":
-        r = ops.relu
+        r = "relu"
         e = C("e0", x, 2, r); e = C("e1", e, 2, r); e = C("e2", e, 2, r); e = C("e3", e, 2, r); e = C("e4", e, 2, r)
         f = FC("e_fc0", ops.flatten_hwc(e), r)
         f = FC("e_fc1", f, r)
@@ -495,14 +568,14 @@ def colordepth_param_shapes(H, V, conf):
 
 def _pre_encode(ops, P, x, scope):
     for name, st in [("e0", 2), ("e0_0", 1), ("e1", 2), ("e1_0", 1), ("e2", 2)]:
-        x = ops.lrelu(ops.conv(x, P["%s/%s/w" % (scope, name)], P["%s/%s/b" % (scope, name)], st))
+        x = _finish(ops, "%s/%s" % (scope, name), ops.conv(x, P["%s/%s/w" % (scope, name)], P["%s/%s/b" % (scope, name)], st), "lrelu")
     return x
 
 
 def _trunk(ops, P, comb, disp, B, H, fully_conv=False):
     h5 = H // 32
-    c = lambda n, x, s: ops.lrelu(ops.conv(x, P[n + "/w"], P[n + "/b"], s))
-    f = lambda n, x: ops.lrelu(ops.linear(x, P[n + "/Matrix"], P[n + "/b"]))
+    c = lambda n, x, s: _finish(ops, n, ops.conv(x, P[n + "/w"], P[n + "/b"], s), "lrelu")
+    f = lambda n, x: _finish(ops, n, ops.linear(x, P[n + "/Matrix"], P[n + "/b"]), "lrelu")
     e = c("e2_0", comb, 1); e = c("e3", e, 2); e = c("e3_0", e, 1); e = c("e4", e, 2); e = c("e4_0", e, 1)
     a2 = f("a2", f("a1", f("a0", disp)))
     if fully_conv:                      # multiobject_appflow.py:147-153
@@ -513,18 +586,18 @@ def _trunk(ops, P, comb, disp, B, H, fully_conv=False):
         e5 = f("fc1", ops.flatten_hwc(e))
         j = f("a5", f("a4", f("a3", ops.concat([e5, a2], 1))))
         a5r = ops.unflatten_hwc(j, h5, h5, 256)
-    d = ops.lrelu(ops.deconv(a5r, P["d4/w"], (B, 2 * h5, 2 * h5, 128), 2))
+    d = _finish(ops, "d4", ops.deconv(a5r, P["d4/w"], (B, 2 * h5, 2 * h5, 128), 2), "lrelu")
     d = c("d4_0", d, 1)
-    d = ops.lrelu(ops.deconv(d, P["d3/w"], (B, 4 * h5, 4 * h5, 64), 2))
+    d = _finish(ops, "d3", ops.deconv(d, P["d3/w"], (B, 4 * h5, 4 * h5, 64), 2), "lrelu")
     return c("d3_0", d, 1)
 
 
 def _decode(ops, P, x, scope, B, H, cout):
     h5 = H // 32
-    d = ops.lrelu(ops.deconv(x, P[scope + "/d2/w"], (B, 8 * h5, 8 * h5, 32), 2))
-    d = ops.lrelu(ops.conv(d, P[scope + "/d2_0/w"], P[scope + "/d2_0/b"], 1))
-    d = ops.lrelu(ops.deconv(d, P[scope + "/d1/w"], (B, 16 * h5, 16 * h5, 32), 2))
-    d = ops.lrelu(ops.conv(d, P[scope + "/d1_0/w"], P[scope + "/d1_0/b"], 1))
+    d = _finish(ops, scope + "/d2", ops.deconv(x, P[scope + "/d2/w"], (B, 8 * h5, 8 * h5, 32), 2), "lrelu")
+    d = _finish(ops, scope + "/d2_0", ops.conv(d, P[scope + "/d2_0/w"], P[scope + "/d2_0/b"], 1), "lrelu")
+    d = _finish(ops, scope + "/d1", ops.deconv(d, P[scope + "/d1/w"], (B, 16 * h5, 16 * h5, 32), 2), "lrelu")
+    d = _finish(ops, scope + "/d1_0", ops.conv(d, P[scope + "/d1_0/w"], P[scope + "/d1_0/b"], 1), "lrelu")
     return ops.deconv(d, P[scope + "/d0/w"], (B, H, H, cout), 2)
 
 
@@ -695,25 +768,23 @@ def multiview_forward(ops, params, conf, batch):
     """batch: image0 [Vw,B,H,H,3] source frames, (depth0,) image0_mask0/1 [Vw,B,H,H,1], displacement [Vw,B,V] (each
     frame's viewpoint change to the target).  Frame v runs the multi-object trunk (shared weights) and one 3-channel
     head: flow_v = head[...,0:2], logit_v = head[...,2]; gen_v = warp(image0_v, flow_v);
-    fused = sum_v softmax_v(logit)_v * gen_v   (after Zhou et al. 2016)."""
+    fused = sum_v softmax_v(logit)_v * gen_v   (after Zhou et al. 2016).
+    Every layer acts per sample, so the Vw frames of the B samples are run as one batch of Vw*B."""
     conf = _mv_conf(conf or {})
     P = {k: ops.asarray(v) for k, v in params.items()}
     Vw, B, H = batch["image0"].shape[0], batch["image0"].shape[1], batch["image0"].shape[2]
-    gens, logits, flows = [], [], []
-    for v in range(Vw):
-        feats = []
-        for key, attr, scope, _ in _MO_INPUTS:
-            if key is None or key in conf:
-                feats.append(_pre_encode(ops, P, ops.from_nhwc(batch[attr][v]), scope))
-        d3_0 = _trunk(ops, P, ops.concat(feats, 3), ops.asarray(batch["displacement"][v]), B, H, fully_conv="fully_conv" in conf)
-        head = ops.nhwc(_decode(ops, P, d3_0, "dec_image1", B, H, 3))              # NHWC [B,H,H,3]
-        flow, logit = head[..., 0:2], head[..., 2:3]
-        src = ops.from_nhwc(batch["image0"][v])
-        gen = ops.nhwc(ops.resample(src, flow + ops.asarray(T.coords(H, H, B))))
-        gens.append(gen); logits.append(logit); flows.append(flow)
-    stack = (lambda xs: np.stack(xs, 0)) if ops.name == "numpy" else (lambda xs: __import__("torch").stack(xs, 0))
-    gens, logits = stack(gens), stack(logits)
-    return {"gens": gens, "logits": logits[..., 0], "flows": stack(flows), "fused": fuse_views(ops, gens, logits)}
+    N = Vw * B
+    flat = lambda k: np.asarray(batch[k]).reshape((N,) + tuple(batch[k].shape[2:]))
+    feats = []
+    for key, attr, scope, _ in _MO_INPUTS:
+        if key is None or key in conf:
+            feats.append(_pre_encode(ops, P, ops.from_nhwc(flat(attr)), scope))
+    d3_0 = _trunk(ops, P, ops.concat(feats, 3), ops.asarray(flat("displacement")), N, H, fully_conv="fully_conv" in conf)
+    head = ops.nhwc(_decode(ops, P, d3_0, "dec_image1", N, H, 3))                  # NHWC [Vw*B,H,H,3]
+    flow, logit = head[..., 0:2], head[..., 2:3]
+    gen = ops.nhwc(ops.resample(ops.from_nhwc(flat("image0")), flow + ops.asarray(T.coords(H, H, N))))
+    gens, logits = gen.reshape(Vw, B, H, H, 3), logit.reshape(Vw, B, H, H, 1)
+    return {"gens": gens, "logits": logits[..., 0], "flows": flow.reshape(Vw, B, H, H, 2), "fused": fuse_views(ops, gens, logits)}
 
 
 def multiview_loss(ops, out, image1, mode="l2"):

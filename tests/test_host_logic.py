@@ -380,8 +380,32 @@ def test_chunk_plan_tiles_the_buffer():
     alloc = -(-off // 16384) * 16384
     chunks, v2c, exp = plan_chunks(table, alloc, 1 << 20, 8, {"v%d" % i for i in range(6)})
     assert chunks[0][0] == 0 and chunks[-1][1] == alloc and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
-    assert all((e - s) % (8 * 256) == 0 for s, e in chunks)
-    assert v2c["v4"] == [1, 2, 3, 4] and v2c["v0"] == [0] and sum(exp) == sum(len(c) for c in v2c.values())
+    assert all((e - s) % (8 * 256) == 0 and e - s <= 1 << 20 for s, e in chunks)
+    assert v2c["v0"] == [0] and len(v2c["v4"]) >= 3 and sum(exp) == sum(len(c) for c in v2c.values())
+    for name, o, n in table:                       # every variable lies inside the union of its chunks
+        cs = v2c[name]
+        assert chunks[cs[0]][0] <= o and o + n <= chunks[cs[-1]][1] and cs == list(range(cs[0], cs[-1] + 1))
+
+
+def test_chunk_groups_begin_at_big_variables():
+    """The 224^2 app-flow variable table: the first chunk holds the encoder convolutions only (its exchange cannot start
+    before the last weight gradient of the step), every FC matrix starts a chunk group, pieces <= the chunk size."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200.data_parallel import plan_chunks
+    m = pkg.AppearanceFlowModel({"batch_size": 2, "learning_rate": 1e-4, "image_size": 224, "viewpoint_dim": 19}, device="meta")
+    st = m.store
+    table = [(v.name, v.offset, -(-v.numel // 64) * 64) for v in st.vars.values() if v.offset < st.shard_end]
+    live = {v.name for v in st.trainable_vars()}
+    for world, elems in ((8, 32 << 20), (2, 32 << 20), (1, 8 << 20)):
+        chunks, v2c, exp = plan_chunks(table, st.shard_end, elems, world, live)
+        starts = [c[0] for c in chunks]
+        assert chunks[0] == (0, st.vars["fc1/Matrix"].offset) and chunks[0][1] - chunks[0][0] < 2 << 20
+        assert v2c["e0/w"] == [0] and v2c["e4_0/w"] == [0] and 0 not in v2c["fc1/Matrix"]
+        for name in ("fc1/Matrix", "a3/Matrix", "a4/Matrix", "a5/Matrix"):
+            assert st.vars[name].offset in starts and st.vars[name].offset % 16384 == 0
+        assert chunks[-1][1] == st.shard_end and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+        assert all((e - s) % (world * 256) == 0 and e - s <= elems for s, e in chunks)
+        assert v2c["flow_field/w"] == [len(chunks) - 1] and v2c["a5/Matrix"][-1] == len(chunks) - 1
 
 
 def test_synthetic_batches_are_deterministic_and_in_range():
