@@ -56,6 +56,9 @@ SIGNATURES = {
     "dmv_adam_tick": (_i, [_vp, _f, _f, _f, _vp]),
     "dmv_adam_multi": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                             C.POINTER(_ll), _i, _vp, _f, _f, _f, _f, _vp]),
+    "dmv_dp_signal_words": (_i, [_i]),
+    "dmv_dp_exchange_chunk": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll,
+                                   _i, _i, _i, _i, _vp, _f, _f, _f, _f, _i, _vp]),
 }
 
 _lib = None

@@ -29,12 +29,6 @@ __global__ void adam_tick_kernel(float* st, float lr, float b1, float b2) {
     st[3] = st[3] + 1.0f;
 }
 
-__device__ __forceinline__ void adam_one(float& th, float g, float& m, float& v, float lr_t, float omb1, float omb2, float eps) {
-    m = m + (g - m) * omb1;
-    v = v + (g * g - v) * omb2;
-    th = th - (m * lr_t) / (sqrtf(v) + eps);
-}
-
 __global__ void __launch_bounds__(256) adam_multi_kernel(AdamTable t, const float* __restrict__ state, float omb1, float omb2,
                                                           float eps, float gscale) {
     const float lr_t = __ldg(state + 2);
@@ -52,7 +46,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(AdamTable t, const floa
         float4 g4 = __ldg(reinterpret_cast<const float4*>(G));
         float4 m4 = *reinterpret_cast<float4*>(M);
         float4 v4 = *reinterpret_cast<float4*>(V);
-        g4.x *= gscale; g4.y *= gscale; g4.z *= gscale; g4.w *= gscale;
+        g4.x = __fmul_rn(g4.x, gscale); g4.y = __fmul_rn(g4.y, gscale); g4.z = __fmul_rn(g4.z, gscale); g4.w = __fmul_rn(g4.w, gscale);
         adam_one(p4.x, g4.x, m4.x, v4.x, lr_t, omb1, omb2, eps);
         adam_one(p4.y, g4.y, m4.y, v4.y, lr_t, omb1, omb2, eps);
         adam_one(p4.z, g4.z, m4.z, v4.z, lr_t, omb1, omb2, eps);
@@ -77,7 +71,7 @@ __global__ void adam_scalar_kernel(float* P, const float* G, float* M, float* V,
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float p = P[i], m = M[i], v = V[i];
-        adam_one(p, G[i] * gscale, m, v, lr_t, omb1, omb2, eps);
+        adam_one(p, __fmul_rn(G[i], gscale), m, v, lr_t, omb1, omb2, eps);
         P[i] = p; M[i] = m; V[i] = v;
         if (Hc) Hc[i] = __float2bfloat16_rn(p);
     }

@@ -93,4 +93,11 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
     }
 }
 
+// TF ApplyAdam on one element; shared by adam.cu and exchange.cu so both compile to the same arithmetic
+__device__ __forceinline__ void adam_one(float& th, float g, float& m, float& v, float lr_t, float omb1, float omb2, float eps) {
+    m = m + (g - m) * omb1;
+    v = v + (g * g - v) * omb2;
+    th = th - (m * lr_t) / (sqrtf(v) + eps);
+}
+
 }  // namespace dmv

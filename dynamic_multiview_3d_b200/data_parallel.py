@@ -281,6 +281,9 @@ class ShardedTFAdam:
         """Called after ShardedGradientReducer.finish(): the sharded chunks are already updated and gathered (side
         stream, joined); what is left is the replicated bias tail, whose allreduce has completed."""
         from . import functional as F
+        if getattr(self.red, "tail_done", False):     # the fused exchange summed and updated the bias tail itself
+            self.red.tail_done = False
+            return
         if self.rep is not None:
             st = torch.cuda.current_stream(self.red.flat["grad"].device).cuda_stream
             p, g, m, v, h, n = self.rep
@@ -292,18 +295,115 @@ class ShardedTFAdam:
         return int(self.state[3].item())
 
 
+class PeerExchange:
+    """The buffers and pointer tables of dmv_dp_exchange_chunk (include/dmv3d.h): the flat gradient and bf16 buffers of
+    every rank mapped into every rank's address space (torch.distributed._symmetric_memory: CUDA VMM handles exchanged
+    over the process group; a multicast mapping through the NVSwitch when the driver offers one), the symmetric signal
+    words, and this rank's local epoch/ticket words.  Plumbing only -- the exchange itself is one kernel per chunk."""
+
+    def __init__(self, store, slots, group=None, use_multicast=None):
+        import ctypes as C
+        import os
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.store, self.group = store, group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        dev = store.device
+        alloc = store.alloc
+        words = _lib.load().dmv_dp_signal_words(slots)
+        g = symm.empty(alloc, dtype=torch.float32, device=dev)
+        h = symm.empty(alloc, dtype=torch.bfloat16, device=dev)
+        sig = symm.empty(words, dtype=torch.int32, device=dev)
+        sig.zero_()
+        gname = self.group.group_name
+        self.hg, self.hh, self.hs = symm.rendezvous(g, gname), symm.rendezvous(h, gname), symm.rendezvous(sig, gname)
+        # re-home the gradient and bf16 buffers into the symmetric allocations (the weight-gradient kernels and Adam
+        # address them through the variables' views)
+        g.copy_(store.flat["grad"])
+        h.copy_(store.flat["half"])
+        store.flat["grad"], store.flat["half"] = g, h
+        for v in store.vars.values():
+            sl = slice(v.offset, v.offset + v.numel)
+            v.grad, v.half = g[sl].view(v.shape), h[sl].view(v.shape)
+        self.sig = sig
+        self.local = torch.zeros(2 * slots, dtype=torch.int32, device=dev)
+        vp = C.c_void_p * self.world
+        self.grad_peers = vp(*[int(p) for p in self.hg.buffer_ptrs])
+        self.half_peers = vp(*[int(p) for p in self.hh.buffer_ptrs])
+        self.sig_peers = vp(*[int(p) for p in self.hs.buffer_ptrs])
+        if use_multicast is None:
+            use_multicast = os.environ.get("DMV_DP_MULTICAST", "1") == "1"
+        mc_g, mc_h = int(getattr(self.hg, "multicast_ptr", 0) or 0), int(getattr(self.hh, "multicast_ptr", 0) or 0)
+        self.multicast = bool(use_multicast and mc_g and mc_h)
+        self.grad_mc, self.half_mc = (mc_g, mc_h) if self.multicast else (None, None)
+        self.ctas = int(os.environ.get("DMV_DP_CTAS", "0"))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)            # every rank's signal words are zero before anyone signals
+
+
+class FusedShardedReducer(ShardedGradientReducer):
+    """Sharded data parallelism with the exchange fused into ONE hand-written kernel per chunk over peer memory
+    (csrc/exchange.cu): the owner's Adam reads the summed gradient of its slice from its peers (in-switch reduction with
+    multimem.ld_reduce when a multicast mapping exists, fixed-order peer loads otherwise), updates theta/m/v and
+    broadcasts the bf16 copy (multimem.st / peer stores).  Reduce-scatter + Adam + all-gather become one launch: no
+    gradient write-back, no second read, no NCCL kernels.  The bias tail (replicated fp32 masters) is summed by every
+    rank from its peers in the same fixed order and updated locally."""
+
+    def __init__(self, store, chunk_mb=32.0, group=None):
+        super().__init__(store, chunk_mb, group)
+        self.px = PeerExchange(store, len(self.chunks) + 1, group)
+        self.flat = store.flat
+        self.tail_done = False
+
+    def _exchange(self, c, st):
+        from . import functional as F
+        ad, px, f = self.adam, self.px, self.flat
+        if c >= 0:
+            s, e = self.chunks[c]
+            start, n, slot, rep = s, (e - s) // self.world, c, 0
+        else:
+            start, n, slot, rep = self.shard_end, -(-(self.store.alloc - self.shard_end) // 8) * 8, len(self.chunks), 1
+        F._tag[0] = "dp_exchange"
+        F.call("dmv_dp_exchange_chunk", px.grad_peers, px.half_peers, px.sig_peers, px.grad_mc, px.half_mc,
+               f["master"].data_ptr(), f["m"].data_ptr(), f["v"].data_ptr(), px.local.data_ptr(), start, n, self.rank, self.world,
+               slot, rep, ad.state.data_ptr(), ad.beta1, ad.beta2, ad.eps, ad.grad_scale, px.ctas, st)
+
+    def _launch(self, c):
+        if c >= 0:
+            self.launched.append(c)
+        if self.adam is None:
+            raise RuntimeError("the fused exchange needs the optimizer attached (build_loss=True)")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.flat["grad"].device))
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            self._exchange(c, self.comm_stream.cuda_stream)
+        if c < 0:
+            self.tail_done = True
+
+
 def attach(model, bucket_mb=32.0, group=None, mode=None):
     """Make ``model.train_step`` data-parallel over the default (or given) process group.
     mode "sharded" (default): reduce-scatter + owner-only Adam + bf16 all-gather; "allreduce": replicated Adam."""
     import os
     store = model.store
     mode = mode or os.environ.get("DMV_DP_MODE", "sharded")
-    if mode == "sharded":
-        red = ShardedGradientReducer(store, bucket_mb, group)
+    if mode == "fused" and not (dist.is_initialized() and dist.get_world_size(group) > 1 and store.flat["grad"].is_cuda
+                                and model.optimizer is not None):
+        mode = "sharded"
+    if mode in ("sharded", "fused"):
+        if mode == "fused":
+            if dist.get_world_size(group) > 1:        # replicas must start from identical parameters
+                dist.broadcast(store.flat["master"], src=0, group=group)
+                store.refresh_half()
+            red = FusedShardedReducer(store, bucket_mb, group)
+        else:
+            red = ShardedGradientReducer(store, bucket_mb, group)
+        red.mode = mode
         store.grad_ready_hook = red.on_grad_ready
         model._dp = red
         model.world_size = red.world
-        if red.world > 1:
+        if red.world > 1 and mode != "fused":
             dist.broadcast(store.flat["master"], src=0, group=group)
             store.refresh_half()
         if model.optimizer is not None:

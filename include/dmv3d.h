@@ -229,6 +229,33 @@ int dmv_adam_multi(float* const* params, const float* const* grads, float* const
                    const float* state4, float beta1, float beta2, float eps, float grad_scale,
                    void* stream);
 
+/* ---- data-parallel exchange (new work: the reference is single-GPU) -------------------- *
+ * One chunk of the per-step exchange as ONE kernel over peer-mapped (symmetric) memory on the NVSwitch domain:
+ *   reduce-scatter of the gradients  ->  TF-Adam on the slice this rank owns  ->  all-gather of the bf16 compute copy.
+ * The chunk is elements [start, start + world * n_slice) of the flat buffers (variables.py); rank r owns
+ * [start + r * n_slice, start + (r+1) * n_slice).  The owner reads the summed gradient of its slice straight from its
+ * peers' gradient buffers -- `grad_peers[r]` (device pointers to every rank's flat fp32 gradient buffer; fixed summation
+ * order r = 0..world-1, so the result is deterministic and the same on whichever rank computes it) or, when `grad_mc`
+ * is non-NULL, one `multimem.ld_reduce.add.f32` per 16 bytes on the multicast mapping (in-switch reduction) --, updates
+ * theta / m / v in its LOCAL fp32 buffers, and writes the refreshed bf16 copy into every rank's bf16 buffer
+ * (`half_peers[r]`, or one `multimem.st` on `half_mc`).  No gradient is written back, nothing is read twice, no
+ * library collective runs.
+ * Cross-rank ordering: `signal_peers[r]` points at rank r's signal words (uint32, dmv_dp_signal_words() of them, zeroed
+ * once, symmetric); slot `slot` holds a "gradients ready" and an "update written" word per rank.  Each launch takes the
+ * next epoch from `local_state` (uint32[2 * slots], zeroed once: epoch, ticket), releases its ready word to every
+ * peer, acquires all of theirs, works, releases its done word, and the last CTA waits for every peer's done word -- so
+ * when the kernel has completed on a rank, that rank's bf16 chunk is complete and none of its peers still reads its
+ * gradients.  All ranks must launch the same slots in the same order (they do: the order gradients become ready).
+ * `replicated` != 0: no slicing -- every rank sums the whole range [start, start + n_slice) and updates all of it
+ * locally (the bias tail, whose fp32 masters every rank keeps); nothing is written to peers.
+ * world <= 8; n_slice % 8 == 0; start * 4 and the buffers 16-byte aligned; `ctas` CTAs of 512 threads (0 = default). */
+int dmv_dp_signal_words(int slots);
+int dmv_dp_exchange_chunk(const void* const* grad_peers, void* const* half_peers, void* const* signal_peers,
+                          const void* grad_mc, void* half_mc, float* master, float* m, float* v,
+                          void* local_state, long long start, long long n_slice, int rank, int world, int slot,
+                          int replicated, const float* state4, float beta1, float beta2, float eps,
+                          float grad_scale, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,8 @@
-"""torchrun --nproc-per-node N tools/check_dp.py : the sharded (reduce-scatter + owner Adam + all-gather) and the
-allreduce data-parallel modes must produce the same parameters, identical on every rank."""
+"""torchrun --nproc-per-node N tools/check_dp.py : the data-parallel modes -- allreduce (replicated Adam), sharded (NCCL
+reduce-scatter + owner Adam + all-gather) and fused (ONE hand-written kernel per chunk over peer memory: csrc/exchange.cu,
+once with fixed-order peer loads and once with multimem in-switch reduction where the box offers a multicast mapping) --
+must produce the same parameters, identical on every rank; the fused mode must be bit-reproducible run to run.
+Also run by tests/test_dp_gpu.py when the box has >= 2 GPUs."""
 import os
 import sys
 
@@ -16,9 +19,13 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 res = {}
-for mode in ("allreduce", "allreduce2", "sharded"):
+MODES = ("allreduce", "allreduce2", "sharded", "fused_p2p", "fused_p2p2", "fused_mc")
+for mode in MODES:
+    os.environ["DMV_DP_MULTICAST"] = "1" if mode == "fused_mc" else "0"
     model = pkg.AppearanceFlowModel({"batch_size": 4, "learning_rate": 1e-3, "image_size": 64, "viewpoint_dim": 19, "seed": 0})
-    data_parallel.attach(model, bucket_mb=4.0, mode=mode.rstrip("2"))
+    red = data_parallel.attach(model, bucket_mb=4.0, mode=mode.rstrip("2").split("_")[0])
+    if mode.startswith("fused") and rank == 0:
+        print("mode %s: reducer %s, multicast %s" % (mode, type(red).__name__, getattr(getattr(red, "px", None), "multicast", None)), flush=True)
     b = make_batch(4, 64, "onehot19", seed=7, rank=rank)
     args = [torch.from_numpy(b[k]).to(dev) for k in ("image0", "image1", "disp")]
     losses = [float(model.train_step(*args)) for _ in range(3)]
@@ -43,6 +50,13 @@ if rank == 0:
 err = float((pa - ps).abs().max() / pa.abs().max())
 print("rank %d losses allreduce %s sharded %s  max rel param diff %.3g" % (rank, la, ls, err))
 assert err < 1e-5, err
+for mode in ("fused_p2p", "fused_mc"):
+    lf, pf = res[mode]
+    errf = float((pa - pf).abs().max() / pa.abs().max())
+    print("rank %d losses %s %s  max rel param diff vs allreduce %.3g" % (rank, mode, lf, errf))
+    assert errf < 1e-5, (mode, errf)
+assert torch.equal(res["fused_p2p"][1], res["fused_p2p2"][1]), "fused exchange is not bit-reproducible run to run"
+print("rank %d fused (fixed-order peer loads) run-to-run: bit-identical" % rank)
 dist.barrier()
 if rank == 0:
     print("check_dp ok")

@@ -15,6 +15,7 @@ g = torch.randn(T, device=dev)
 h = torch.zeros(T, dtype=torch.bfloat16, device=dev)
 chunk = int(os.environ.get("CHUNK_MB", 32)) * (1 << 20) // 4
 chunks = [(s, min(T, s + chunk)) for s in range(0, T, chunk)]
+assert all((e - s) % (world * 256) == 0 for s, e in chunks)
 
 
 def rs():
@@ -47,5 +48,41 @@ for name, fn in (("reduce_scatter fp32", rs), ("all_gather bf16", ag), ("all_red
     torch.cuda.synchronize()
     if rank == 0:
         print("world %d chunk %d MB  %-20s %.3f ms per step" % (world, chunk * 4 >> 20, name, e0.elapsed_time(e1) / 10), flush=True)
+# the same exchange as ONE hand-written kernel per chunk over peer memory (csrc/exchange.cu): reduce-scatter + Adam + all-gather
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import types  # noqa: E402
+
+from dynamic_multiview_3d_b200 import _lib, data_parallel  # noqa: E402
+
+for mc in ("0", "1"):
+    os.environ["DMV_DP_MULTICAST"] = mc
+    store = types.SimpleNamespace(device=dev, alloc=T, vars={}, flat={"grad": torch.randn(T, device=dev), "half": torch.zeros(T, dtype=torch.bfloat16, device=dev)})
+    px = data_parallel.PeerExchange(store, len(chunks))
+    if mc == "1" and not px.multicast:
+        if rank == 0:
+            print("no multicast mapping on this box: multimem variant skipped", flush=True)
+        break
+    master, m, v = torch.randn(T, device=dev), torch.zeros(T, device=dev), torch.zeros(T, device=dev)
+    state = torch.tensor([0.9, 0.999, 1e-4, 1.0], device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fused():
+        for c, (s, e) in enumerate(chunks):
+            _lib.call("dmv_dp_exchange_chunk", px.grad_peers, px.half_peers, px.sig_peers, px.grad_mc, px.half_mc, master.data_ptr(), m.data_ptr(),
+                      v.data_ptr(), px.local.data_ptr(), s, (e - s) // world, rank, world, c, 0, state.data_ptr(), 0.9, 0.999, 1e-8, 1.0, px.ctas, st)
+
+    for _ in range(3):
+        fused()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fused()
+    e1.record()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("world %d chunk %d MB  %-20s %.3f ms per step (reduce-scatter + Adam on 1/%d + bf16 all-gather, ctas %s)" % (
+            world, chunk * 4 >> 20, "fused kernel " + ("multimem" if px.multicast else "peer ld/st"), e0.elapsed_time(e1) / 10, world, px.ctas or "default"), flush=True)
 dist.barrier()
 os._exit(0)
