@@ -338,8 +338,13 @@ def main():
     model = Model(conf)
     # N > 1: sharded data parallelism.  N == 1: the same chunk pipeline without the exchange -- Adam runs chunk by chunk on a
     # side stream as soon as a chunk's gradients are complete, so the HBM-bound update overlaps the rest of backward.
+    exchange = "none"
     if world > 1 or os.environ.get("DMV_OVERLAP_ADAM", "1") == "1":
-        data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128" if world > 1 else "32")))
+        red = data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128" if world > 1 else "32")))
+        if world > 1:
+            exchange = getattr(red, "mode", "allreduce")
+            if exchange == "fused":
+                exchange += " (one kernel per chunk over peer memory, %s)" % ("multimem in-switch reduction" if red.px.multicast else "fixed-order peer loads")
     b = synthetic_batch(model, seed=1234, rank=rank)
     # The host batch is held in the reference's storage format: uint8 pixels (read_tf_records.py:104-111, images are
     # tf.decode_raw(..., tf.uint8) / 255).  The same quantised images, converted on the device, are the HBM-resident batch.
@@ -494,7 +499,7 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "bench_config": args.config, "model_class": cls_name,
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": H, "loss": loss_name,
-                       "parallelism": "dp%d" % world, "cuda_graph": not args.eager,
+                       "parallelism": "dp%d" % world, "exchange": exchange, "cuda_graph": not args.eager,
                        "host_input": "uint8 pixels (reference TFRecord format), /255 on the device" if u8 else "float32", "algo": args.algo or F.get_default_algo(),
                        "l2_policy": "per-step working set (parameters, Adam state, activations: several GB) >> 126 MB L2"},
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

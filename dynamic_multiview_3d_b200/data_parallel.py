@@ -396,7 +396,12 @@ def attach(model, bucket_mb=32.0, group=None, mode=None):
             if dist.get_world_size(group) > 1:        # replicas must start from identical parameters
                 dist.broadcast(store.flat["master"], src=0, group=group)
                 store.refresh_half()
-            red = FusedShardedReducer(store, bucket_mb, group)
+            try:
+                red = FusedShardedReducer(store, bucket_mb, group)
+            except Exception as ex:               # no peer mapping on this box / torch build: the NCCL pipeline still works
+                import sys
+                print("data_parallel: fused exchange unavailable (%r); using the NCCL reduce-scatter pipeline" % (ex,), file=sys.stderr)
+                mode, red = "sharded", ShardedGradientReducer(store, bucket_mb, group)
         else:
             red = ShardedGradientReducer(store, bucket_mb, group)
         red.mode = mode
