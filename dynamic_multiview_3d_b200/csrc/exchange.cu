@@ -9,7 +9,7 @@ namespace {
 using namespace dmv;
 
 constexpr int kMaxWorld = 8;
-constexpr int kThreads = 512;
+constexpr int kThreads = 256;
 
 struct ExchangeArgs {
     const float* grad[kMaxWorld];
@@ -36,11 +36,11 @@ __device__ __forceinline__ float4 mm_ld_reduce_v4(const float* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void mm_st_v4(void* p, uint4 v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void mm_st_v2(void* p, uint2 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
-__device__ __forceinline__ void st_sys_v4(void* p, uint4 v) {
-    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void st_sys_v2(void* p, uint2 v) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acq_sys(const unsigned* p) {
     unsigned v;
@@ -57,8 +57,14 @@ __device__ __forceinline__ int sig_index(int slot, int phase, int r) { return (s
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// U = float4 groups a thread has in flight per peer: W * U remote-or-local gradient loads (16 B each) plus 3 U local
+// loads are issued before anything is consumed -- the loop is bound by NVLink / HBM latency x bytes in flight
 template <int W>
-__global__ void __launch_bounds__(kThreads) exchange_kernel(ExchangeArgs a) {
+struct Unroll { static constexpr int value = W >= 8 ? 1 : (W >= 4 ? 2 : 4); };
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, 2) exchange_kernel(ExchangeArgs a) {
+    constexpr int U = Unroll<W>::value;
     __shared__ int s_last;
     unsigned* epoch = a.local + 2 * a.slot;
     unsigned* ticket = epoch + 1;
@@ -73,62 +79,67 @@ __global__ void __launch_bounds__(kThreads) exchange_kernel(ExchangeArgs a) {
     __syncthreads();
 
     const float lr_t = __ldg(a.state + 2);
+    const float gs = a.gscale;
     const long long base = a.start + (a.replicated ? 0 : (long long)a.rank * a.n_slice);
-    const long long n8 = a.n_slice >> 3;
-    const long long stride = (long long)gridDim.x * kThreads;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n8; i += stride) {
-        const long long off = base + i * 8;
-        float4 g0, g1;
+    const long long n4 = a.n_slice >> 2;
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5, warps = ((long long)gridDim.x * kThreads) >> 5;
+    // a warp owns blocks of U x 32 consecutive float4; within a block, load u of lane l is float4 (u * 32 + l): every
+    // instruction of the warp touches 512 contiguous bytes
+    for (long long blk = warp_id * (U * 32); blk < n4; blk += warps * (U * 32)) {
+        float4 g[U], p[U], m[U], v[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) live[u] = blk + u * 32 + lane < n4;
         if (a.grad_mc) {                                   // in-switch reduction: one load returns the sum over ranks
-            g0 = mm_ld_reduce_v4(a.grad_mc + off);
-            g1 = mm_ld_reduce_v4(a.grad_mc + off + 4);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (live[u]) g[u] = mm_ld_reduce_v4(a.grad_mc + base + (blk + u * 32 + lane) * 4);
         } else {                                           // all loads in flight first, then a fixed-order sum r = 0..W-1
-            float4 x0[W], x1[W];
+            float4 x[W][U];
 #pragma unroll
-            for (int r = 0; r < W; ++r) {
-                x0[r] = ld_sys_v4(a.grad[r] + off);
-                x1[r] = ld_sys_v4(a.grad[r] + off + 4);
-            }
-            g0 = x0[0];
-            g1 = x1[0];
+            for (int r = 0; r < W; ++r)
 #pragma unroll
-            for (int r = 1; r < W; ++r) {
-                g0 = add4(g0, x0[r]);
-                g1 = add4(g1, x1[r]);
+                for (int u = 0; u < U; ++u)
+                    if (live[u]) x[r][u] = ld_sys_v4(a.grad[r] + base + (blk + u * 32 + lane) * 4);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                g[u] = x[0][u];
+#pragma unroll
+                for (int r = 1; r < W; ++r) g[u] = add4(g[u], x[r][u]);
             }
         }
-        float4 p0 = *reinterpret_cast<float4*>(a.master + off), p1 = *reinterpret_cast<float4*>(a.master + off + 4);
-        float4 m0 = *reinterpret_cast<float4*>(a.m + off), m1 = *reinterpret_cast<float4*>(a.m + off + 4);
-        float4 v0 = *reinterpret_cast<float4*>(a.v + off), v1 = *reinterpret_cast<float4*>(a.v + off + 4);
-        const float gs = a.gscale;
-        adam_one(p0.x, __fmul_rn(g0.x, gs), m0.x, v0.x, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p0.y, __fmul_rn(g0.y, gs), m0.y, v0.y, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p0.z, __fmul_rn(g0.z, gs), m0.z, v0.z, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p0.w, __fmul_rn(g0.w, gs), m0.w, v0.w, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p1.x, __fmul_rn(g1.x, gs), m1.x, v1.x, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p1.y, __fmul_rn(g1.y, gs), m1.y, v1.y, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p1.z, __fmul_rn(g1.z, gs), m1.z, v1.z, lr_t, a.omb1, a.omb2, a.eps);
-        adam_one(p1.w, __fmul_rn(g1.w, gs), m1.w, v1.w, lr_t, a.omb1, a.omb2, a.eps);
-        *reinterpret_cast<float4*>(a.master + off) = p0;
-        *reinterpret_cast<float4*>(a.master + off + 4) = p1;
-        *reinterpret_cast<float4*>(a.m + off) = m0;
-        *reinterpret_cast<float4*>(a.m + off + 4) = m1;
-        *reinterpret_cast<float4*>(a.v + off) = v0;
-        *reinterpret_cast<float4*>(a.v + off + 4) = v1;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(p0.x, p0.y), h1 = __floats2bfloat162_rn(p0.z, p0.w);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(p1.x, p1.y), h3 = __floats2bfloat162_rn(p1.z, p1.w);
-        uint4 pk;
-        pk.x = *reinterpret_cast<unsigned*>(&h0);
-        pk.y = *reinterpret_cast<unsigned*>(&h1);
-        pk.z = *reinterpret_cast<unsigned*>(&h2);
-        pk.w = *reinterpret_cast<unsigned*>(&h3);
-        if (a.replicated) {
-            *reinterpret_cast<uint4*>(a.half[a.rank] + off) = pk;
-        } else if (a.half_mc) {
-            mm_st_v4(a.half_mc + off, pk);
-        } else {
 #pragma unroll
-            for (int r = 0; r < W; ++r) st_sys_v4(a.half[r] + off, pk);
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            const long long off = base + (blk + u * 32 + lane) * 4;
+            p[u] = *reinterpret_cast<const float4*>(a.master + off);
+            m[u] = *reinterpret_cast<const float4*>(a.m + off);
+            v[u] = *reinterpret_cast<const float4*>(a.v + off);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            const long long off = base + (blk + u * 32 + lane) * 4;
+            adam_one(p[u].x, __fmul_rn(g[u].x, gs), m[u].x, v[u].x, lr_t, a.omb1, a.omb2, a.eps);
+            adam_one(p[u].y, __fmul_rn(g[u].y, gs), m[u].y, v[u].y, lr_t, a.omb1, a.omb2, a.eps);
+            adam_one(p[u].z, __fmul_rn(g[u].z, gs), m[u].z, v[u].z, lr_t, a.omb1, a.omb2, a.eps);
+            adam_one(p[u].w, __fmul_rn(g[u].w, gs), m[u].w, v[u].w, lr_t, a.omb1, a.omb2, a.eps);
+            *reinterpret_cast<float4*>(a.master + off) = p[u];
+            *reinterpret_cast<float4*>(a.m + off) = m[u];
+            *reinterpret_cast<float4*>(a.v + off) = v[u];
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p[u].x, p[u].y), hi = __floats2bfloat162_rn(p[u].z, p[u].w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&lo);
+            pk.y = *reinterpret_cast<unsigned*>(&hi);
+            if (a.replicated) {
+                *reinterpret_cast<uint2*>(a.half[a.rank] + off) = pk;
+            } else if (a.half_mc) {
+                mm_st_v2(a.half_mc + off, pk);
+            } else {
+#pragma unroll
+                for (int r = 0; r < W; ++r) st_sys_v2(a.half[r] + off, pk);
+            }
         }
     }
     // ---- everything this rank writes to its peers is out: last CTA releases "done" and waits for every peer's, so that
@@ -187,8 +198,11 @@ int dmv_dp_exchange_chunk(const void* const* grad_peers, void* const* half_peers
     a.start = start; a.n_slice = n_slice;
     a.rank = rank; a.world = world; a.slot = slot; a.replicated = replicated ? 1 : 0;
     a.omb1 = 1.0f - beta1; a.omb2 = 1.0f - beta2; a.eps = eps; a.gscale = grad_scale;
-    long long want = dmv::ceil_div_ll(n_slice / 8, kThreads);
-    int grid = ctas > 0 ? ctas : 48;
+    // default grid: four 256-thread CTAs per SM at most (the kernel also carries the owned slice's Adam traffic, 28 B per element,
+    // which needs the whole memory system at small world sizes), at least ~4 blocks of work per warp
+    const int U = world >= 8 ? 1 : (world >= 4 ? 2 : 4);
+    long long want = dmv::ceil_div_ll(n_slice / 4, (long long)kThreads * U * 4);
+    int grid = ctas > 0 ? ctas : 4 * 148;
     if (grid > want) grid = (int)want;
     if (grid < 1) grid = 1;
     cudaStream_t st = (cudaStream_t)stream;

@@ -248,7 +248,7 @@ int dmv_adam_multi(float* const* params, const float* const* grads, float* const
  * gradients.  All ranks must launch the same slots in the same order (they do: the order gradients become ready).
  * `replicated` != 0: no slicing -- every rank sums the whole range [start, start + n_slice) and updates all of it
  * locally (the bias tail, whose fp32 masters every rank keeps); nothing is written to peers.
- * world <= 8; n_slice % 8 == 0; start * 4 and the buffers 16-byte aligned; `ctas` CTAs of 512 threads (0 = default). */
+ * world <= 8; n_slice % 8 == 0; start * 4 and the buffers 16-byte aligned; `ctas` CTAs of 256 threads (0 = default). */
 int dmv_dp_signal_words(int slots);
 int dmv_dp_exchange_chunk(const void* const* grad_peers, void* const* half_peers, void* const* signal_peers,
                           const void* grad_mc, void* half_mc, float* master, float* m, float* v,
