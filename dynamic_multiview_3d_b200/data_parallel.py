@@ -1,14 +1,19 @@
-"""Batch-sharded data parallelism: one process per GPU, replicated parameters, ONE exchange
-per step -- a sum-allreduce of the flat gradient buffer over NCCL (NVLink 5 / NVSwitch).
-New work relative to the reference, which is single-GPU.
+"""Batch-sharded data parallelism: one process per GPU, ONE exchange per step over NVLink 5 / NVSwitch.
+New work relative to the reference, which is single-GPU.  Three modes (``attach``):
 
-The flat gradient buffer (variables.py) is cut into contiguous buckets in REVERSE creation
-order, i.e. the order backward produces gradients: decoder convs, a5, a4, a3, fc1, encoder.
-When the last gradient of a bucket has been written, the bucket's allreduce is enqueued on a
-side stream behind an event, so the four big FC buckets (97 % of the bytes) fly while the
-FLOP-heavy encoder backward still runs.  The loss already divides by the GLOBAL pixel count,
-so the summed gradient is the global-batch gradient and Adam needs no rescale.  Everything
-is stream-ordered (events, no host sync), hence capturable in a CUDA graph.
+  fused     (default, CUDA, world > 1)  ZeRO-1 style.  The flat buffers are cut into chunks that begin where the big
+            FC matrices begin (``plan_chunks``); when the last gradient of a chunk has been written, ONE hand-written
+            kernel (csrc/exchange.cu, include/dmv3d.h: dmv_dp_exchange_chunk) runs on a side stream: the owner of each
+            1/world slice sums the gradient straight out of its peers' buffers (symmetric memory; fixed rank order, or
+            multimem.ld_reduce through the switch), applies TF-Adam to its fp32 masters and moments, and writes the
+            refreshed bf16 compute copy into every rank's buffer.  No NCCL kernels, no gradient write-back.
+  sharded   the same pipeline on NCCL collectives: reduce_scatter -> owner Adam -> all_gather of the bf16 copies
+            (fallback when peer mapping is unavailable; what the CPU / gloo host-logic tests run).
+  allreduce bucketed sum-allreduce in REVERSE creation order (the order backward produces gradients), replicated Adam.
+
+The loss already divides by the GLOBAL pixel count, so the summed gradient is the global-batch gradient and Adam needs
+no rescale.  Everything is stream-ordered (events, no host sync), hence capturable in a CUDA graph.  The three modes give
+bit-identical parameters (tools/check_dp.py, tests/test_dp_gpu.py).
 """
 import torch
 import torch.distributed as dist
@@ -384,10 +389,12 @@ class FusedShardedReducer(ShardedGradientReducer):
 
 def attach(model, bucket_mb=32.0, group=None, mode=None):
     """Make ``model.train_step`` data-parallel over the default (or given) process group.
-    mode "sharded" (default): reduce-scatter + owner-only Adam + bf16 all-gather; "allreduce": replicated Adam."""
+    mode "fused" (default on CUDA with world > 1): one hand-written kernel per chunk over peer memory (reduce-scatter +
+    owner-only Adam + bf16 all-gather, csrc/exchange.cu); "sharded": the same pipeline on NCCL collectives (also the
+    fallback when no peer mapping can be made, and what CPU/gloo runs use); "allreduce": bucketed allreduce, replicated Adam."""
     import os
     store = model.store
-    mode = mode or os.environ.get("DMV_DP_MODE", "sharded")
+    mode = mode or os.environ.get("DMV_DP_MODE", "fused")
     if mode == "fused" and not (dist.is_initialized() and dist.get_world_size(group) > 1 and store.flat["grad"].is_cuda
                                 and model.optimizer is not None):
         mode = "sharded"

@@ -119,6 +119,36 @@ def test_fused_grid_matches_warp_pts_layer(order):
         assert np.array_equal(out.cpu().numpy(), r["out"])
 
 
+@pytest.mark.parametrize("C", [1, 3, 4])
+@pytest.mark.parametrize("regime", ["jitter", "rotation", "far", "boundary"])
+def test_reference_grid_transposed_lane_kernel(C, regime):
+    """The reference's (Y,X) grid fused into the kernel (flags = ADD_GRID) takes the transposed-lane kernel
+    (sampler_tr_kernel: lanes walk down output columns, padded shared tiles): forward and grad_warp bit-equal to the
+    oracle on a ragged, NON-square output over a non-square source (out[i,j] = bilinear(src, x = i + f0, y = j + f1)),
+    and bit-equal to the lanes-along-rows kernel the debug call takes."""
+    rng = np.random.default_rng(C * 31 + len(regime))
+    B, H, W, Ho, Wo = 3, 52, 76, 72, 44                     # W*C, Wo*C multiples of 4; 32x32 tiles ragged on both sides
+    data = rng.random((B, H, W, C), dtype=np.float32)
+    if regime == "jitter":
+        flow = rng.uniform(-3, 3, (B, Ho, Wo, 2)).astype(np.float32)
+    elif regime == "rotation":
+        ii, jj = np.meshgrid(np.arange(Ho, dtype=np.float32), np.arange(Wo, dtype=np.float32), indexing="ij")
+        c, s_ = np.cos(np.radians(10)), np.sin(np.radians(10))
+        flow = np.broadcast_to(np.stack([ii * c + jj * s_ - ii, -ii * s_ + jj * c - jj], -1)[None], (B, Ho, Wo, 2)).astype(np.float32)
+    elif regime == "far":                                    # tap boxes beyond the staged window: global gathers
+        flow = rng.uniform(-40, 40, (B, Ho, Wo, 2)).astype(np.float32)
+    else:
+        flow = np.zeros((B, Ho, Wo, 2), np.float32)
+        flow[:, :, :, 0] = rng.choice(np.array([-1.0, -1 + 1e-6, -0.5, 0.0, 0.5, 1e6, np.nan], np.float32), (B, Ho, Wo))
+        flow[:, :, :, 1] = rng.choice(np.array([-1.0, -0.25, 0.0, 0.75, 3.0, -1e6], np.float32), (B, Ho, Wo))
+    flow = np.ascontiguousarray(flow)
+    go = rng.standard_normal((B, Ho, Wo, C)).astype(np.float32)
+    r = _run(data, flow, 1, go, need_data_grad=False)
+    ii, jj = np.meshgrid(np.arange(Ho, dtype=np.float32), np.arange(Wo, dtype=np.float32), indexing="ij")
+    warp = (flow + np.stack([ii, jj], -1)[None]).astype(np.float32)              # tf_utils.py:44-52: channel 0 += row, 1 += column
+    _check(data, warp, go, r)
+
+
 def test_sample_list_layout_and_empty_validity():
     rng = np.random.default_rng(4)
     data = rng.random((2, 8, 8, 3), dtype=np.float32)
