@@ -35,6 +35,7 @@ SIGNATURES = {
     "dmv_scale_by_device_scalar": (_i, [_vp, _vp, _ll, _vp]),
     "dmv_conv_workspace_size": (_sz, [_i] * 8),
     "dmv_u8_to_f32": (_i, [_vp, _vp, _ll, _f, _vp]),
+    "dmv_u8_crop_resize_bicubic": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dmv_thin_s2d_size": (_sz, [_i] * 8),
     "dmv_thin_s2d_prep": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "dmv_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),

@@ -46,9 +46,6 @@ using namespace dmv;
 #ifndef SAMPLER_TMA_MINBLOCKS
 #define SAMPLER_TMA_MINBLOCKS 5
 #endif
-#ifndef SAMPLER_TR
-#define SAMPLER_TR 1           // reference (Y,X) grid: lanes walk down output columns (sampler_tr_kernel)
-#endif
 #ifndef SAMPLER_BOX
 #define SAMPLER_BOX 40         // source window box of the TMA kernel, pixels per side
 #endif
@@ -313,41 +310,6 @@ struct FuseArgs {
     float* grad_wf;
 };
 
-// deterministic loss of the fused kernels: fixed tree inside the CTA, per-CTA partials (double), ordered sum by the last
-// CTA to finish (all its threads, fixed tree); the counter resets itself for the next launch
-__device__ __forceinline__ void fused_loss_tail(const FuseArgs& fa, float loss_acc) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    __shared__ double s_red[kWarps];
-    __shared__ bool s_last;
-    double local = (double)loss_acc;
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if (lane == 0) s_red[warp] = local;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < kWarps; ++w) t += s_red[w];
-        fa.partials[blockIdx.x] = t;
-        __threadfence();
-        s_last = (atomicAdd(fa.counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        double t = 0.0;
-        for (unsigned q = tid; q < gridDim.x; q += kThreads) t += __ldcg(fa.partials + q);   // thread-strided, fixed order
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-        __syncthreads();
-        if (lane == 0) s_red[warp] = t;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < kWarps; ++w) tot += s_red[w];
-            *fa.loss_out = (float)(tot * (double)fa.inv_count);
-            *fa.counter = 0;          // ready for the next launch (stream-ordered)
-        }
-    }
-}
-
 template <int C, int MODE>
 __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_kernel(
     const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_src_l,
@@ -536,228 +498,39 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_k
         __syncthreads();
         if (tid == 0) tc::tma_store_3d(&map_io, s_io, j0 * C, i0, b);
     }
-    if (MODE == 2) fused_loss_tail(fa, loss_acc);
-    if ((MODE == 0 || MODE == 2) && tid == 0) tc::bulk_commit_wait_read();   // the tile stays in shared memory until the store has read it
-}
-
-// TR kernel (transposed lanes): the form the reference's (Y,X) grid needs.  With warp = flow + (row, col) fed to an
-// (x, y) sampler (tf_utils.py:44-52) the source x follows the OUTPUT ROW index, so in sampler_tma_kernel -- lanes along
-// an output row -- the 32 lanes of a warp read taps one source ROW apart: window pitch 120 / 144 floats = 24 / 16 mod 32,
-// i.e. 8- / 16-way bank conflicts on every one of the 12 scalar tap reads (ncu, round 1: 3.4 M conflicts in 5.2 M shared
-// wavefronts, L1TEX-bound at 47 % of HBM).  Here lanes walk down an output COLUMN: their taps are C floats apart in one
-// source row -- conflict-free for smooth flows.  Every global access stays coalesced by going through padded shared tiles
-// (row pitch = 1 mod 32 floats): the flow tile, the grad_out / target tile and the result tile move by cooperative
-// row-wise 16-byte loads / stores and are read / written column-wise by their owner threads; the source window is the
-// same TMA box load in extended coordinates.  Same arithmetic, same bits as the other two kernels.
-template <int C>
-__device__ __forceinline__ void tr_load_tile(float* s_tile, const float* __restrict__ src, const Geom& g, int b, int i0, int j0) {
-    // [32][32*C] region of an NHWC image -> padded tile; rows are 16-byte aligned (Wo*C % 4 == 0, 32*C % 4 == 0)
-    constexpr int kPIO = 32 * C + 1, kRowV = 32 * C / 4;
-    for (int q = threadIdx.x; q < 32 * kRowV; q += kThreads) {
-        const int r = q / kRowV, e = (q - r * kRowV) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i0 + r < g.Ho && j0 * C + e < g.Wo * C)
-            v = __ldg(reinterpret_cast<const float4*>(src + ((long long)b * g.Ho + i0 + r) * g.Wo * C + j0 * C + e));
-        float* d = s_tile + r * kPIO + e;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-}
-template <int C>
-__device__ __forceinline__ void tr_store_tile(const float* s_tile, float* __restrict__ dst, const Geom& g, int b, int i0, int j0) {
-    constexpr int kPIO = 32 * C + 1, kRowV = 32 * C / 4;
-    for (int q = threadIdx.x; q < 32 * kRowV; q += kThreads) {
-        const int r = q / kRowV, e = (q - r * kRowV) * 4;
-        if (i0 + r < g.Ho && j0 * C + e < g.Wo * C) {
-            const float* t = s_tile + r * kPIO + e;
-            *reinterpret_cast<float4*>(dst + ((long long)b * g.Ho + i0 + r) * g.Wo * C + j0 * C + e) = make_float4(t[0], t[1], t[2], t[3]);
-        }
-    }
-}
-
-template <int C, int MODE>
-__global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tr_kernel(
-    const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_src_l, const float* __restrict__ data,
-    const float* __restrict__ wf, const float* __restrict__ aux /* MODE 1: grad_out, MODE 2: target */, float* __restrict__ out, Geom g,
-    const FuseArgs fa) {
-    extern __shared__ __align__(128) float s_dyn[];
-    constexpr int kPIO = 32 * C + 1;                   // row pitch of the io / aux tiles: = 1 mod 32 floats
-    constexpr int kPFL = 33;                           // row pitch of the flow tile (float2)
-    float* s_win = s_dyn;                              // [box][box * C], box = kBoxS or kBoxL
-    float* s_io = s_dyn + kBoxL * kBoxL * C;           // MODE 0/2: results; MODE 1: grad_out
-    float* s_aux = s_io + 32 * kPIO;                   // MODE 2: target
-    // flow tile in, flow gradient out.  MODE 0 needs it only before the first result is written: it aliases s_io there
-    float2* s_fl = reinterpret_cast<float2*>(MODE == 0 ? s_io : (MODE == 2 ? s_aux + 32 * kPIO + 1 : s_io + 32 * kPIO + 1));
-    __shared__ __align__(8) uint64_t s_bar[1];
-    __shared__ int s_box[4];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int b, i0, j0;
-    tile_origin(g, blockIdx.x, b, i0, j0);
-    if (tid < 4) s_box[tid] = (tid & 1) ? -0x7fffffff : 0x7fffffff;
-    if (tid == 0) {
-        tc::mbar_init(&s_bar[0], 1);
-        tc::fence_barrier_init();
-        tc::fence_proxy_async();
-    }
-    const long long img_pix = (long long)b * g.Ho * g.Wo;
-    // flow tile: row-wise coalesced float2 loads (thread (warp, k) -> row warp + 8k, column lane)
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-        const int r = warp + k * kWarps;
-        float2 f = make_float2(0.f, 0.f);
-        if (i0 + r < g.Ho && j0 + lane < g.Wo) f = __ldg(reinterpret_cast<const float2*>(wf) + img_pix + (long long)(i0 + r) * g.Wo + j0 + lane);
-        s_fl[r * kPFL + lane] = f;
-    }
-    if (MODE == 1) tr_load_tile<C>(s_io, aux, g, b, i0, j0);
-    if (MODE == 2) tr_load_tile<C>(s_aux, aux, g, b, i0, j0);
-    __syncthreads();
-
-    // from here on a thread owns pixels (row = lane, column = warp + 8k) of the tile
-    const int i = i0 + lane;
-    float loss_acc = 0.f;
-    float sx[kPPT], sy[kPPT];
-    bool valid[kPPT];
-    int fx[kPPT], fy[kPPT];
-    int bxlo = 0x7fffffff, bxhi = -0x7fffffff, bylo = 0x7fffffff, byhi = -0x7fffffff;
-    const float fW = (float)g.W, fH = (float)g.H;
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-        const int cq = warp + k * kWarps, j = j0 + cq;
-        const bool inb = (i < g.Ho) && (j < g.Wo);
-        const float2 f = s_fl[lane * kPFL + cq];
-        sx[k] = f.x; sy[k] = f.y;
-        if (g.flags & DMV_SAMPLER_ADD_GRID) {
-            if (g.flags & DMV_SAMPLER_GRID_XY) {
-                sx[k] = __fadd_rn(f.x, (float)j);
-                sy[k] = __fadd_rn(f.y, (float)i);
-            } else {
-                sx[k] = __fadd_rn(f.x, (float)i);
-                sy[k] = __fadd_rn(f.y, (float)j);
-            }
-        }
-        valid[k] = inb && (sx[k] > -1.0f) && (sy[k] > -1.0f) && (sx[k] < fW) && (sy[k] < fH);
-        fx[k] = valid[k] ? __float2int_rd(sx[k]) : 0;
-        fy[k] = valid[k] ? __float2int_rd(sy[k]) : 0;
-        if (valid[k]) {
-            bxlo = min(bxlo, fx[k]); bxhi = max(bxhi, fx[k] + 1);
-            bylo = min(bylo, fy[k]); byhi = max(byhi, fy[k] + 1);
-        }
-    }
-    bxlo = __reduce_min_sync(0xffffffffu, bxlo); bxhi = __reduce_max_sync(0xffffffffu, bxhi);
-    bylo = __reduce_min_sync(0xffffffffu, bylo); byhi = __reduce_max_sync(0xffffffffu, byhi);
-    if (lane == 0) {
-        atomicMin(&s_box[0], bxlo); atomicMax(&s_box[1], bxhi);
-        atomicMin(&s_box[2], bylo); atomicMax(&s_box[3], byhi);
-    }
-    __syncthreads();                                   // also: every thread has read its flow (MODE 0: s_fl aliases s_io)
-    const int xlo = s_box[0], xhi = s_box[1], ylo = s_box[2], yhi = s_box[3];
-    const bool any_valid = xlo <= xhi;
-    const int xa = (C == 4) ? xlo : (xlo & ~3);
-    const int span = max(xhi - xa, yhi - ylo);
-    const bool staged = any_valid && (span < kBoxL);
-    const int box = (span < kBoxS) ? kBoxS : kBoxL;
-    const int kPitch = box * C;
-    if (staged) {
+    if (MODE == 2) {
+        // deterministic loss: fixed tree inside the CTA, per-CTA partials, ordered sum by the last CTA to finish
+        __shared__ double s_red[kWarps];
+        __shared__ bool s_last;
+        double local = (double)loss_acc;
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if (lane == 0) s_red[warp] = local;
+        __syncthreads();
         if (tid == 0) {
-            tc::mbar_expect_tx(&s_bar[0], box * box * C * 4);
-            tc::tma_load_3d(s_win, span < kBoxS ? &map_src : &map_src_l, &s_bar[0], xa * C, ylo, b);
+            double t = 0.0;
+            for (int w = 0; w < kWarps; ++w) t += s_red[w];
+            fa.partials[blockIdx.x] = t;
+            __threadfence();
+            s_last = (atomicAdd(fa.counter, 1u) == gridDim.x - 1);
         }
-        tc::mbar_wait(&s_bar[0], 0);
-    }
-
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-        const int cq = warp + k * kWarps;
-        const int cx = fx[k] + 1, cy = fy[k] + 1;
-        const float dx = valid[k] ? __fsub_rn((float)cx, sx[k]) : 0.f;
-        const float dy = valid[k] ? __fsub_rn((float)cy, sy[k]) : 0.f;
-        const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
-        float p_ff[C], p_cc[C], p_fc[C], p_cf[C];
-        if (staged) {
-            const float* t = s_win + (valid[k] ? (fy[k] - ylo) * kPitch + (fx[k] - xa) * C : 0);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                p_ff[c] = t[c]; p_cf[c] = t[C + c]; p_fc[c] = t[kPitch + c]; p_cc[c] = t[kPitch + C + c];
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double t = 0.0;
+            for (unsigned q = tid; q < gridDim.x; q += kThreads) t += __ldcg(fa.partials + q);   // thread-strided, fixed order
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            __syncthreads();
+            if (lane == 0) s_red[warp] = t;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < kWarps; ++w) tot += s_red[w];
+                *fa.loss_out = (float)(tot * (double)fa.inv_count);
+                *fa.counter = 0;          // ready for the next launch (stream-ordered)
             }
-        } else {  // tap box larger than the window: predicated gathers from global (L1/L2)
-            const bool fxi = fx[k] >= 0, cxi = cx <= g.W - 1, fyi = fy[k] >= 0, cyi = cy <= g.H - 1;
-            const float* base = data + (((long long)b * g.H + fy[k]) * g.W + fx[k]) * C;
-            const int rowf = g.W * C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                p_ff[c] = (valid[k] && fxi && fyi) ? __ldg(base + c) : 0.f;
-                p_cf[c] = (valid[k] && cxi && fyi) ? __ldg(base + C + c) : 0.f;
-                p_fc[c] = (valid[k] && fxi && cyi) ? __ldg(base + rowf + c) : 0.f;
-                p_cc[c] = (valid[k] && cxi && cyi) ? __ldg(base + rowf + C + c) : 0.f;
-            }
-        }
-        float* io = s_io + lane * kPIO + cq * C;
-        if (MODE == 0) {
-            const float w_ff = __fmul_rn(dx, dy), w_cc = __fmul_rn(omdx, omdy), w_fc = __fmul_rn(dx, omdy),
-                        w_cf = __fmul_rn(omdx, dy);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float v = __fmul_rn(w_ff, p_ff[c]);
-                v = __fadd_rn(v, __fmul_rn(w_cc, p_cc[c]));
-                v = __fadd_rn(v, __fmul_rn(w_fc, p_fc[c]));
-                v = __fadd_rn(v, __fmul_rn(w_cf, p_cf[c]));
-                io[c] = valid[k] ? v : 0.f;
-            }
-        } else if (MODE == 2) {
-            const float w_ff = __fmul_rn(dx, dy), w_cc = __fmul_rn(omdx, omdy), w_fc = __fmul_rn(dx, omdy),
-                        w_cf = __fmul_rn(omdx, dy);
-            const float* tg = s_aux + lane * kPIO + cq * C;
-            float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float v = __fmul_rn(w_ff, p_ff[c]);
-                v = __fadd_rn(v, __fmul_rn(w_cc, p_cc[c]));
-                v = __fadd_rn(v, __fmul_rn(w_fc, p_fc[c]));
-                v = __fadd_rn(v, __fmul_rn(w_cf, p_cf[c]));
-                v = valid[k] ? v : 0.f;
-                io[c] = v;
-                // loss and dL/dgen exactly as loss_flat_kernel (loss.cu): out-of-image pixels have gen = target = 0
-                const float d = __fsub_rn(v, tg[c]);
-                float gq;
-                if (fa.mode == DMV_LOSS_L2) {
-                    loss_acc = __fadd_rn(loss_acc, __fmul_rn(__fmul_rn(fa.w[c], d), d));
-                    gq = __fmul_rn(2.0f, d);
-                } else {
-                    loss_acc = __fadd_rn(loss_acc, __fmul_rn(fa.w[c], fabsf(d)));
-                    gq = (d > 0.f) ? 1.0f : (d < 0.f ? -1.0f : 0.0f);
-                }
-                const float gc = __fmul_rn(__fmul_rn(gq, fa.w[c]), fa.inv_count);
-                const float a0 = __fadd_rn(__fmul_rn(omdy, __fsub_rn(p_cc[c], p_fc[c])), __fmul_rn(dy, __fsub_rn(p_cf[c], p_ff[c])));
-                const float a1 = __fadd_rn(__fmul_rn(omdx, __fsub_rn(p_cc[c], p_cf[c])), __fmul_rn(dx, __fsub_rn(p_fc[c], p_ff[c])));
-                g0 = __fadd_rn(g0, __fmul_rn(gc, a0));
-                g1 = __fadd_rn(g1, __fmul_rn(gc, a1));
-            }
-            s_fl[lane * kPFL + cq] = valid[k] ? make_float2(g0, g1) : make_float2(0.f, 0.f);
-        } else {
-            float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float gc = io[c];
-                const float a0 = __fadd_rn(__fmul_rn(omdy, __fsub_rn(p_cc[c], p_fc[c])), __fmul_rn(dy, __fsub_rn(p_cf[c], p_ff[c])));
-                const float a1 = __fadd_rn(__fmul_rn(omdx, __fsub_rn(p_cc[c], p_cf[c])), __fmul_rn(dx, __fsub_rn(p_fc[c], p_ff[c])));
-                g0 = __fadd_rn(g0, __fmul_rn(gc, a0));
-                g1 = __fadd_rn(g1, __fmul_rn(gc, a1));
-            }
-            s_fl[lane * kPFL + cq] = valid[k] ? make_float2(g0, g1) : make_float2(0.f, 0.f);
         }
     }
-    __syncthreads();
-    // row-wise coalesced stores of the tiles the owner threads filled column-wise
-    if (MODE == 0 || MODE == 2) tr_store_tile<C>(s_io, out, g, b, i0, j0);
-    if (MODE >= 1) {
-        float* gw = (MODE == 2) ? fa.grad_wf : out;
-#pragma unroll
-        for (int k = 0; k < kPPT; ++k) {
-            const int r = warp + k * kWarps;
-            if (i0 + r < g.Ho && j0 + lane < g.Wo)
-                reinterpret_cast<float2*>(gw)[img_pix + (long long)(i0 + r) * g.Wo + j0 + lane] = s_fl[r * kPFL + lane];
-        }
-    }
-    if (MODE == 2) fused_loss_tail(fa, loss_acc);
+    if ((MODE == 0 || MODE == 2) && tid == 0) tc::bulk_commit_wait_read();   // the tile stays in shared memory until the store has read it
 }
 
 int encode_f32_map(CUtensorMap* map, const float* base, int inner, int rows, int batch, int box_inner, int box_rows) {
@@ -920,25 +693,6 @@ int launch_tile(const float* data, const float* wf, const float* go, float* out,
         if (rc) return rc;
         rc = encode_f32_map(&map_io, MODE == 0 ? out : go, g.Wo * g.C, g.Ho, g.B, 32 * g.C, 32);
         if (rc) return rc;
-        const bool tr = SAMPLER_TR && (g.flags & DMV_SAMPLER_ADD_GRID) && !(g.flags & DMV_SAMPLER_GRID_XY) && !di && !dm;
-        if (tr) {
-            // smem: window + io tile (padded) [+ flow tile for MODE 1; MODE 0 aliases it with the io tile]
-            const size_t tsm = (size_t)(kBoxL * kBoxL * g.C + 32 * (32 * g.C + 1) + 1) * sizeof(float) + (MODE == 1 ? 32 * 33 * sizeof(float2) : 0);
-#define DMV_LAUNCH_TR(CT)                                                                                \
-    do {                                                                                                 \
-        static bool attr_done = false;                                                                   \
-        if (!attr_done) {                                                                                \
-            cudaFuncSetAttribute(sampler_tr_kernel<CT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm); \
-            attr_done = true;                                                                            \
-        }                                                                                                \
-        sampler_tr_kernel<CT, MODE><<<grid, kThreads, tsm, st>>>(map_src, map_src_l, data, wf, go, out, g, FuseArgs()); \
-    } while (0)
-            if (g.C == 1) DMV_LAUNCH_TR(1);
-            else if (g.C == 3) DMV_LAUNCH_TR(3);
-            else DMV_LAUNCH_TR(4);
-#undef DMV_LAUNCH_TR
-            return check_launch(MODE == 0 ? "sampler_fwd(tr)" : "sampler_grad_warp(tr)");
-        }
         const size_t wsm = (size_t)(kBoxL * kBoxL + 32 * 32) * g.C * sizeof(float);
 #define DMV_LAUNCH_TMA(CT)                                                                               \
     do {                                                                                                 \
@@ -1074,25 +828,8 @@ int dmv_sampler_loss_fused(const float* data, const float* wf, const float* targ
     fa.counter = reinterpret_cast<unsigned*>(workspace);                 // fixed place: survives calls with other grid sizes
     fa.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
     fa.loss_out = loss_out; fa.grad_wf = grad_wf;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (SAMPLER_TR && (flags & DMV_SAMPLER_ADD_GRID) && !(flags & DMV_SAMPLER_GRID_XY)) {
-        const size_t tsm = (size_t)(kBoxL * kBoxL * C + 2 * 32 * (32 * C + 1) + 1) * sizeof(float) + 32 * 33 * sizeof(float2);
-#define DMV_LAUNCH_FTR(CT)                                                                                    \
-    do {                                                                                                      \
-        static bool attr_done = false;                                                                        \
-        if (!attr_done) {                                                                                     \
-            cudaFuncSetAttribute(sampler_tr_kernel<CT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm); \
-            attr_done = true;                                                                                 \
-        }                                                                                                     \
-        sampler_tr_kernel<CT, 2><<<grid, kThreads, tsm, st>>>(map_src, map_src_l, data, wf, target, gen_out, g, fa); \
-    } while (0)
-        if (C == 1) DMV_LAUNCH_FTR(1);
-        else if (C == 3) DMV_LAUNCH_FTR(3);
-        else DMV_LAUNCH_FTR(4);
-#undef DMV_LAUNCH_FTR
-        return check_launch("sampler_loss_fused(tr)");
-    }
     const size_t wsm = (size_t)(kBoxL * kBoxL + 2 * 32 * 32) * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
 #define DMV_LAUNCH_FUSED(CT)                                                                                  \
     do {                                                                                                      \
         static bool attr_done = false;                                                                        \

@@ -644,6 +644,30 @@ def fused_views_loss(gens, logits, target, mode="l2", weights=None, inv_count=No
     return _FusedLoss.apply(gens, logits, target, mask, tuple(weights), mode, inv_count, want_fused)
 
 
+# ----------------------------------------------------------------------------- input images
+def prepare_images(u8, size, out=None):
+    """read_tf_records.py:100-111 on the device: uint8 [..., H0, W0, C] as stored -> central crop to min(H0, W0) ->
+    tf.image.resize_bicubic to [size, size] -> float32 / 255.  One kernel; with H0 = W0 = size it is the plain
+    uint8 -> float32 / 255 conversion."""
+    _need_cuda(u8)
+    if u8.dtype != torch.uint8:
+        raise TypeError("prepare_images takes uint8 pixels")
+    u8 = u8.contiguous()
+    H0, W0, Cc = u8.shape[-3], u8.shape[-2], u8.shape[-1]
+    lead = tuple(u8.shape[:-3])
+    n = 1
+    for d in lead:
+        n *= int(d)
+    if out is None:
+        out = torch.empty(lead + (size, size, Cc), dtype=torch.float32, device=u8.device)
+    _tag[0] = "input"
+    if H0 == size and W0 == size and out.numel() % 4 == 0:
+        call("dmv_u8_to_f32", _p(u8), _p(out), out.numel(), 255.0, _stream(u8))
+    else:
+        call("dmv_u8_crop_resize_bicubic", _p(u8), _p(out), n, H0, W0, Cc, size, 255.0, _stream(u8))
+    return out
+
+
 # ----------------------------------------------------------------------------- casts (network inputs)
 def to_bf16(x):
     """fp32 -> bf16 for non-differentiable network inputs (viewpoint codes)."""

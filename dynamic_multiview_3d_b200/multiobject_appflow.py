@@ -97,6 +97,11 @@ class MultiObjectAppFlow(ModelBase):
         self.forward(batch)
         return self.build_loss(batch)
 
+    def visualize(self, *args, **kw):
+        """multiobject_appflow.py:289-393: imgdata.pkl with every clipped input / output (+ PNG panels)."""
+        from .visualize import visualize_multiobject
+        return visualize_multiobject(self, self._as_batch(args), **kw)
+
     # -- graph ---------------------------------------------------------------------------------
     def image_preprocessing(self, x, scope):
         """multiobject_appflow.py:80-87"""
@@ -253,6 +258,10 @@ class MultiViewFusionAppFlow(MultiObjectAppFlow):
         spec.update(image0_mask0=(Vw, B, H, H, 1), image0_mask1=(Vw, B, H, H, 1), displacement=(Vw, B, self.viewpoint_dim),
                     image1=(B, H, H, 3))
         return spec
+
+    def visualize(self, *args, **kw):
+        from .visualize import visualize_multiview
+        return visualize_multiview(self, self._as_batch(args), **kw)
 
     def decode_flowconf(self, src_img, x, scope):
         """One 3-channel head: flow (channels 0-1) + confidence logit (channel 2), SURVEY 8(f)-3."""

@@ -218,11 +218,18 @@ class TFRecordInput(object):
                     yield parse_example(rec)
 
     def _image(self, ex, name, chan):
+        """tf.decode_raw + reshape to the STORED size [ORIGINAL_HEIGHT, ORIGINAL_WIDTH, C] (read_tf_records.py:92-102; the
+        reference hard-codes 128 x 128, here conf['original_height'/'original_width'] or, for square records, the byte
+        count decides).  The crop + bicubic resize to the model's size and the / 255 (:103-111) run on the device
+        (dmv_u8_crop_resize_bicubic, one kernel) so that uint8 pixels are what crosses PCIe."""
         raw = np.frombuffer(ex[name], dtype=np.uint8)
-        side = self.size
-        if raw.size != side * side * chan:
-            raise ValueError("%s holds %d bytes, expected %dx%dx%d (resize is not implemented)" % (name, raw.size, side, side, chan))
-        return raw.reshape(side, side, chan)
+        h0, w0 = self.conf.get("original_height"), self.conf.get("original_width")
+        if h0 is None or w0 is None:
+            side = int(round(np.sqrt(raw.size // chan)))
+            h0 = w0 = side
+        if raw.size != h0 * w0 * chan:
+            raise ValueError("%s holds %d bytes, which is not %dx%dx%d; set conf['original_height'/'original_width']" % (name, raw.size, h0, w0, chan))
+        return raw.reshape(h0, w0, chan)
 
     def next_batch(self):
         cols = {k: [] for k in self.schema}
@@ -236,15 +243,15 @@ class TFRecordInput(object):
         out["displacement"] = np.stack(disp, 0)
         return out
 
-    def float_batch(self, device=None):
-        b = self.next_batch()
-        if device is None:
-            return {k: (v.astype(np.float32) / np.float32(255.0) if v.dtype == np.uint8 else v) for k, v in b.items()}
+    def float_batch(self, device):
+        """The reader's output as the reference's graph sees it: float32 images in [0,1] at the model's size
+        (read_tf_records.py:103-111: central crop, bicubic resize, / 255 -- one CUDA kernel), displacement float32."""
         import torch
+        from . import functional as F
         out = {}
-        for k, v in b.items():
+        for k, v in self.next_batch().items():
             t = torch.from_numpy(v).to(device, non_blocking=True)
-            out[k] = t.to(torch.float32).div_(255.0) if v.dtype == np.uint8 else t
+            out[k] = F.prepare_images(t, self.size) if v.dtype == np.uint8 else t
         return out
 
     __next__ = next_batch

@@ -79,18 +79,18 @@ class GraphedTrainStep:
     def _copy_in(self, batch):
         """Bring a batch into the graph's static fp32 buffers.  uint8 images (the reference's TFRecord pixel format,
         a quarter of the PCIe bytes) are converted on the device: float32(pixel) / 255 (read_tf_records.py:111)."""
-        from . import _lib
-        st = torch.cuda.current_stream(self.model.device).cuda_stream
+        from . import functional as F
         for k, dst in self.static.items():
             src = batch[k]
             if src.dtype == torch.uint8:
                 if not src.is_cuda:
                     buf = self._u8.get(k)
-                    if buf is None:
-                        buf = self._u8[k] = torch.empty(dst.shape, dtype=torch.uint8, device=dst.device)
+                    if buf is None or buf.shape != src.shape:
+                        buf = self._u8[k] = torch.empty(src.shape, dtype=torch.uint8, device=dst.device)
                     buf.copy_(src, non_blocking=True)
                     src = buf
-                _lib.call("dmv_u8_to_f32", src.data_ptr(), dst.data_ptr(), dst.numel(), 255.0, st)
+                # stored size != model size: central crop + bicubic resize + / 255 in the same kernel (read_tf_records.py:103-111)
+                F.prepare_images(src, dst.shape[-2], out=dst)
             else:
                 dst.copy_(src, non_blocking=True)
 
@@ -239,12 +239,14 @@ def build_model(conf, build_loss=True, device=None):
     return Model(conf, load_tfrec=True, build_loss=build_loss, device=device)
 
 
-def to_device_f32(batch, device):
-    """Host batch -> device float32 tensors (uint8 pixels / 255, read_tf_records.py:111) for the un-captured calls."""
+def to_device_f32(batch, device, size=None):
+    """Host batch -> device float32 tensors for the un-captured calls; uint8 pixels go through the reader's image
+    preparation on the device (crop + bicubic resize to ``size`` + / 255, read_tf_records.py:103-111)."""
+    from . import functional as F
     out = {}
     for k, v in batch.items():
         t = v.to(device, non_blocking=True)
-        out[k] = t.to(torch.float32).div_(255.0) if t.dtype == torch.uint8 else t
+        out[k] = F.prepare_images(t, size if size is not None else t.shape[-2]) if t.dtype == torch.uint8 else t
     return out
 
 
@@ -285,7 +287,8 @@ def main(argv=None):
         b = synthetic_batch(model, seed=99)
         info = model.visualize(*(torch.from_numpy(b[k]).to(model.device) for k in model.INPUT_KEYS))
         print("loss", info["loss"])
-        print("max resample coord:", info["max_resample_coord"])
+        if info.get("max_resample_coord") == info.get("max_resample_coord"):      # not NaN: the single-view flow models
+            print("max resample coord:", info["max_resample_coord"])
         return
     itr_0 = 0
     if args.pretrained:                       # train.py:95-103: resume AT the checkpoint's iteration
@@ -315,11 +318,11 @@ def main(argv=None):
     for itr in range(itr_0, conf["num_iterations"] + 1):
         t0 = time.time()
         batch = next_batch(itr)
-        loss = step(to_device_f32(batch, model.device)) if args.eager else step(batch)
+        loss = step(to_device_f32(batch, model.device, model.image_shape[0])) if args.eager else step(batch)
         if itr % 10 == 0 and rank == 0:
             print("%d %g" % (itr, float(loss)))
         if itr % VAL_INTERVAL == 0 and itr != 0:            # train.py:128-132: one validation batch, no update
-            vloss = float(model.eval_loss(to_device_f32(next_batch(itr, val=True), model.device)))
+            vloss = float(model.eval_loss(to_device_f32(next_batch(itr, val=True), model.device, model.image_shape[0])))
             if writer is not None:
                 writer.add_scalar("val_loss", vloss, itr)
         if itr % SAVE_INTERVAL == 0 and itr != 0:           # train.py:134-136 (collective under sharded data parallelism)

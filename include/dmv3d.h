@@ -211,6 +211,12 @@ int dmv_thin_s2d_prep(const void* thin, int thin_dtype, void* x2, int N, int H, 
 /* uint8 pixels -> float32, dst = src / divisor in IEEE division (tf.cast(image, tf.float32) / 255.0,
  * utils/read_tf_records.py:111): lets the input pipeline ship the reference's uint8 pixel format over PCIe. */
 int dmv_u8_to_f32(const unsigned char* src, float* dst, long long n, float divisor, void* stream);
+/* The reader's whole image preparation (utils/read_tf_records.py:100-111) in one kernel: uint8 [B,H0,W0,C] as stored ->
+ * central crop to min(H0,W0) (tf.image.resize_image_with_crop_or_pad) -> tf.image.resize_bicubic to [S,S] (TF-1.3 rule:
+ * legacy coordinates in = out * crop / S, Keys A = -0.75 from a 1024-entry table, clamped taps, horizontal then vertical,
+ * float32) -> / divisor.  With H0 = W0 = S (the reference's 128) it equals dmv_u8_to_f32 bit for bit.  C in {1,3,4}. */
+int dmv_u8_crop_resize_bicubic(const unsigned char* src, float* dst, int B, int H0, int W0, int C, int S, float divisor,
+                               void* stream);
 int dmv_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int dmv_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, void* stream);
 

@@ -330,3 +330,68 @@ def adam_lr_t(lr, t, beta1=0.9, beta2=0.999):
         p1 = f(p1 * f(beta1))
         p2 = f(p2 * f(beta2))
     return f(f(lr) * np.sqrt(f(1.0) - p2, dtype=np.float32) / (f(1.0) - p1))
+
+
+# --------------------------------------------------------------------------- #
+# input-side image preparation (utils/read_tf_records.py:88-112)
+# --------------------------------------------------------------------------- #
+_BICUBIC_TABLE = 1 << 10
+
+
+def _bicubic_coeffs():
+    """resize_bicubic_op.cc InitCoeffsTable [TF-upstream, recalled]: Keys kernel, A = -0.75, 1025 x 2 float32 entries."""
+    A = -0.75
+    tab = np.empty((_BICUBIC_TABLE + 1) * 2, np.float32)
+    for i in range(_BICUBIC_TABLE + 1):
+        x = float(np.float32(i * 1.0 / _BICUBIC_TABLE))
+        tab[i * 2] = np.float32(((A + 2) * x - (A + 3)) * x * x + 1)
+        x = float(np.float32(x + 1.0))
+        tab[i * 2 + 1] = np.float32(((A * x - 5 * A) * x + 8 * A) * x - 4 * A)
+    return tab
+
+
+def _bicubic_taps(scale, out_size, limit, tab):
+    """GetWeightsAndIndices for every output location: weights [out,4] float32, indices [out,4]."""
+    loc = np.arange(out_size, dtype=np.float32)
+    pos = (np.float32(scale) * loc).astype(np.float32)
+    in_loc = pos.astype(np.int64)                                      # int64 in_loc = scale * out_loc
+    delta = (pos - in_loc.astype(np.float32)).astype(np.float32)
+    offset = np.rint((delta * np.float32(_BICUBIC_TABLE)).astype(np.float32)).astype(np.int64)      # lrintf: round half to even
+    w = np.stack([tab[offset * 2 + 1], tab[offset * 2], tab[(_BICUBIC_TABLE - offset) * 2], tab[(_BICUBIC_TABLE - offset) * 2 + 1]], 1)
+    idx = np.clip(in_loc[:, None] + np.arange(-1, 3)[None, :], 0, limit - 1)
+    return w.astype(np.float32), idx
+
+
+def resize_bicubic_tf13(images, out_h, out_w):
+    """tf.image.resize_bicubic(images [B,H,W,C], [out_h, out_w]) with align_corners=False as TensorFlow 1.3 computes
+    it [TF-upstream, recalled]: legacy coordinates in = out * in_size / out_size, table-sampled Keys weights, clamped
+    taps, horizontal pass then vertical pass, float32 sums in index order.  Returns float32."""
+    x = np.asarray(images)
+    B, H, W, C = x.shape
+    tab = _bicubic_coeffs()
+    wy, iy = _bicubic_taps(np.float32(H) / np.float32(out_h), out_h, H, tab)
+    wx, ix = _bicubic_taps(np.float32(W) / np.float32(out_w), out_w, W, tab)
+    xf = x.astype(np.float32)
+    f = np.float32
+    rows = xf[:, iy]                                                   # [B, out_h, 4, W, C]
+    g = rows[:, :, :, ix]                                              # [B, out_h, 4, out_w, 4, C]
+    wxe = wx[None, None, None, :, :, None]
+    h = (g[..., 0, :] * wxe[..., 0, :]).astype(f)
+    for k in range(1, 4):
+        h = (h + (g[..., k, :] * wxe[..., k, :]).astype(f)).astype(f)  # [B, out_h, 4, out_w, C]
+    wye = wy[None, :, :, None, None]
+    out = (h[:, :, 0] * wye[:, :, 0]).astype(f)
+    for k in range(1, 4):
+        out = (out + (h[:, :, k] * wye[:, :, k]).astype(f)).astype(f)
+    return out
+
+
+def process_image(raw_u8, out_size):
+    """read_tf_records.py:100-111 on a batch of decoded uint8 images [B,H0,W0,C]: central crop to min(H0,W0)
+    (resize_image_with_crop_or_pad), resize_bicubic to [out_size, out_size], float32 / 255."""
+    x = np.asarray(raw_u8)
+    H0, W0 = x.shape[1], x.shape[2]
+    crop = min(H0, W0)
+    oy, ox = (H0 - crop) // 2, (W0 - crop) // 2
+    x = x[:, oy:oy + crop, ox:ox + crop]
+    return (resize_bicubic_tf13(x, out_size, out_size) / np.float32(255.0)).astype(np.float32)

@@ -259,6 +259,32 @@ def test_visualize_writes_the_reference_outputs(tmp_path):
     m = pkg.AppearanceFlowModel(conf, build_loss=False)
     b = _batch(B, H, V)
     info = m.visualize(*(torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")))
-    for name in ("output_120.png", "tr_gt_120.png", "tr_input_120.png", "flow_120.png"):
+    for name in ("output_120.png", "tr_gt_120.png", "tr_input_120.png", "flow_120.png", "quiver_120.png", "corr_plot_120.png"):
         assert os.path.getsize(os.path.join(str(tmp_path), name)) > 100
     assert np.isfinite(info["loss"]) and len(info["correspondences"]) == 6 and info["max_resample_coord"] < H + 5
+
+
+def test_multiobject_and_multiview_visualize(tmp_path):
+    """multiobject_appflow.py:289-393: imgdata.pkl with every clipped input and output (+ panels); config 5: grids."""
+    import pickle
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200.synthetic import make_multiobject_batch, make_multiview_multiobject_batch
+    B, H = 2, 64
+    conf = dict({"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": 2, "output_dir": str(tmp_path), "visualize": "model7"},
+                **MO_CONFS[0])
+    m = pkg.MultiObjectAppFlow(conf, build_loss=False)
+    t = {k: torch.from_numpy(v).cuda() for k, v in make_multiobject_batch(B, H).items()}
+    info = m.visualize(t)
+    d = pickle.load(open(os.path.join(str(tmp_path), "imgdata.pkl"), "rb"))
+    assert np.isfinite(info["loss"]) and {"image0", "gen_image1", "gen_depth1_only1", "gen_image1_mask0", "depth1_only0"} <= set(d)
+    assert all(v.min() >= 0.0 and v.max() <= 1.0 for v in d.values()) and d["gen_image1"].shape == (B, H, H, 3)
+    for name in ("img_exp_iter7_0.png", "depth_exp_iter7_1.png", "masks_exp_iter7_0.png"):
+        assert os.path.getsize(os.path.join(str(tmp_path), name)) > 100
+    conf5 = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": 2, "num_views": 3, "use_depth": 0.1,
+             "output_dir": str(tmp_path), "visualize": "model9"}
+    m5 = pkg.MultiViewFusionAppFlow(conf5, build_loss=False)
+    t5 = {k: torch.from_numpy(v).cuda() for k, v in make_multiview_multiobject_batch(B, H, 3).items()}
+    info5 = m5.visualize(t5)
+    assert abs(sum(info5["mean_confidence"]) - 1.0) < 1e-4
+    for name in ("output_9.png", "tr_gt_9.png", "tr_input_v2_9.png", "warp_v0_9.png", "confidence_v1_9.png"):
+        assert os.path.getsize(os.path.join(str(tmp_path), name)) > 100

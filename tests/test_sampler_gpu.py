@@ -121,11 +121,9 @@ def test_fused_grid_matches_warp_pts_layer(order):
 
 @pytest.mark.parametrize("C", [1, 3, 4])
 @pytest.mark.parametrize("regime", ["jitter", "rotation", "far", "boundary"])
-def test_reference_grid_transposed_lane_kernel(C, regime):
-    """The reference's (Y,X) grid fused into the kernel (flags = ADD_GRID) takes the transposed-lane kernel
-    (sampler_tr_kernel: lanes walk down output columns, padded shared tiles): forward and grad_warp bit-equal to the
-    oracle on a ragged, NON-square output over a non-square source (out[i,j] = bilinear(src, x = i + f0, y = j + f1)),
-    and bit-equal to the lanes-along-rows kernel the debug call takes."""
+def test_reference_grid_on_nonsquare_geometry(C, regime):
+    """The reference's (Y,X) grid fused into the kernel (flags = ADD_GRID) on a ragged, NON-square output over a
+    non-square source (out[i,j] = bilinear(src, x = i + f0, y = j + f1)): forward and grad_warp bit-equal to the oracle."""
     rng = np.random.default_rng(C * 31 + len(regime))
     B, H, W, Ho, Wo = 3, 52, 76, 72, 44                     # W*C, Wo*C multiples of 4; 32x32 tiles ragged on both sides
     data = rng.random((B, H, W, C), dtype=np.float32)

@@ -60,3 +60,25 @@ def test_flow_color_wheel():
     assert tuple(c[0, 0]) == (255, 0, 0)             # +x: hue 0 = red
     assert tuple(c[1, 1]) == (255, 255, 255)         # zero flow: unsaturated
     assert c[0, 1, 1] == 255 and c[1, 0, 2] == 255   # +y: hue 1/4 (green channel full), -x: hue 1/2 (cyan)
+
+
+def test_quiver_and_correspondence_figures():
+    """The reference's two matplotlib figures (appearance_flow_model.py:151-179), rasterised: arrows point along
+    (U, V) with y up, probes are joined from the generated image to the sampled source location."""
+    ii, jj = np.meshgrid(np.arange(32.0), np.arange(32.0), indexing="ij")
+    q = V.quiver_image(np.stack([np.ones_like(ii), np.zeros_like(ii)], -1), cell=10, stride=4)      # U = 1, V = 0: arrows to the right
+    ink = np.argwhere((q < 255).any(-1))
+    assert q.dtype == np.uint8 and q.shape == (8 * 10 + 10, 8 * 10 + 10, 3) and len(ink) > 8 * 8 * 5
+    rows = np.unique(ink[:, 0])
+    assert len(rows) < 8 * 9                             # horizontal arrows: ink only on the shaft rows and the barbs next to them
+    a, b = np.zeros((16, 16, 3)), np.ones((16, 16, 3))
+    c = V.corr_plot_image(a, b, [(4, 5)], [(10, 2)])
+    assert c.shape == (16, 16 * 2 + 8, 3)
+    assert tuple(c[10, 2]) == (230, 30, 30) and tuple(c[4, 16 + 8 + 5]) == (230, 30, 30)          # both end points carry the probe's colour
+    assert tuple(c[0, 0]) == (0, 0, 0) and tuple(c[0, 40 - 1]) == (255, 255, 255)
+
+
+def test_panel_layout():
+    p = V.panel([np.ones((4, 6, 3)), None, np.zeros((4, 6, 1))], 1, 3)
+    assert p.shape == (4 + 8, 3 * (6 + 4) + 4, 3)
+    assert tuple(p[5, 5]) == (255, 255, 255) and tuple(p[5, 4 + 2 * 10 + 1]) == (0, 0, 0)
