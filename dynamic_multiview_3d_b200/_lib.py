@@ -39,14 +39,14 @@ SIGNATURES = {
     "dmv_thin_s2d_size": (_sz, [_i] * 8),
     "dmv_thin_s2d_prep": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "dmv_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
-    "dmv_conv2d_dgrad": (_i, [_vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
+    "dmv_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp, _i] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_wgrad_workspace_size": (_sz, [_i] * 8),
     "dmv_conv2d_wgrad": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_deconv2d_fwd": (_i, [_vp, _vp, _vp, _i] + [_i] * 9 + [_vp, _sz, _i, _vp]),
-    "dmv_deconv2d_dgrad": (_i, [_vp, _i, _vp, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
+    "dmv_deconv2d_dgrad": (_i, [_vp, _i, _vp, _vp, _vp, _i] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_deconv2d_wgrad": (_i, [_vp, _vp, _i, _vp] + [_i] * 8 + [_vp, _sz, _i, _vp]),
     "dmv_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
-    "dmv_linear_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "dmv_linear_dgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "dmv_linear_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _i, _vp]),
     "dmv_act_fwd": (_i, [_vp, _vp, _i, _ll, _i, _vp]),
     "dmv_act_bwd": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),

@@ -100,7 +100,7 @@ class AppearanceFlowModel(ModelBase):
         e3_0 = conv2d_msra(e3, 128, 3, 3, 1, 1, "e3_0", act=a, algo=g)
         e4 = conv2d_msra(e3_0, 256, 3, 3, 2, 2, "e4", act=a, algo=g)
         e4_0 = conv2d_msra(e4, 256, 3, 3, 1, 1, "e4_0", act=a, algo=g)
-        e4r = e4_0.reshape(B, h5 * h5 * 256)                       # NHWC flatten, (h, w, c) order
+        e4r = F.reshape(e4_0, (B, h5 * h5 * 256))                       # NHWC flatten, (h, w, c) order
         e5 = linear_msra(e4r, 4096, "fc1", act=a, algo=g)
 
         concated = torch.cat([e5, self.decodeAngle(disp)], dim=1)
@@ -108,7 +108,7 @@ class AppearanceFlowModel(ModelBase):
         a3 = linear_msra(concated, 4096, "a3", act=a, algo=g)
         a4 = linear_msra(a3, 4096, "a4", act=a, algo=g)
         a5 = linear_msra(a4, h5 * h5 * 256, "a5", act=a, algo=g)
-        a5r = a5.reshape(B, h5, h5, 256)
+        a5r = F.reshape(a5, (B, h5, h5, 256))
 
         d4 = deconv2d_msra(a5r, [B, 2 * h5, 2 * h5, 128], 3, 3, 2, 2, "d4", act=a, algo=g)
         d4_0 = conv2d_msra(d4, 128, 3, 3, 1, 1, "d4_0", act=a, algo=g)
@@ -215,13 +215,13 @@ class AppearanceFlowTinghui(AppearanceFlowModel):
         e = image0
         for name, c in [("e0", 16), ("e1", 32), ("e2", 64), ("e3", 128), ("e4", 256)]:
             e = conv2d_msra(e, c, 3, 3, 2, 2, name, act="relu", algo=g)
-        e4r = e.reshape(B, (H // 32) ** 2 * 256)
+        e4r = F.reshape(e, (B, (H // 32) ** 2 * 256))
         e_fc0 = linear_msra(e4r, 2048, "e_fc0", act="relu", algo=g)
         e_fc1 = linear_msra(e_fc0, 2048, "e_fc1", act="relu", algo=g)
         concated = torch.cat([e_fc1, self.decodeAngle(disp)], dim=1)
         d_fc0 = linear_msra(concated, 2048, "a3", act="relu", algo=g)
         d_fc1 = linear_msra(d_fc0, (H // 16) ** 2 * 32, "a4", act="relu", algo=g)
-        d = d_fc1.reshape(B, H // 16, H // 16, 32)
+        d = F.reshape(d_fc1, (B, H // 16, H // 16, 32))
         d = deconv2d_msra(d, [B, H // 8, H // 8, 128], 3, 3, 2, 2, "d3", act="relu", algo=g)
         d = deconv2d_msra(d, [B, H // 4, H // 4, 64], 3, 3, 2, 2, "d2", act="relu", algo=g)
         d = deconv2d_msra(d, [B, H // 2, H // 2, 32], 3, 3, 2, 2, "d1", act="relu", algo=g)

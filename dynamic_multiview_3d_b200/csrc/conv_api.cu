@@ -9,6 +9,19 @@ using namespace dmv;
 #define DMV_CHECK_ALGO(algo) \
     DMV_REQUIRE((algo) == DMV_ALGO_AUTO || (algo) == DMV_ALGO_SIMT || (algo) == DMV_ALGO_TCGEN05, DMV_E_INVALID_ARG, "unknown algo")
 
+// Input gradients with the producer's activation derivative folded in: dx <- dx * act'(y_in).  ``run`` launches the
+// input-gradient kernels; the tensor-core paths apply the factor in their epilogue (before the bf16 rounding), any other
+// path is followed by one elementwise pass in place.
+template <typename F>
+static int dgrad_with_dact(const void* y_in, int act_in, void* dx, long long n, cudaStream_t st, F run) {
+    if (!y_in || act_in == DMV_ACT_NONE) return run();
+    tc_set_dact(y_in, act_in);
+    const int rc = run();
+    const bool fused = tc_finish_dact();
+    if (rc != DMV_OK || fused) return rc;
+    return dmv_act_bwd(dx, y_in, dx, DMV_DT_BF16, n, act_in, st);
+}
+
 extern "C" {
 
 size_t dmv_act_bwd_bias_workspace_size(long long rows, int C) { return rows > 0 && C > 0 ? act_bwd_bias_workspace(rows, C) : 0; }
@@ -88,16 +101,18 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias,
     return simt_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, st);
 }
 
-int dmv_conv2d_dgrad(const void* dy, const void* w, void* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
-                     void* workspace, size_t workspace_bytes, int algo, void* stream) {
+int dmv_conv2d_dgrad(const void* dy, const void* w, void* dx, const void* y_in, int act_in, int B, int H, int W, int Cin, int Cout,
+                     int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "conv2d_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
-        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
-    }
-    return simt_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, st);
+    return dgrad_with_dact(y_in, act_in, dx, (long long)B * H * W * Cin, st, [&]() -> int {
+        if (algo != DMV_ALGO_SIMT) {
+            int rc = tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+            if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+        }
+        return simt_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, st);
+    });
 }
 
 int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
@@ -150,25 +165,29 @@ int dmv_deconv2d_fwd(const void* x, const void* w, void* y, int y_dtype, int B, 
     return simt_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, st);
 }
 
-int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, int B, int Hout, int Wout, int Cin, int Cout,
-                       int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
+int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, const void* y_in, int act_in, int B, int Hout, int Wout,
+                       int Cin, int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "deconv2d_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dy_dtype == DMV_DT_S2D) {
+    if (dy_dtype == DMV_DT_S2D)
         DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cout), DMV_E_INVALID_ARG, "deconv2d_dgrad: DMV_DT_S2D needs the tensor-core thin path");
-        return tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace, workspace_bytes, st);
-    }
-    if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {   // flow head: dx = conv of the 2-channel gradient with w[r,s,c,ci]
-        int rc = tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
-                             workspace_bytes, st);
-        if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
-    }
-    if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
-        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
-    }
-    return simt_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, st);
+    const SamePad ph = same_pad(Hout, kh, stride), pw = same_pad(Wout, kw, stride);
+    return dgrad_with_dact(y_in, act_in, dx, (long long)B * ph.out * pw.out * Cin, st, [&]() -> int {
+        if (dy_dtype == DMV_DT_S2D)
+            return tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
+                               workspace_bytes, st);
+        if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {   // flow head: dx = conv of the 2-channel gradient with w[r,s,c,ci]
+            int rc = tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
+                                 workspace_bytes, st);
+            if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
+        }
+        if (algo != DMV_ALGO_SIMT) {
+            int rc = tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+            if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+        }
+        return simt_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, st);
+    });
 }
 
 int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, int B, int Hout, int Wout, int Cin, int Cout,
@@ -206,16 +225,18 @@ int dmv_linear_fwd(const void* x, const void* w, const float* bias, void* y, int
     return simt_conv_fwd(x, DMV_DT_BF16, w, bias, y, DMV_DT_BF16, M, 1, 1, K, N, 1, 1, 1, act, st);
 }
 
-int dmv_linear_dgrad(const void* dy, const void* w, void* dx, int M, int K, int N, void* workspace, size_t workspace_bytes, int algo,
-                     void* stream) {
+int dmv_linear_dgrad(const void* dy, const void* w, void* dx, const void* y_in, int act_in, int M, int K, int N, void* workspace,
+                     size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "linear_dgrad: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo != DMV_ALGO_SIMT) {
-        int rc = tc_linear_dgrad(dy, w, dx, M, K, N, workspace, workspace_bytes, st);
-        if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
-    }
-    return simt_conv_dgrad(dy, w, dx, M, 1, 1, K, N, 1, 1, 1, st);
+    return dgrad_with_dact(y_in, act_in, dx, (long long)M * K, st, [&]() -> int {
+        if (algo != DMV_ALGO_SIMT) {
+            int rc = tc_linear_dgrad(dy, w, dx, M, K, N, workspace, workspace_bytes, st);
+            if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
+        }
+        return simt_conv_dgrad(dy, w, dx, M, 1, 1, K, N, 1, 1, 1, st);
+    });
 }
 
 int dmv_linear_wgrad(const void* x, const void* dy, float* dw, float* db, int M, int K, int N, void* workspace,

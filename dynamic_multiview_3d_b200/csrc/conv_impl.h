@@ -56,6 +56,11 @@ int thin_s2d_gather_dw(const float* dw2, float* dw, int Ct, int Cw, int kh, int 
 int thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride,
                void* ws, size_t ws_bytes, cudaStream_t st);
 
+// Activation-derivative fusion for input-gradient launches: after tc_set_dact(y, act) the next tc_*_dgrad / thin dgrad
+// launch of this thread writes dX * act'(y) (y: bf16, same shape as dX); tc_finish_dact() tells whether a launch applied
+// it (a path that did not must be followed by an elementwise pass) and clears the request.
+void tc_set_dact(const void* y_bf16, int act);
+bool tc_finish_dact();
 size_t tc_wgrad_workspace(int taps, int Cin, int Cout, long long pixels);
 size_t tc_pack_workspace(int taps, int Cin, int Cout);
 int tc_conv_fwd(const void* x, int xdt, const void* w, const float* bias, void* y, int ydt, int B, int H, int W, int Cin, int Cout,

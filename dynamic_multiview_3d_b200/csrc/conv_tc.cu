@@ -63,7 +63,23 @@ struct IgemmParams {
     Tap taps[kMaxTaps];
     const float* bias;
     void* out;
+    // input-gradient launches: the bf16 result is multiplied by act'(dact_y[same index]) before it is rounded, i.e. the
+    // kernel writes dPre of the layer that produced this launch's input (dX * act'(Y)) instead of dX (NULL: off)
+    const bf16* dact_y;
+    int dact;
 };
+
+// act'(y) of 16 (or 8) consecutive bf16 outputs applied to the fp32 accumulators
+__device__ __forceinline__ void apply_dact8(float* f, const bf16* __restrict__ y, int act) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(y));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 v = __bfloat1622float2(h[k]);
+        f[2 * k] *= act_grad_from_output(v.x, act);
+        f[2 * k + 1] *= act_grad_from_output(v.y, act);
+    }
+}
 
 // Epilogue of one accumulator tile for one thread (= one output pixel): TMEM -> registers in 16-column
 // chunks, + bias (shared memory copy when the layer has a single N tile), activation (uniform switch hoisted
@@ -113,6 +129,15 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t tadd
             }
         } else {
             bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + ncol0 + c0;
+            if (p.dact_y) {
+                const bf16* yq = p.dact_y + opix * p.n_real + ncol0 + c0;
+                if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
+                    apply_dact8(f, yq, p.dact);
+                    apply_dact8(f + 8, yq + 8, p.dact);
+                } else {
+                    for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) f[k] *= act_grad_from_output(__bfloat162float(yq[k]), p.dact);
+                }
+            }
             if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
                 uint4 q0, q1;
                 __nv_bfloat162 h;
@@ -170,6 +195,10 @@ __device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t 
 #pragma unroll
                 for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(q + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
             } else {
+                if (p.dact_y) {
+                    apply_dact8(f, p.dact_y + o, p.dact);
+                    apply_dact8(f + 8, p.dact_y + o + 8, p.dact);
+                }
                 uint4 q0, q1;
                 __nv_bfloat162 h;
                 h = __floats2bfloat162_rn(f[0], f[1]); q0.x = *reinterpret_cast<uint32_t*>(&h);
@@ -191,7 +220,8 @@ __device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t 
                 if (oy >= p.out_H || ox >= p.out_W) continue;
                 const long long o = (((long long)n * p.out_H + oy) * p.out_W + ox) * C + cc;
                 if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = f[k];
-                else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(f[k]);
+                else reinterpret_cast<bf16*>(p.out)[o] =
+                    __float2bfloat16_rn(p.dact_y ? f[k] * act_grad_from_output(__bfloat162float(p.dact_y[o]), p.dact) : f[k]);
             }
         }
     }
@@ -228,6 +258,18 @@ __device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t 
                     for (int k = 0; k < 16; ++k) f[k] = tanhf(f[k]);
                     break;
                 default: break;
+            }
+            if (p.dact_y) {
+                // this thread's row is class-grid pixel (jh, jw); columns py*64 + q4*16 .. +15 are channels (q4 & 1) * 16 ..
+                // of output pixel (2 jh + py, 2 jw + (q4 >> 1))
+                const int m = quarter * 32 + lane;
+                const int jh = th * 16 + (m >> 3), jw = tw * 8 + (m & 7);
+                const int oy = 2 * jh + py, ox = 2 * jw + (q4 >> 1);
+                if (jh < p.Jh && jw < p.Jw && oy < p.out_H && ox < p.out_W) {
+                    const bf16* yq = p.dact_y + (((long long)n * p.out_H + oy) * p.out_W + ox) * 32 + (q4 & 1) * 16;
+                    apply_dact8(f, yq, p.dact);
+                    apply_dact8(f + 8, yq + 8, p.dact);
+                }
             }
             __nv_bfloat162 h;
             uint4 a, b;
@@ -597,13 +639,15 @@ __global__ void __launch_bounds__(kThreads, EPI ? 1 : 2) halo_kernel(const __gri
 
 // split-K finish: y[m][n] = act( sum_ks part[ks][m][n] + bias[n] ) in bf16, splits added in order
 __global__ void splitk_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias, bf16* __restrict__ y, long long mn, int N,
-                                     int splits, int act) {
+                                     int splits, int act, const bf16* __restrict__ dact_y, int dact) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += stride) {
         float s = 0.f;
         for (int z = 0; z < splits; ++z) s += part[(long long)z * mn + i];
         if (bias) s += __ldg(bias + (int)(i % N));
-        y[i] = __float2bfloat16_rn(apply_act(s, act));
+        s = apply_act(s, act);
+        if (dact_y) s *= act_grad_from_output(__bfloat162float(dact_y[i]), dact);
+        y[i] = __float2bfloat16_rn(s);
     }
 }
 
@@ -659,6 +703,12 @@ struct Problem {
     const float* bias; int act;
 };
 
+// The activation-derivative factor of the NEXT input-gradient launch of this thread (tc_set_dact): taken by launch_igemm
+// when it finalises the parameters of a bf16-output launch.
+thread_local const void* tl_dact_y = nullptr;
+thread_local int tl_dact = 0;
+thread_local bool tl_dact_taken = false;
+
 int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_bytes, cudaStream_t st) {
     const int Cc = q.Cs;                            // contraction channels per tap
     if (p.planes != 2) p.planes = 1;
@@ -684,6 +734,13 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     p.tiles_per_class = p.tiles_w * p.tiles_h * p.groups;
     p.out_mul = q.out_mul; p.out_H = q.out_H; p.out_W = q.out_W;
     p.act = q.act; p.out_f32 = q.out_f32; p.bias = q.bias; p.out = q.out;
+    p.dact_y = nullptr; p.dact = 0;
+    if (tl_dact_y && !q.out_f32) {
+        p.dact_y = reinterpret_cast<const bf16*>(tl_dact_y);
+        p.dact = tl_dact;
+        tl_dact_y = nullptr;
+        tl_dact_taken = true;
+    }
     const bool prepacked = q.b_mode_override == 3;      // w_hwio already holds the packed [n][K] K-major matrix
     p.b_mode = prepacked ? 0 : (q.b_mode_override >= 0 ? q.b_mode_override : (q.g_form ? 1 : 0));
 
@@ -839,6 +896,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     void* final_out = p.out;
     const float* final_bias = p.bias;
     const int final_act = p.act;
+    const bf16* final_dact_y = p.dact_y;
     if (q.k_splits > 1) {
         int ks = q.k_splits;
         if (ks > p.kc_per_tap / 4) ks = p.kc_per_tap / 4;
@@ -852,6 +910,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
             p.out_f32 = 1;
             p.bias = nullptr;
             p.act = DMV_ACT_NONE;
+            p.dact_y = nullptr;           // applied by the finish kernel, after the splits are summed
         }
     }
     // ---- shared memory / grid
@@ -887,7 +946,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         long long blocks = ceil_div_ll(mn, 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         splitk_finish_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), final_bias, reinterpret_cast<bf16*>(final_out), mn,
-                                                           q.n_real, p.k_splits, final_act);
+                                                           q.n_real, p.k_splits, final_act, final_dact_y, p.dact);
         return check_launch("splitk_finish");
     }
     return DMV_OK;
@@ -1119,6 +1178,18 @@ int launch_subpixel(const void* src, int N, int Hs, int Ws, int Cs, const void* 
 // entry points used by conv_api.cu
 // ----------------------------------------------------------------------------------------------
 namespace dmv {
+void tc_set_dact(const void* y_bf16, int act) {
+    tl_dact_y = (act != DMV_ACT_NONE) ? y_bf16 : nullptr;
+    tl_dact = act;
+    tl_dact_taken = false;
+}
+bool tc_finish_dact() {          // true when a launch applied the factor; clears the request either way
+    const bool taken = tl_dact_taken;
+    tl_dact_y = nullptr;
+    tl_dact_taken = false;
+    return taken;
+}
+
 
 
 size_t tc_pack_workspace(int taps, int Cin, int Cout) {

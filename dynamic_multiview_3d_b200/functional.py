@@ -215,10 +215,53 @@ def _anchor_for(t):
     return a
 
 
+# --- activation-derivative fusion between consecutive layers ----------------------------------------------------
+# Backward of a hidden layer L needs dPre_L = dY_L * act'(Y_L).  dY_L is the input gradient dX of the layer(s) that
+# consume Y_L, and Y_L is exactly their saved input -- so the consumer's dgrad kernel applies act'(its own input) in its
+# epilogue and hands back dPre_L directly (include/dmv3d.h, y_in / act_in); the producer then skips its elementwise
+# pass and only sums the bias gradient (on the weight-gradient side stream).  The hand-shake is a cell attached to the
+# producer's output tensor: a consuming layer that will fuse marks it in its forward; the producer reads it in its
+# backward.  Tensors that pass through torch ops (cat, chunk, slicing) carry no cell: both sides fall back to the
+# separate pass.  ``reshape`` below keeps the cell across a view.  A tagged tensor must not be fed to a fusing layer AND
+# used by a torch op directly (no graph of this package does).
+class _ActCell(object):
+    __slots__ = ("act", "fused")
+
+    def __init__(self, act):
+        self.act, self.fused = act, False
+
+
+def fuse_dact_enabled():
+    import os
+    return os.environ.get("DMV_FUSE_DACT", "1") == "1" and not _meta_depth[0]
+
+
+def _out_cell(act, out_dtype):
+    return _ActCell(act) if (act in ("lrelu", "relu") and out_dtype == torch.bfloat16 and fuse_dact_enabled()) else None
+
+
+def _claim_input(x):
+    """Consumer side, in forward: returns the producer's cell if this layer's dgrad will apply act'(x)."""
+    cell = getattr(x, "_dmv_cell", None)
+    if cell is None or not x.requires_grad or not torch.is_grad_enabled() or x.dtype != torch.bfloat16 or not x.is_contiguous():
+        return None
+    cell.fused = True
+    return cell
+
+
+def reshape(y, shape):
+    """y.reshape(shape) that keeps the activation cell when the result is a view of the same storage."""
+    r = y.reshape(shape)
+    cell = getattr(y, "_dmv_cell", None)
+    if cell is not None and r.data_ptr() == y.data_ptr() and r.is_contiguous():
+        r._dmv_cell = cell
+    return r
+
+
 # ----------------------------------------------------------------------------- conv / deconv / linear
 class _Conv2d(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, x, wvar, bvar, stride, act, algo, out_dtype):
+    def forward(ctx, anchor, x, wvar, bvar, stride, act, algo, out_dtype, in_cell, out_cell):
         _need_cuda(x)
         x = x.contiguous()
         B, H, W, Cin = x.shape
@@ -239,6 +282,7 @@ class _Conv2d(torch.autograd.Function):
         ctx.save_for_backward(x if ctx.needs_input_grad[1] or not n2 else xs, y, xs)
         ctx.xshape, ctx.xdtype, ctx.xs_dt = tuple(x.shape), x.dtype, xs_dt
         ctx.cfg = (wvar, bvar, stride, act, algo)
+        ctx.cells = (in_cell, out_cell)
         return y
 
     @staticmethod
@@ -251,7 +295,10 @@ class _Conv2d(torch.autograd.Function):
         _tag[0] = wvar.name
         dy = dy.contiguous()
         bias_done = False
-        if bvar is not None and ACT[act] and y.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and Cout % 8 == 0:
+        in_cell, out_cell = ctx.cells
+        if out_cell is not None and out_cell.fused and dy.dtype == torch.bfloat16:
+            dpre = dy                          # the consumer's dgrad epilogue already applied act'(y)
+        elif bvar is not None and ACT[act] and y.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and Cout % 8 == 0:
             dpre = torch.empty_like(y)
             rows = y.numel() // Cout
             ws = workspace(_lib.load().dmv_act_bwd_bias_workspace_size(rows, Cout), x.device)
@@ -270,7 +317,8 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx = torch.empty(ctx.xshape, dtype=torch.bfloat16, device=y.device)
             ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), y.device)
-            call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
+            call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
+                 ACT[in_cell.act] if in_cell is not None else 0, B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
             if ctx.xdtype != torch.bfloat16:
                 dxf = torch.empty(ctx.xshape, dtype=ctx.xdtype, device=y.device)
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
@@ -285,12 +333,12 @@ class _Conv2d(torch.autograd.Function):
             if bvar is not None:
                 store.notify_grad(bvar)
             store.notify_grad(wvar)
-        return None, dx, None, None, None, None, None, None
+        return None, dx, None, None, None, None, None, None, None, None
 
 
 class _Deconv2d(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, x, wvar, out_hw, stride, act, algo, out_dtype):
+    def forward(ctx, anchor, x, wvar, out_hw, stride, act, algo, out_dtype, in_cell, out_cell):
         _need_cuda(x)
         x = x.contiguous()
         if x.dtype != torch.bfloat16:
@@ -307,6 +355,7 @@ class _Deconv2d(torch.autograd.Function):
              ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
         ctx.cfg = (wvar, stride, act, algo)
+        ctx.cells = (in_cell, out_cell)
         return y
 
     @staticmethod
@@ -318,7 +367,10 @@ class _Deconv2d(torch.autograd.Function):
         st = _stream(x)
         _tag[0] = wvar.name
         dy = dy.contiguous()
-        if ACT[act]:
+        in_cell, out_cell = ctx.cells
+        if out_cell is not None and out_cell.fused and dy.dtype == torch.bfloat16:
+            dpre = dy
+        elif ACT[act]:
             dpre = torch.empty(y.shape, dtype=y.dtype, device=y.device)
             call("dmv_act_bwd", _p(dy), _p(y), _p(dpre), _dt(y), y.numel(), ACT[act], st)
         else:
@@ -334,8 +386,8 @@ class _Deconv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
             ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
-            call("dmv_deconv2d_dgrad", _p(dps), dps_dt, _p(wvar.half), _p(dx), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
-                 ws.numel(), algo, st)
+            call("dmv_deconv2d_dgrad", _p(dps), dps_dt, _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
+                 ACT[in_cell.act] if in_cell is not None else 0, B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
         wctx, wsf = _wgrad_ctx(x.device, x, dps)
         with wctx:
@@ -343,12 +395,12 @@ class _Deconv2d(torch.autograd.Function):
             call("dmv_deconv2d_wgrad", _p(x), _p(dps), dps_dt, _p(wvar.grad), B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws),
                  ws.numel(), algo, _stream(x))
             wvar.store.notify_grad(wvar)
-        return None, dx, None, None, None, None, None, None
+        return None, dx, None, None, None, None, None, None, None, None
 
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, x, wvar, bvar, act, algo):
+    def forward(ctx, anchor, x, wvar, bvar, act, algo, in_cell, out_cell):
         _need_cuda(x)
         x = x.contiguous()
         if x.dtype != torch.bfloat16:
@@ -363,6 +415,7 @@ class _Linear(torch.autograd.Function):
              _p(ws), ws.numel(), algo, _stream(x))
         ctx.save_for_backward(x, y)
         ctx.cfg = (wvar, bvar, act, algo)
+        ctx.cells = (in_cell, out_cell)
         return y
 
     @staticmethod
@@ -375,7 +428,10 @@ class _Linear(torch.autograd.Function):
         _tag[0] = wvar.name
         dy = dy.contiguous()
         bias_done = False
-        if bvar is not None and ACT[act] and N % 8 == 0:
+        in_cell, out_cell = ctx.cells
+        if out_cell is not None and out_cell.fused:
+            dpre = dy
+        elif bvar is not None and ACT[act] and N % 8 == 0:
             dpre = torch.empty_like(y)
             ws = workspace(_lib.load().dmv_act_bwd_bias_workspace_size(M, N), x.device)
             call("dmv_act_bwd_bias", _p(dy), _p(y), _p(dpre), _p(bvar.grad), M, N, ACT[act], _p(ws), ws.numel(), st)
@@ -389,7 +445,8 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx = torch.empty_like(x)
             ws = workspace(_lib.load().dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), x.device)
-            call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), M, K, N, _p(ws), ws.numel(), algo, st)
+            call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
+                 ACT[in_cell.act] if in_cell is not None else 0, M, K, N, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
         wctx, wsf = _wgrad_ctx(x.device, x, dpre)
         with wctx:
@@ -399,19 +456,29 @@ class _Linear(torch.autograd.Function):
             if bvar is not None:
                 wvar.store.notify_grad(bvar)
             wvar.store.notify_grad(wvar)
-        return None, dx, None, None, None, None
+        return None, dx, None, None, None, None, None, None
+
+
+def _tagged(y, cell):
+    if cell is not None:
+        y._dmv_cell = cell
+    return y
 
 
 def conv2d(x, wvar, bvar, stride, act=None, algo=None, out_dtype=torch.bfloat16):
-    return _Conv2d.apply(wvar.store.anchor, x, wvar, bvar, int(stride), act, _algo(algo), out_dtype)
+    cell = _out_cell(act, out_dtype)
+    return _tagged(_Conv2d.apply(wvar.store.anchor, x, wvar, bvar, int(stride), act, _algo(algo), out_dtype, _claim_input(x), cell), cell)
 
 
 def deconv2d(x, wvar, out_hw, stride, act=None, algo=None, out_dtype=torch.bfloat16):
-    return _Deconv2d.apply(wvar.store.anchor, x, wvar, (int(out_hw[0]), int(out_hw[1])), int(stride), act, _algo(algo), out_dtype)
+    cell = _out_cell(act, out_dtype)
+    return _tagged(_Deconv2d.apply(wvar.store.anchor, x, wvar, (int(out_hw[0]), int(out_hw[1])), int(stride), act, _algo(algo), out_dtype,
+                                   _claim_input(x), cell), cell)
 
 
 def linear(x, wvar, bvar, act=None, algo=None):
-    return _Linear.apply(wvar.store.anchor, x, wvar, bvar, act, _algo(algo))
+    cell = _out_cell(act, torch.bfloat16)
+    return _tagged(_Linear.apply(wvar.store.anchor, x, wvar, bvar, act, _algo(algo), _claim_input(x), cell), cell)
 
 
 # ----------------------------------------------------------------------------- activations

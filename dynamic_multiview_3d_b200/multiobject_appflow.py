@@ -159,11 +159,11 @@ class MultiObjectAppFlow(ModelBase):
             e4_1 = conv2d_msra(concated, 256, 3, 3, 1, 1, "e4_1", act=a, algo=g)
             a5r = conv2d_msra(e4_1, 256, 3, 3, 1, 1, "e4_2", act=a, algo=g)
         else:
-            e5 = linear_msra(e4_0.reshape(B, h5 * h5 * 256), 4096, "fc1", act=a, algo=g)
+            e5 = linear_msra(F.reshape(e4_0, (B, h5 * h5 * 256)), 4096, "fc1", act=a, algo=g)
             a3 = linear_msra(torch.cat([e5, a2], dim=1), 4096, "a3", act=a, algo=g)
             a4 = linear_msra(a3, 4096, "a4", act=a, algo=g)
             a5 = linear_msra(a4, h5 * h5 * 256, "a5", act=a, algo=g)
-            a5r = a5.reshape(B, h5, h5, 256)
+            a5r = F.reshape(a5, (B, h5, h5, 256))
         d4 = deconv2d_msra(a5r, [B, 2 * h5, 2 * h5, 128], 3, 3, 2, 2, "d4", act=a, algo=g)
         d4_0 = conv2d_msra(d4, 128, 3, 3, 1, 1, "d4_0", act=a, algo=g)
         d3 = deconv2d_msra(d4_0, [B, 4 * h5, 4 * h5, 64], 3, 3, 2, 2, "d3", act=a, algo=g)

@@ -18,13 +18,16 @@ from .variables import current_store
 
 def _rec(store, var, y):
     """Test hooks: ``store.record`` (dict) receives every layer's output under the layer's name; ``store.record_grad``
-    (dict) the gradient that output receives in backward."""
+    (dict) the gradient that output receives in backward -- (kind, tensor) with kind "pre" when the consuming layer's
+    dgrad already applied the activation derivative (functional.py: activation-derivative fusion; the tensor is then the
+    gradient w.r.t. the layer's PRE-activation), else "out"."""
     if store.record is not None:
         name = var.name.rsplit("/", 1)[0]
         store.record[name] = y
         rg = getattr(store, "record_grad", None)
         if rg is not None and y.requires_grad:
-            y.register_hook(lambda g, name=name: rg.__setitem__(name, g.detach()))
+            cell = getattr(y, "_dmv_cell", None)
+            y.register_hook(lambda g, name=name, cell=cell: rg.__setitem__(name, ("pre" if (cell is not None and cell.fused) else "out", g.detach())))
     return y
 
 

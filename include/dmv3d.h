@@ -156,10 +156,15 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w_bf16, const float* 
                    int y_dtype, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                    int stride, int act, void* workspace, size_t workspace_bytes, int algo,
                    void* stream);
-/* replaces Conv2DBackpropInput (implicit, appearance_flow_model.py:77) */
-int dmv_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int B, int H, int W,
-                     int Cin, int Cout, int kh, int kw, int stride, void* workspace,
-                     size_t workspace_bytes, int algo, void* stream);
+/* replaces Conv2DBackpropInput (implicit, appearance_flow_model.py:77).
+ * Input-gradient entry points (conv, deconv, linear) take `y_in` / `act_in`: when `y_in` (bf16, the layer's own INPUT
+ * as stored, i.e. the output of the producing layer's activation) is non-NULL and act_in != DMV_ACT_NONE they write
+ *     dx * act_in'(y_in)      -- the gradient w.r.t. the producer's PRE-activation (TF: the LeakyRelu/Relu grad node) --
+ * instead of dx, the factor applied to the fp32 accumulator in the epilogue before the single bf16 rounding.  This
+ * replaces a separate elementwise pass (6 B per element) over every hidden activation of the backward pass.        */
+int dmv_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, const void* y_in,
+                     int act_in, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                     void* workspace, size_t workspace_bytes, int algo, void* stream);
 /* replaces Conv2DBackpropFilter + BiasAddGrad.  dw f32 [kh,kw,Cin,Cout], db f32 [Cout] or NULL.
  * Deterministic split-K (fixed-order second pass).  workspace: dmv_wgrad_workspace_size.   */
 size_t dmv_wgrad_workspace_size(int B, int H, int W, int Cbig, int Csmall, int kh, int kw, int stride);
@@ -173,9 +178,10 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy_bf16, float* dw,
 int dmv_deconv2d_fwd(const void* x_bf16, const void* w_bf16, void* y, int y_dtype, int B, int Hout,
                      int Wout, int Cin, int Cout, int kh, int kw, int stride, int act,
                      void* workspace, size_t workspace_bytes, int algo, void* stream);
-int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w_bf16, void* dx_bf16, int B,
-                       int Hout, int Wout, int Cin, int Cout, int kh, int kw, int stride,
-                       void* workspace, size_t workspace_bytes, int algo, void* stream);
+int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w_bf16, void* dx_bf16,
+                       const void* y_in, int act_in, int B, int Hout, int Wout, int Cin, int Cout,
+                       int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo,
+                       void* stream);
 int dmv_deconv2d_wgrad(const void* x_bf16, const void* dy, int dy_dtype, float* dw, int B, int Hout,
                        int Wout, int Cin, int Cout, int kh, int kw, int stride, void* workspace,
                        size_t workspace_bytes, int algo, void* stream);
@@ -184,8 +190,9 @@ int dmv_deconv2d_wgrad(const void* x_bf16, const void* dy, int dy_dtype, float* 
 int dmv_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, void* y_bf16, int M,
                    int K, int N, int act, void* workspace, size_t workspace_bytes, int algo,
                    void* stream);
-int dmv_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, int M, int K, int N,
-                     void* workspace, size_t workspace_bytes, int algo, void* stream);
+int dmv_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, const void* y_in,
+                     int act_in, int M, int K, int N, void* workspace, size_t workspace_bytes,
+                     int algo, void* stream);
 int dmv_linear_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, float* db, int M, int K,
                      int N, void* workspace, size_t workspace_bytes, int algo, void* stream);
 

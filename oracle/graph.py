@@ -253,9 +253,11 @@ class Bf16TorchCpuOps(TorchCpuOps):
       * the input of every conv / deconv / FC (network inputs are cast: thin_s2d_prep, dmv_cast_f32_to_bf16; hidden
         activations are already bf16, the rounding is idempotent);
       * the output of every lrelu / relu epilogue (stored bf16); tanh / linear heads write fp32 and are NOT rounded;
-      * backward: the gradient arriving at a bf16 activation (the next layer's dX is written as bf16) and the gradient
-        leaving the activation derivative (dPre = dY * act'(Y) is written as bf16: dmv_act_bwd_bias / dmv_act_bwd,
-        and thin_s2d_prep for the fp32 heads) -- both dgrad and wgrad consume that rounded dPre.
+      * backward: the gradient leaving the activation derivative, dPre = dX_next * act'(Y), is written as bf16 -- by the
+        consuming layer's input-gradient epilogue, which applies act'(its input) to the fp32 accumulator before its one
+        rounding (include/dmv3d.h, y_in / act_in), or by thin_s2d_prep for the fp32 heads; both dgrad and wgrad consume
+        that rounded dPre.  (Where a torch op sits between two layers -- concat, channel split -- dX is rounded once more
+        before the factor is applied; the difference is below the test tolerances and not modelled.)
     Weight gradients, the sampler, the losses and Adam are fp32 on both sides."""
     name = "torch-cpu"
 
@@ -273,10 +275,10 @@ class Bf16TorchCpuOps(TorchCpuOps):
         return self.rb(super().linear(self.rf(x), self.rf(m), b))
 
     def lrelu(self, x):
-        return self.rfb(super().lrelu(x))
+        return self.rf(super().lrelu(x))
 
     def relu(self, x):
-        return self.rfb(super().relu(x))
+        return self.rf(super().relu(x))
 
 
 # --------------------------------------------------------------------------- #
@@ -389,6 +391,8 @@ class forcing:
     ``free[L]``, its gradients from the oracle's."""
 
     def __init__(self, record, grad_record=None):
+        """grad_record: name -> (kind, tensor); kind "out" = gradient w.r.t. the layer's output, "pre" = w.r.t. its
+        pre-activation (what an implementation with the activation derivative fused into the consumer's dgrad has)."""
         self.record, self.grad_record = record, grad_record
         self.free, self.free_grad = {}, {}
 
@@ -400,12 +404,12 @@ class forcing:
         _FORCE[0] = _FREE[0] = _FORCE_GRAD[0] = _FREE_GRAD[0] = None
 
 
-def _force_grad(ops, name, y):
+def _force_grad(ops, name, y, kind):
     gr, free = _FORCE_GRAD[0], _FREE_GRAD[0]
-    if gr is None or name not in gr:
+    if gr is None or name not in gr or gr[name][0] != kind:
         return y
     t = ops.t
-    g_forced = t.as_tensor(gr[name]).detach().to(t.float32)
+    g_forced = t.as_tensor(gr[name][1]).detach().to(t.float32)
     g_forced = ops.from_nhwc(g_forced) if g_forced.dim() == 4 else g_forced
 
     class ForceGrad(t.autograd.Function):
@@ -439,7 +443,7 @@ def _finish(ops, name, pre, act, acts=None):
             pc = t.where(yc > 0, yc, -t.ones_like(yc))
         else:
             pc = yc
-        y = _force_grad(ops, name, fn(pre + (pc - pre).detach()))
+        y = _force_grad(ops, name, fn(_force_grad(ops, name, pre + (pc - pre).detach(), "pre")), "out")
     return y
 
 

@@ -288,3 +288,29 @@ def test_multiobject_and_multiview_visualize(tmp_path):
     assert abs(sum(info5["mean_confidence"]) - 1.0) < 1e-4
     for name in ("output_9.png", "tr_gt_9.png", "tr_input_v2_9.png", "warp_v0_9.png", "confidence_v1_9.png"):
         assert os.path.getsize(os.path.join(str(tmp_path), name)) > 100
+
+
+@pytest.mark.parametrize("cls", ["AppearanceFlowModel", "AppearanceFlowTinghui"])
+def test_activation_derivative_fusion_matches_the_separate_pass(cls, monkeypatch):
+    """functional.py hand-shake: with the producer's act' applied in the consumer's dgrad epilogue (default) every
+    parameter gradient equals the one from the separate elementwise pass (DMV_FUSE_DACT=0) up to the one bf16 rounding
+    the fusion saves per layer, and fewer kernels are launched."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200 import _lib
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "seed": 11}
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    grads, launches = {}, {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DMV_FUSE_DACT", mode)
+        m = getattr(pkg, cls)(conf)
+        n0 = _lib.launch_count()
+        m.forward_and_loss(*args).backward()
+        torch.cuda.synchronize()
+        launches[mode] = _lib.launch_count() - n0
+        grads[mode] = {k: v.grad.clone() for k, v in m.store.vars.items()}
+    assert launches["1"] < launches["0"] - 10
+    for k in grads["1"]:
+        a, r = grads["1"][k], grads["0"][k]
+        assert float((a - r).norm() / (r.norm() + 1e-30)) < 5e-3, k

@@ -398,10 +398,11 @@ def test_bf16_aware_backend_rounds_where_the_cuda_path_stores_bf16():
     g = torch.as_tensor(rng.standard_normal(tuple(y16.shape)).astype(np.float32))
     (gw,) = torch.autograd.grad(y16, w, g)
     assert not torch.equal(gw, r(gw))                                   # fp32 weight gradient
-    # the gradient that reaches the conv is dPre = round(round(g) * act'(y)): compare with that fed to the fp32 backend
+    # the gradient that reaches the conv is dPre = round(g * act'(y)) (the factor is applied before the one rounding:
+    # the consumer's dgrad epilogue does it on the fp32 accumulator): compare with that fed to the fp32 backend
     y32b = ops32.conv(ops32.from_nhwc(x), w, bias, 1)
     slope = torch.where(y32b > 0, torch.ones_like(y32b), torch.full_like(y32b, 0.2))
-    (gw_ref,) = torch.autograd.grad(y32b, w, r(r(g) * slope))
+    (gw_ref,) = torch.autograd.grad(y32b, w, r(g * slope))
     assert torch.allclose(gw, gw_ref, rtol=1e-5, atol=1e-6)
 
 

@@ -191,7 +191,7 @@ def _record(model):
 def _records(model):
     torch.cuda.synchronize()
     acts = {k: v.detach().float().cpu() for k, v in model.store.record.items()}
-    grads = {k: v.detach().float().cpu() for k, v in model.store.record_grad.items()}
+    grads = {k: (kind, v.detach().float().cpu()) for k, (kind, v) in model.store.record_grad.items()}
     model.store.record = model.store.record_grad = None
     return acts, grads
 
@@ -215,8 +215,9 @@ def _check(model, tag, oracle_loss, outputs, lines):
         if not e < TOL:
             bad.append(("fwd " + name, e))
     for name in f.free_grad:
-        e = _rl2(_np(grads[name]), _np(nh(f.free_grad[name])))
-        lines.append("forced dgrad %-26s %.3e   |ref| %.3e" % (name, e, float(f.free_grad[name].norm())))
+        e = _rl2(_np(grads[name][1]), _np(nh(f.free_grad[name])))
+        lines.append("forced dgrad %-26s %.3e   |ref| %.3e   (w.r.t. %s)" % (name, e, float(f.free_grad[name].norm()),
+                                                                            "pre-activation, fused into the consumer's dgrad" if grads[name][0] == "pre" else "output"))
         if not e < TOL:
             bad.append(("dgrad into " + name, e))
     assert set(f.free) == set(acts) - {k for k in acts if k.endswith("/d0")}, sorted(set(acts) ^ set(f.free))

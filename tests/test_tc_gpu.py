@@ -194,3 +194,78 @@ def test_tc_linear_fwd_dgrad(M, K, N):
         assert _lib.tc_launch_count() >= n1 + 2, "linear dgrad / wgrad did not take the tensor-core path"
     gref = gy.float() @ wh.t()
     assert float((xt.grad.float() - gref).abs().max() / gref.abs().max()) < 1e-2
+
+
+DACT = [  # kind, k, s, H (big side), cin, cout : every input-gradient kernel form of the graph (halo, sub-pixel C=32 and generic,
+          # parity planes, per-tap igemm, thin space-to-depth head) at batch 8
+    ("conv", 5, 1, 112, 32, 32), ("conv", 5, 2, 112, 32, 32), ("conv", 5, 2, 56, 32, 64), ("conv", 3, 2, 28, 64, 128),
+    ("conv", 3, 1, 14, 128, 128), ("conv", 3, 1, 7, 256, 256), ("conv", 5, 1, 56, 32, 64),
+    ("deconv", 3, 2, 14, 256, 128), ("deconv", 5, 2, 56, 64, 32), ("deconv", 5, 2, 112, 64, 32), ("deconv", 5, 2, 224, 32, 2),
+]
+
+
+@pytest.mark.parametrize("kind,k,s,H,cin,cout", DACT)
+def test_dgrad_with_fused_activation_derivative(kind, k, s, H, cin, cout):
+    """include/dmv3d.h y_in / act_in: dgrad(..., y_in, lrelu) == act_bwd(dgrad(...), y_in) up to the rounding it saves
+    (the factor is applied to the fp32 accumulator): bit-identical where the slope is 1, within one bf16 ulp elsewhere."""
+    from dynamic_multiview_3d_b200 import _lib
+    L = _lib.load()
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(k + s + H + cin + cout)
+    st = torch.cuda.current_stream().cuda_stream
+    bf = torch.bfloat16
+    if kind == "conv":
+        xs, ys = (B, H, H, cin), (B, -(-H // s), -(-H // s), cout)
+        w = (torch.randn((k, k, cin, cout), device="cuda", generator=g) * T.conv_stddev(k, k, cin)).to(bf)
+    else:
+        xs, ys = (B, -(-H // s), -(-H // s), cin), (B, H, H, cout)
+        w = (torch.randn((k, k, cout, cin), device="cuda", generator=g) * T.deconv_stddev(k, k, cin, s, s)).to(bf)
+    y_in = torch.randn(xs, device="cuda", generator=g).to(bf)                       # the layer's input = the producer's lrelu output
+    dy = torch.randn(ys, device="cuda", generator=g).to(bf if cout >= 8 else torch.float32)
+    ws = torch.empty(max(L.dmv_conv_workspace_size(B, H, H, cin if kind == "conv" else cout, cout if kind == "conv" else cin, k, k, s), 256) + (64 << 20),
+                     dtype=torch.uint8, device="cuda")
+    outs = []
+    for fused in (False, True):
+        dx = torch.empty(xs, dtype=bf, device="cuda")
+        yp, act = (y_in.data_ptr(), 1) if fused else (None, 0)
+        if kind == "conv":
+            _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), yp, act, B, H, H, cin, cout, k, k, s, ws.data_ptr(), ws.numel(), 0, st)
+        else:
+            _lib.call("dmv_deconv2d_dgrad", dy.data_ptr(), 0 if dy.dtype == bf else 1, w.data_ptr(), dx.data_ptr(), yp, act, B, H, H, cin, cout, k, k, s,
+                      ws.data_ptr(), ws.numel(), 0, st)
+        if not fused:
+            _lib.call("dmv_act_bwd", dx.data_ptr(), y_in.data_ptr(), dx.data_ptr(), 0, dx.numel(), 1, st)
+        outs.append(dx.float())
+    two_pass, fused = outs
+    pos = y_in.float() > 0
+    assert torch.equal(two_pass[pos], fused[pos])
+    assert float(((two_pass - fused).abs() - 2.0 ** -7 * fused.abs()).max()) <= 0.0
+    assert float(fused.abs().max()) > 0
+
+
+@pytest.mark.parametrize("M,K,N", [(64, 12544, 4096), (64, 4096, 12544), (64, 4160, 4096), (64, 64, 64)])
+def test_linear_dgrad_with_fused_activation_derivative(M, K, N):
+    """The split-K linear input gradient applies the factor in its finish pass."""
+    from dynamic_multiview_3d_b200 import _lib
+    L = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    st = torch.cuda.current_stream().cuda_stream
+    bf = torch.bfloat16
+    w = (torch.randn((K, N), device="cuda", generator=g) * T.linear_stddev(K)).to(bf)
+    y_in = torch.randn((M, K), device="cuda", generator=g).to(bf)
+    dy = torch.randn((M, N), device="cuda", generator=g).to(bf)
+    ws = torch.empty(max(L.dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), 256), dtype=torch.uint8, device="cuda")
+    outs = []
+    for fused in (False, True):
+        dx = torch.empty((M, K), dtype=bf, device="cuda")
+        _lib.call("dmv_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), y_in.data_ptr() if fused else None, 1 if fused else 0, M, K, N,
+                  ws.data_ptr(), ws.numel(), 0, st)
+        if not fused:
+            _lib.call("dmv_act_bwd", dx.data_ptr(), y_in.data_ptr(), dx.data_ptr(), 0, dx.numel(), 1, st)
+        outs.append(dx.float())
+    two_pass, fused = outs
+    pos = y_in.float() > 0
+    assert torch.equal(two_pass[pos], fused[pos])
+    assert float(((two_pass - fused).abs() - 2.0 ** -7 * fused.abs()).max()) <= 0.0
+    ref = (dy.float() @ w.float().t()) * torch.where(pos, 1.0, 0.2)
+    assert float((fused - ref).abs().max() / ref.abs().max()) < 1e-2

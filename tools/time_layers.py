@@ -54,7 +54,7 @@ def conv(name, H, k, s, cin, cout, f32in=False):
     timeit(name + " fwd", lambda: _lib.call("dmv_conv2d_fwd", x.data_ptr(), xdt, w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, B, H, H, cin, cout,
                                             k, k, s, 1, ws.data_ptr(), ws.numel(), 0, st), flop)
     if not f32in:
-        timeit(name + " dgrad", lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, cin, cout, k, k, s,
+        timeit(name + " dgrad", lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), x.data_ptr(), 1, B, H, H, cin, cout, k, k, s,
                                                   ws.data_ptr(), ws.numel(), 0, st), flop)
     timeit(name + " wgrad", lambda: _lib.call("dmv_conv2d_wgrad", x.data_ptr(), xdt, dy.data_ptr(), dw.data_ptr(), None, B, H, H, cin, cout, k, k,
                                               s, ws.data_ptr(), ws.numel(), 0, st), flop)
@@ -73,7 +73,7 @@ def deconv(name, Ho, k, s, cin, cout, f32out=False):
     ydt = 1 if f32out else 0
     timeit(name + " fwd", lambda: _lib.call("dmv_deconv2d_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), ydt, B, Ho, Ho, cin, cout, k, k, s, 0,
                                             ws.data_ptr(), ws.numel(), 0, st), flop)
-    timeit(name + " dgrad", lambda: _lib.call("dmv_deconv2d_dgrad", dy.data_ptr(), ydt, w.data_ptr(), dx.data_ptr(), B, Ho, Ho, cin, cout, k, k, s,
+    timeit(name + " dgrad", lambda: _lib.call("dmv_deconv2d_dgrad", dy.data_ptr(), ydt, w.data_ptr(), dx.data_ptr(), x.data_ptr(), 1, B, Ho, Ho, cin, cout, k, k, s,
                                               ws.data_ptr(), ws.numel(), 0, st), flop)
     timeit(name + " wgrad", lambda: _lib.call("dmv_deconv2d_wgrad", x.data_ptr(), dy.data_ptr(), ydt, dw.data_ptr(), B, Ho, Ho, cin, cout, k, k, s,
                                               ws.data_ptr(), ws.numel(), 0, st), flop)
@@ -93,7 +93,7 @@ def linear(name, K, N):
     nb = K * N
     timeit(name + " fwd", lambda: _lib.call("dmv_linear_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, K, N, 1, ws.data_ptr(),
                                             ws.numel(), 0, st), flop)
-    timeit(name + " dgrad", lambda: _lib.call("dmv_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, K, N, ws.data_ptr(), ws.numel(),
+    timeit(name + " dgrad", lambda: _lib.call("dmv_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), x.data_ptr(), 1, M, K, N, ws.data_ptr(), ws.numel(),
                                               0, st), flop)
     timeit(name + " wgrad", lambda: _lib.call("dmv_linear_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), None, M, K, N, ws.data_ptr(),
                                               ws.numel(), 0, st), flop)
