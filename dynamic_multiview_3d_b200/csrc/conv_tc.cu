@@ -84,13 +84,39 @@ __device__ __forceinline__ void apply_dact8(float* f, const bf16* __restrict__ y
 // Epilogue of one accumulator tile for one thread (= one output pixel): TMEM -> registers in 16-column
 // chunks, + bias (shared memory copy when the layer has a single N tile), activation (uniform switch hoisted
 // out of the element loop), NHWC store (bf16 or fp32).
-__device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t taddr, bool ok, long long opix, int ncol0, int ks,
-                                             const float* __restrict__ s_bias) {
-    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+// act'(y) from an already loaded 16-byte group
+__device__ __forceinline__ void apply_dact8_reg(float* f, const uint4& q, int act) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 v = __bfloat1622float2(h[k]);
+        f[2 * k] *= act_grad_from_output(v.x, act);
+        f[2 * k + 1] *= act_grad_from_output(v.y, act);
+    }
+}
+
+// The epilogue warps know where a tile goes before its MMAs have finished: the first kPreCols columns of the dact factor
+// are fetched BEFORE the wait on the accumulator barrier, so their latency hides behind the tensor work.
+constexpr int kPreCols = 64;
+struct YPre {
+    uint4 v[kPreCols / 8];
+};
+__device__ __forceinline__ void prefetch_dact_row(const IgemmParams& p, bool ok, long long opix, int ncol0, YPre& y) {
+    if (!p.dact_y || p.out_f32 || !ok || (p.n_real & 7)) return;
+    const bf16* yq = p.dact_y + opix * p.n_real + ncol0;
+#pragma unroll
+    for (int j = 0; j < kPreCols / 8; ++j)
+        if (ncol0 + j * 8 + 8 <= p.n_real && j * 8 < p.n_pad) y.v[j] = __ldg(reinterpret_cast<const uint4*>(yq + j * 8));
+}
+
+template <bool PRE>
+__device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, uint32_t taddr, bool ok, long long opix, int ncol0, int ks,
+                                               const float* __restrict__ s_bias, int c0, const uint4& y0, const uint4& y1) {
+    {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (!ok) continue;
+        if (!ok) return;
         float f[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
@@ -132,8 +158,13 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t tadd
             if (p.dact_y) {
                 const bf16* yq = p.dact_y + opix * p.n_real + ncol0 + c0;
                 if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
-                    apply_dact8(f, yq, p.dact);
-                    apply_dact8(f + 8, yq + 8, p.dact);
+                    if (PRE) {
+                        apply_dact8_reg(f, y0, p.dact);
+                        apply_dact8_reg(f + 8, y1, p.dact);
+                    } else {
+                        apply_dact8(f, yq, p.dact);
+                        apply_dact8(f + 8, yq + 8, p.dact);
+                    }
                 } else {
                     for (int k = 0; k < 16 && ncol0 + c0 + k < p.n_real; ++k) f[k] *= act_grad_from_output(__bfloat162float(yq[k]), p.dact);
                 }
@@ -156,6 +187,15 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t tadd
             }
         }
     }
+}
+
+__device__ __forceinline__ void epilogue_row(const IgemmParams& p, uint32_t taddr, bool ok, long long opix, int ncol0, int ks,
+                                             const float* __restrict__ s_bias, const YPre& ypre) {
+    // the first kPreCols columns use the factors fetched before the accumulator wait (static register indices)
+#pragma unroll
+    for (int j = 0; j < kPreCols / 16; ++j)
+        if (j * 16 < p.n_pad) epilogue_chunk<true>(p, taddr, ok, opix, ncol0, ks, s_bias, j * 16, ypre.v[2 * j], ypre.v[2 * j + 1]);
+    for (int c0 = kPreCols; c0 < p.n_pad; c0 += 16) epilogue_chunk<false>(p, taddr, ok, opix, ncol0, ks, s_bias, c0, ypre.v[0], ypre.v[0]);
 }
 
 // Sub-pixel epilogue (stride-2 G forms run as ONE stride-1 problem, see launch_subpixel): the accumulator row of
@@ -232,9 +272,9 @@ __device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t 
 // pieces per instruction (the kernel was bound by L1 -> L2 write requests); instead each warp stages its 32 x 128 B in an
 // XOR-swizzled shared tile and writes it back with four full 128-byte lines per instruction.
 __device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t taddr, int n, int th, int tw, int quarter, int lane,
-                                                 uint4* __restrict__ s_epi) {
+                                                 uint4* __restrict__ s_epi, const uint4* __restrict__ ypre) {
     bf16* outp = reinterpret_cast<bf16*>(p.out);
-#pragma unroll 1
+#pragma unroll
     for (int py = 0; py < 2; ++py) {
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -265,10 +305,9 @@ __device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t 
                 const int m = quarter * 32 + lane;
                 const int jh = th * 16 + (m >> 3), jw = tw * 8 + (m & 7);
                 const int oy = 2 * jh + py, ox = 2 * jw + (q4 >> 1);
-                if (jh < p.Jh && jw < p.Jw && oy < p.out_H && ox < p.out_W) {
-                    const bf16* yq = p.dact_y + (((long long)n * p.out_H + oy) * p.out_W + ox) * 32 + (q4 & 1) * 16;
-                    apply_dact8(f, yq, p.dact);
-                    apply_dact8(f + 8, yq + 8, p.dact);
+                if (jh < p.Jh && jw < p.Jw && oy < p.out_H && ox < p.out_W) {     // fetched before the accumulator wait
+                    apply_dact8_reg(f, ypre[(py * 2 + (q4 >> 1)) * 4 + (q4 & 1) * 2], p.dact);
+                    apply_dact8_reg(f + 8, ypre[(py * 2 + (q4 >> 1)) * 4 + (q4 & 1) * 2 + 1], p.dact);
                 }
             }
             __nv_bfloat162 h;
@@ -448,10 +487,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             const int oy = p.out_mul * jh + c.py, ox = p.out_mul * jw + c.px;
             const bool ok = (m < p.rows) && (n < p.Nimg) && (jh < p.Jh) && (jw < p.Jw) && (oy < p.out_H) && (ox < p.out_W);
             const long long opix = ((long long)n * p.out_H + oy) * p.out_W + ox;
+            YPre ypre;
+            prefetch_dact_row(p, ok, opix, ncol0, ypre);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            epilogue_row(p, taddr, ok, opix, ncol0, ks, p.n_tiles == 1 ? s_bias : nullptr);
+            epilogue_row(p, taddr, ok, opix, ncol0, ks, p.n_tiles == 1 ? s_bias : nullptr, ypre);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -617,12 +658,29 @@ __global__ void __launch_bounds__(kThreads, EPI ? 1 : 2) halo_kernel(const __gri
             const int n = t, oy = th * 16 + bh, ox = tw * 8 + bw;
             const bool ok = (oy < p.out_H) && (ox < p.out_W);
             const long long opix = ((long long)n * p.out_H + oy) * p.out_W + ox;
+            YPre ypre;
+            uint4 ypre_d2s[EPI == 1 ? 16 : 1];
+            if (EPI == 1) {
+                if (p.dact_y) {                     // class-grid pixel (oy, ox) -> output pixels (2 oy + py, 2 ox + px), 64 bytes each
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int yy = 2 * oy + (q >> 1), xx = 2 * ox + (q & 1);
+                        if (oy < p.Jh && ox < p.Jw && yy < p.out_H && xx < p.out_W) {
+                            const uint4* yq = reinterpret_cast<const uint4*>(p.dact_y + (((long long)n * p.out_H + yy) * p.out_W + xx) * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ypre_d2s[q * 4 + j] = __ldg(yq + j);
+                        }
+                    }
+                }
+            } else if (!p.d2s) {
+                prefetch_dact_row(p, ok, opix, 0, ypre);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            if (EPI == 1) epilogue_d2s_c32(p, taddr, n, th, tw, quarter, lane, s_epi_all + (warp - 2) * 256);
+            if (EPI == 1) epilogue_d2s_c32(p, taddr, n, th, tw, quarter, lane, s_epi_all + (warp - 2) * 256, ypre_d2s);
             else if (p.d2s) epilogue_row_d2s(p, taddr, (oy < p.Jh) && (ox < p.Jw), n, oy, ox);
-            else epilogue_row(p, taddr, ok, opix, 0, 0, s_bias);
+            else epilogue_row(p, taddr, ok, opix, 0, 0, s_bias, ypre);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -224,6 +224,11 @@ def _anchor_for(t):
 # backward.  Tensors that pass through torch ops (cat, chunk, slicing) carry no cell: both sides fall back to the
 # separate pass.  ``reshape`` below keeps the cell across a view.  A tagged tensor must not be fed to a fusing layer AND
 # used by a torch op directly (no graph of this package does).
+# MEASURED (round 2, profiles/r02_dact_fusion.txt): with the present kernels the fusion LOSES -- the tensor-core kernels of
+# the wide layers are bound by their four epilogue warps, and the extra 2 B/element read there costs more (e1 dgrad
+# 29 -> 83 us, d1 dgrad 40 -> 75 us, flow head 59 -> 86 us; step 2.91 -> 3.22 ms) than the HBM-rate elementwise pass it
+# removes (6 B/element at 5.9 TB/s).  It is therefore OFF by default (DMV_FUSE_DACT=1 turns it on); the C ABI keeps the
+# capability and its tests -- the remedy is a producer-warp TMA load of the Y tile, not more epilogue loads.
 class _ActCell(object):
     __slots__ = ("act", "fused")
 
@@ -233,7 +238,7 @@ class _ActCell(object):
 
 def fuse_dact_enabled():
     import os
-    return os.environ.get("DMV_FUSE_DACT", "1") == "1" and not _meta_depth[0]
+    return os.environ.get("DMV_FUSE_DACT", "0") == "1" and not _meta_depth[0]
 
 
 def _out_cell(act, out_dtype):
