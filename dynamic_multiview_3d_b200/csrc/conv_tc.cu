@@ -33,6 +33,14 @@ using namespace dmv::tc;
 // ----------------------------------------------------------------------------------------------
 constexpr int kMaxTaps = 40;
 constexpr int kThreads = 192;
+// Activation-derivative factor in the input-gradient epilogues (IgemmParams::dact_y).  Compiled OUT by default: measured
+// slower than the separate HBM-rate elementwise pass with the present four-epilogue-warp kernels
+// (profiles/r02_dact_fusion.txt); the entry points then apply the factor with that pass, same results.  Build with
+// -DDMV_DACT_EPILOGUE=1 to get the fused epilogues.
+#ifndef DMV_DACT_EPILOGUE
+#define DMV_DACT_EPILOGUE 0
+#endif
+constexpr bool kDactEpilogue = DMV_DACT_EPILOGUE != 0;
 
 struct TapClass {
     int tap_begin, tap_count, k_elem_offset, py, px;
@@ -102,7 +110,7 @@ struct YPre {
     uint4 v[kPreCols / 8];
 };
 __device__ __forceinline__ void prefetch_dact_row(const IgemmParams& p, bool ok, long long opix, int ncol0, YPre& y) {
-    if (!p.dact_y || p.out_f32 || !ok || (p.n_real & 7)) return;
+    if (!kDactEpilogue || !p.dact_y || p.out_f32 || !ok || (p.n_real & 7)) return;
     const bf16* yq = p.dact_y + opix * p.n_real + ncol0;
 #pragma unroll
     for (int j = 0; j < kPreCols / 8; ++j)
@@ -155,7 +163,7 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, uint32_t ta
             }
         } else {
             bf16* o = reinterpret_cast<bf16*>(p.out) + opix * p.n_real + ncol0 + c0;
-            if (p.dact_y) {
+            if (kDactEpilogue && p.dact_y) {
                 const bf16* yq = p.dact_y + opix * p.n_real + ncol0 + c0;
                 if (ncol0 + c0 + 16 <= p.n_real && (p.n_real & 7) == 0) {
                     if (PRE) {
@@ -235,7 +243,7 @@ __device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t 
 #pragma unroll
                 for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(q + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
             } else {
-                if (p.dact_y) {
+                if (kDactEpilogue && p.dact_y) {
                     apply_dact8(f, p.dact_y + o, p.dact);
                     apply_dact8(f + 8, p.dact_y + o + 8, p.dact);
                 }
@@ -261,7 +269,7 @@ __device__ __forceinline__ void epilogue_row_d2s(const IgemmParams& p, uint32_t 
                 const long long o = (((long long)n * p.out_H + oy) * p.out_W + ox) * C + cc;
                 if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = f[k];
                 else reinterpret_cast<bf16*>(p.out)[o] =
-                    __float2bfloat16_rn(p.dact_y ? f[k] * act_grad_from_output(__bfloat162float(p.dact_y[o]), p.dact) : f[k]);
+                    __float2bfloat16_rn((kDactEpilogue && p.dact_y) ? f[k] * act_grad_from_output(__bfloat162float(p.dact_y[o]), p.dact) : f[k]);
             }
         }
     }
@@ -299,7 +307,7 @@ __device__ __forceinline__ void epilogue_d2s_c32(const IgemmParams& p, uint32_t 
                     break;
                 default: break;
             }
-            if (p.dact_y) {
+            if (kDactEpilogue && p.dact_y) {
                 // this thread's row is class-grid pixel (jh, jw); columns py*64 + q4*16 .. +15 are channels (q4 & 1) * 16 ..
                 // of output pixel (2 jh + py, 2 jw + (q4 >> 1))
                 const int m = quarter * 32 + lane;
@@ -661,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, EPI ? 1 : 2) halo_kernel(const __gri
             YPre ypre;
             uint4 ypre_d2s[EPI == 1 ? 16 : 1];
             if (EPI == 1) {
-                if (p.dact_y) {                     // class-grid pixel (oy, ox) -> output pixels (2 oy + py, 2 ox + px), 64 bytes each
+                if (kDactEpilogue && p.dact_y) {    // class-grid pixel (oy, ox) -> output pixels (2 oy + py, 2 ox + px), 64 bytes each
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int yy = 2 * oy + (q >> 1), xx = 2 * ox + (q & 1);
@@ -704,7 +712,7 @@ __global__ void splitk_finish_kernel(const float* __restrict__ part, const float
         for (int z = 0; z < splits; ++z) s += part[(long long)z * mn + i];
         if (bias) s += __ldg(bias + (int)(i % N));
         s = apply_act(s, act);
-        if (dact_y) s *= act_grad_from_output(__bfloat162float(dact_y[i]), dact);
+        if (kDactEpilogue && dact_y) s *= act_grad_from_output(__bfloat162float(dact_y[i]), dact);
         y[i] = __float2bfloat16_rn(s);
     }
 }
@@ -793,7 +801,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     p.out_mul = q.out_mul; p.out_H = q.out_H; p.out_W = q.out_W;
     p.act = q.act; p.out_f32 = q.out_f32; p.bias = q.bias; p.out = q.out;
     p.dact_y = nullptr; p.dact = 0;
-    if (tl_dact_y && !q.out_f32) {
+    if (kDactEpilogue && tl_dact_y && !q.out_f32) {
         p.dact_y = reinterpret_cast<const bf16*>(tl_dact_y);
         p.dact = tl_dact;
         tl_dact_y = nullptr;

@@ -227,8 +227,10 @@ def _anchor_for(t):
 # MEASURED (round 2, profiles/r02_dact_fusion.txt): with the present kernels the fusion LOSES -- the tensor-core kernels of
 # the wide layers are bound by their four epilogue warps, and the extra 2 B/element read there costs more (e1 dgrad
 # 29 -> 83 us, d1 dgrad 40 -> 75 us, flow head 59 -> 86 us; step 2.91 -> 3.22 ms) than the HBM-rate elementwise pass it
-# removes (6 B/element at 5.9 TB/s).  It is therefore OFF by default (DMV_FUSE_DACT=1 turns it on); the C ABI keeps the
-# capability and its tests -- the remedy is a producer-warp TMA load of the Y tile, not more epilogue loads.
+# removes (6 B/element at 5.9 TB/s).  It is therefore OFF by default (DMV_FUSE_DACT=1 turns the hand-shake on, and the
+# library must be built with -DDMV_DACT_EPILOGUE=1 for the fused epilogues -- otherwise the entry points apply the factor
+# with the elementwise pass themselves, same results); the C ABI keeps the capability and its tests.  The remedy is a
+# producer-warp TMA load of the Y tile, not more epilogue loads.
 class _ActCell(object):
     __slots__ = ("act", "fused")
 

@@ -160,8 +160,9 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w_bf16, const float* 
  * Input-gradient entry points (conv, deconv, linear) take `y_in` / `act_in`: when `y_in` (bf16, the layer's own INPUT
  * as stored, i.e. the output of the producing layer's activation) is non-NULL and act_in != DMV_ACT_NONE they write
  *     dx * act_in'(y_in)      -- the gradient w.r.t. the producer's PRE-activation (TF: the LeakyRelu/Relu grad node) --
- * instead of dx, the factor applied to the fp32 accumulator in the epilogue before the single bf16 rounding.  This
- * replaces a separate elementwise pass (6 B per element) over every hidden activation of the backward pass.        */
+ * instead of dx.  Library builds with -DDMV_DACT_EPILOGUE=1 apply the factor to the fp32 accumulator in the tensor-core
+ * epilogue (one rounding); the default build runs the elementwise pass (dmv_act_bwd, in place) behind the kernel --
+ * measured faster with the present kernels, profiles/r02_dact_fusion.txt.  Results agree to one bf16 ulp.            */
 int dmv_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, void* dx_bf16, const void* y_in,
                      int act_in, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
                      void* workspace, size_t workspace_bytes, int algo, void* stream);

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_exchange_kernel_emulated_ranks_equal_allreduce_then_adam(world):
     """``world`` ranks emulated on ONE device (every rank's buffers live on cuda:0, every rank's kernel on its own
     stream, the kernels wait on each other through the signal words exactly as across GPUs): after two steps every
