@@ -125,11 +125,14 @@ def side_stream_enabled():
 
 
 class side_stream:
-    """Context: run the enclosed launches on the device's side stream, ordered after everything enqueued so far on
-    the current stream.  ``keep`` are tensors the side work reads."""
+    """Context: run the enclosed launches on one of the device's side streams ("lanes"), ordered after everything
+    enqueued so far on the current stream.  ``keep`` are tensors the side work reads.  Lane 0 carries the convolution
+    weight gradients; lane 1 the weight gradients of the big FC matrices, so that they do not queue behind ~0.4 ms of
+    decoder convolution gradients: their chunks are 97 % of the bytes of the data-parallel exchange / of Adam's
+    traffic, and the earlier they are written the more of it hides behind the encoder's backward."""
 
-    def __init__(self, device, *keep):
-        key = (device.type, device.index)
+    def __init__(self, device, *keep, lane=0):
+        key = (device.type, device.index, lane)
         st = _side.get(key)
         if st is None:
             st = _side[key] = torch.cuda.Stream(device=device)
@@ -159,21 +162,21 @@ def reset_side_stream_state():
     """Start of a forward pass: forget a join that a failed backward pass left queued."""
     if _join_queued[0]:
         _join_queued[0] = False
-        for (kind, idx), st in list(_side.items()):
+        for (kind, idx, _lane), st in list(_side.items()):
             torch.cuda.current_stream(torch.device(kind, idx)).wait_stream(st)
         del _held[:]
 
 
 def _auto_join(device, main):
     _join_queued[0] = False
-    st = _side.get((device.type, device.index))
-    if st is not None:
-        main.wait_stream(st)
+    for (kind, idx, _lane), st in list(_side.items()):
+        if (kind, idx) == (device.type, device.index):
+            main.wait_stream(st)
     del _held[:]
 
 
-def side_workspace(nbytes, device):
-    key = ("side", device.type, device.index)
+def side_workspace(nbytes, device, lane=0):
+    key = ("side", device.type, device.index, lane)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -189,10 +192,16 @@ class _main_stream_ctx:
         return False
 
 
-def _wgrad_ctx(device, *keep):
+BIG_LINEAR = 1 << 20      # weights; linear layers this large take side-stream lane 1
+
+
+def _wgrad_ctx(device, *keep, lane=0):
     """(context manager, workspace function) for a weight-gradient launch."""
     if side_stream_enabled():
-        return side_stream(device, *keep), side_workspace
+        import os
+        if os.environ.get("DMV_FC_LANE", "1") != "1":
+            lane = 0
+        return side_stream(device, *keep, lane=lane), (lambda n, d, lane=lane: side_workspace(n, d, lane))
     return _main_stream_ctx(), workspace
 
 
@@ -455,7 +464,7 @@ class _Linear(torch.autograd.Function):
             call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
                  ACT[in_cell.act] if in_cell is not None else 0, M, K, N, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
-        wctx, wsf = _wgrad_ctx(x.device, x, dpre)
+        wctx, wsf = _wgrad_ctx(x.device, x, dpre, lane=1 if K * N >= BIG_LINEAR else 0)
         with wctx:
             ws = wsf(nws, x.device)
             call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,

@@ -19,11 +19,15 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 res = {}
-MODES = ("allreduce", "allreduce2", "sharded", "fused_p2p", "fused_p2p2", "fused_mc")
+MODES = ("allreduce", "allreduce2", "sharded", "fused_p2p", "fused_p2p2", "fused_mc", "fused_mc2")
+# Two ranks: a + b has one order, so every mode gives the same bits.  More ranks: NCCL's allreduce and reduce-scatter,
+# the switch's multimem reduction and the kernel's rank-order sum each fix their own fp32 order; three Adam steps at
+# lr 1e-3 turn that last-bit difference into ~1e-4 relative parameter difference (Adam's early updates are +-lr).
+TOL = 1e-5 if world <= 2 else 2e-3
 for mode in MODES:
-    os.environ["DMV_DP_MULTICAST"] = "1" if mode == "fused_mc" else "0"
+    os.environ["DMV_DP_MULTICAST"] = "1" if mode.startswith("fused_mc") else "0"
     model = pkg.AppearanceFlowModel({"batch_size": 4, "learning_rate": 1e-3, "image_size": 64, "viewpoint_dim": 19, "seed": 0})
-    red = data_parallel.attach(model, bucket_mb=4.0, mode=mode.rstrip("2").split("_")[0])
+    red = data_parallel.attach(model, bucket_mb=4.0, mode=mode.split("_")[0].rstrip("2"))
     if mode.startswith("fused") and rank == 0:
         print("mode %s: reducer %s, multicast %s" % (mode, type(red).__name__, getattr(getattr(red, "px", None), "multicast", None)), flush=True)
     b = make_batch(4, 64, "onehot19", seed=7, rank=rank)
@@ -49,14 +53,15 @@ if rank == 0:
         print("   diff %.3g %s %s" % r)
 err = float((pa - ps).abs().max() / pa.abs().max())
 print("rank %d losses allreduce %s sharded %s  max rel param diff %.3g" % (rank, la, ls, err))
-assert err < 1e-5, err
+assert err < TOL, err
 for mode in ("fused_p2p", "fused_mc"):
     lf, pf = res[mode]
     errf = float((pa - pf).abs().max() / pa.abs().max())
     print("rank %d losses %s %s  max rel param diff vs allreduce %.3g" % (rank, mode, lf, errf))
-    assert errf < 1e-5, (mode, errf)
+    assert errf < TOL, (mode, errf)
 assert torch.equal(res["fused_p2p"][1], res["fused_p2p2"][1]), "fused exchange is not bit-reproducible run to run"
 print("rank %d fused (fixed-order peer loads) run-to-run: bit-identical" % rank)
+print("rank %d fused (multimem in-switch reduction) run-to-run: %s" % (rank, "bit-identical" if torch.equal(res["fused_mc"][1], res["fused_mc2"][1]) else "DIFFERS"))
 dist.barrier()
 if rank == 0:
     print("check_dp ok")
