@@ -344,7 +344,12 @@ class PeerExchange:
         mc_g, mc_h = int(getattr(self.hg, "multicast_ptr", 0) or 0), int(getattr(self.hh, "multicast_ptr", 0) or 0)
         self.multicast = bool(use_multicast and mc_g and mc_h)
         self.grad_mc, self.half_mc = (mc_g, mc_h) if self.multicast else (None, None)
-        self.ctas = int(os.environ.get("DMV_DP_CTAS", "0"))
+        # Grid of the exchange kernel.  Alone it is fastest with every SM busy, but it runs NEXT TO the backward pass: at 8
+        # GPUs 64 CTAs give 2.83 ms/step where 148 give 3.09 and 592 give 3.33 (profiles/r02_bench_8gpu_c2_fused_mc_ctas*.json)
+        # -- fewer resident CTAs steal fewer issue slots from the tensor-core kernels' epilogue warps, and the transfer
+        # has the whole backward pass to finish in.  At 2 GPUs the kernel also carries half of Adam's HBM traffic and
+        # wants more (592: 2.97 ms, 64: 3.26 ms).  DMV_DP_CTAS overrides.
+        self.ctas = int(os.environ.get("DMV_DP_CTAS", "0")) or max(32, 512 // self.world)
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)            # every rank's signal words are zero before anyone signals
 
