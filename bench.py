@@ -451,7 +451,18 @@ def main():
             (dname, dtag), dms = ranked[0]
             gf = layer_gflop(BATCH) if args.config in (2, 3) else {}
             lname = dtag.split("/")[0]
-            if lname in gf:
+            if dname == "dmv_linear_wgrad_adam":
+                # the FC matrix's weight gradient + Adam in one pass (csrc/fc_adam.cu): SURVEY 8(d)'s 28 B/param minus the
+                # gradient that is never written or read = 24 B/param (theta, m, v in and out); the bf16 copy (2 B/param)
+                # is moved as well and reported separately.  The bf16 operands (x, dy: < 3 MB) stay in L2.
+                var = pmodel.store.vars[dtag]
+                nbytes = 24.0 * var.numel
+                gbs = nbytes / (dms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "kernel": "dmv_linear_wgrad_adam[%s]" % dtag, "achieved": round(gbs, 1), "peak": pk["hbm_gbs"],
+                        "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": ncu_traffic("fc_wgrad_adam_kernel"),
+                        "peak_src": pk["src"], "bytes_per_launch": nbytes, "bytes_moved_per_launch": 26.0 * var.numel,
+                        "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
+            elif lname in gf:
                 tf = gf[lname] / dms          # GFLOP / ms == TFLOP/s
                 peak = pk["bf16_tflops_sustained"]
                 roof = {"bound": "tensor", "kernel": "%s[%s]" % (dname, dtag), "achieved": round(tf, 2), "peak": peak,

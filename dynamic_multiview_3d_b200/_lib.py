@@ -57,6 +57,10 @@ SIGNATURES = {
     "dmv_adam_tick": (_i, [_vp, _f, _f, _f, _vp]),
     "dmv_adam_multi": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                             C.POINTER(_ll), _i, _vp, _f, _f, _f, _f, _vp]),
+    "dmv_adam_multi_gated": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                  C.POINTER(_ll), _i, _vp, _f, _f, _f, _f, _vp, _vp]),
+    "dmv_set_flag": (_i, [_vp, _i, _vp]),
+    "dmv_linear_wgrad_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _f, _f, _f, _vp]),
     "dmv_dp_signal_words": (_i, [_i]),
     "dmv_dp_exchange_chunk": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll,
                                    _i, _i, _i, _i, _vp, _f, _f, _f, _f, _i, _vp]),

@@ -85,6 +85,14 @@ class AppearanceFlowModel(ModelBase):
         a1 = linear_msra(a0, 64, "a1", act="lrelu", algo=self.algo)
         return linear_msra(a1, 64, "a2", act="lrelu", algo=self.algo)
 
+    def _viewpoint_code(self, disp):
+        """decodeAngle on a branch stream: independent of the image encoder until the concat (functional.branch)."""
+        if os.environ.get("DMV_VIEW_BRANCH", "1") != "1" or disp.device.type != "cuda":
+            return self.decodeAngle(disp)
+        with F.branch(disp.device, disp) as br:
+            code = self.decodeAngle(disp)
+        return br.join(code)
+
     def buildModel(self, image0, disp):
         """appearance_flow_model.py:83-127 with the shape rule; activations fused into the layers."""
         B, H = image0.shape[0], image0.shape[1]
@@ -103,7 +111,7 @@ class AppearanceFlowModel(ModelBase):
         e4r = F.reshape(e4_0, (B, h5 * h5 * 256))                       # NHWC flatten, (h, w, c) order
         e5 = linear_msra(e4r, 4096, "fc1", act=a, algo=g)
 
-        concated = torch.cat([e5, self.decodeAngle(disp)], dim=1)
+        concated = torch.cat([e5, self._viewpoint_code(disp)], dim=1)
 
         a3 = linear_msra(concated, 4096, "a3", act=a, algo=g)
         a4 = linear_msra(a3, 4096, "a4", act=a, algo=g)
@@ -218,7 +226,7 @@ class AppearanceFlowTinghui(AppearanceFlowModel):
         e4r = F.reshape(e, (B, (H // 32) ** 2 * 256))
         e_fc0 = linear_msra(e4r, 2048, "e_fc0", act="relu", algo=g)
         e_fc1 = linear_msra(e_fc0, 2048, "e_fc1", act="relu", algo=g)
-        concated = torch.cat([e_fc1, self.decodeAngle(disp)], dim=1)
+        concated = torch.cat([e_fc1, self._viewpoint_code(disp)], dim=1)
         d_fc0 = linear_msra(concated, 2048, "a3", act="relu", algo=g)
         d_fc1 = linear_msra(d_fc0, (H // 16) ** 2 * 32, "a4", act="relu", algo=g)
         d = F.reshape(d_fc1, (B, H // 16, H // 16, 32))

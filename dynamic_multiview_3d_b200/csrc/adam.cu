@@ -4,6 +4,8 @@
 // Bytes per parameter: read theta,g,m,v (16) + write theta,m,v (12) [+ 2 for the bf16 copy].
 // The step-dependent scalars live on the device (state4 = {b1^t, b2^t, lr_t, t}) and are
 // advanced by dmv_adam_tick, so a captured CUDA graph replays without host updates.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -20,6 +22,8 @@ struct AdamTable {
     int count;
 };
 
+__global__ void set_flag_kernel(int* flag, int value) { *flag = value; }
+
 __global__ void adam_tick_kernel(float* st, float lr, float b1, float b2) {
     // float32 running powers, as TF keeps beta1_power / beta2_power variables
     const float p1 = st[0] * b1, p2 = st[1] * b2;
@@ -30,7 +34,8 @@ __global__ void adam_tick_kernel(float* st, float lr, float b1, float b2) {
 }
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(AdamTable t, const float* __restrict__ state, float omb1, float omb2,
-                                                          float eps, float gscale) {
+                                                          float eps, float gscale, const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;      // deferred update with nothing pending (dmv_adam_multi_gated)
     const float lr_t = __ldg(state + 2);
     const long long total = t.start[t.count];
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -66,7 +71,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(AdamTable t, const floa
 
 // scalar tail / unaligned tensors
 __global__ void adam_scalar_kernel(float* P, const float* G, float* M, float* V, __nv_bfloat16* Hc, long long n,
-                                   const float* __restrict__ state, float omb1, float omb2, float eps, float gscale) {
+                                   const float* __restrict__ state, float omb1, float omb2, float eps, float gscale,
+                                   const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const float lr_t = __ldg(state + 2);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -139,9 +146,9 @@ int dmv_adam_tick(float* state4, float lr, float beta1, float beta2, void* strea
     return dmv::check_launch("adam_tick");
 }
 
-int dmv_adam_multi(float* const* params, const float* const* grads, float* const* m, float* const* v,
-                   void* const* bf16_copy, const long long* n, int count, const float* state4, float beta1, float beta2,
-                   float eps, float grad_scale, void* stream) {
+static int adam_multi_impl(float* const* params, const float* const* grads, float* const* m, float* const* v,
+                           void* const* bf16_copy, const long long* n, int count, const float* state4, float beta1, float beta2,
+                           float eps, float grad_scale, const int* gate, void* stream) {
     DMV_REQUIRE(params && grads && m && v && n && state4 && count >= 0, DMV_E_INVALID_ARG, "adam: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
@@ -166,19 +173,45 @@ int dmv_adam_multi(float* const* params, const float* const* grads, float* const
             if (tail > 0) {
                 const long long off = vec * 4;
                 adam_scalar_kernel<<<grid_for(tail, 256), 256, 0, st>>>(params[i] + off, grads[i] + off, m[i] + off, v[i] + off,
-                                                                         h ? h + off : nullptr, tail, state4, omb1, omb2, eps, grad_scale);
+                                                                         h ? h + off : nullptr, tail, state4, omb1, omb2, eps, grad_scale, gate);
                 int rc = dmv::check_launch("adam_scalar");
                 if (rc) return rc;
             }
             ++i;
         }
         if (t.count > 0) {
-            adam_multi_kernel<<<grid_for(t.start[t.count], 256), 256, 0, st>>>(t, state4, omb1, omb2, eps, grad_scale);
+            static int cap = -1;      // DMV_ADAM_CTAS: cap of the grid (A/B: room for co-resident tensor-core CTAs)
+            if (cap < 0) {
+                const char* e = getenv("DMV_ADAM_CTAS");
+                cap = e ? atoi(e) : 0;
+            }
+            int grid = grid_for(t.start[t.count], 256);
+            if (cap > 0 && grid > cap) grid = cap;
+            adam_multi_kernel<<<grid, 256, 0, st>>>(t, state4, omb1, omb2, eps, grad_scale, gate);
             int rc = dmv::check_launch("adam_multi");
             if (rc) return rc;
         }
     }
     return DMV_OK;
+}
+
+int dmv_adam_multi(float* const* params, const float* const* grads, float* const* m, float* const* v,
+                   void* const* bf16_copy, const long long* n, int count, const float* state4, float beta1, float beta2,
+                   float eps, float grad_scale, void* stream) {
+    return adam_multi_impl(params, grads, m, v, bf16_copy, n, count, state4, beta1, beta2, eps, grad_scale, nullptr, stream);
+}
+
+int dmv_adam_multi_gated(float* const* params, const float* const* grads, float* const* m, float* const* v,
+                         void* const* bf16_copy, const long long* n, int count, const float* state4, float beta1, float beta2,
+                         float eps, float grad_scale, const int* gate, void* stream) {
+    DMV_REQUIRE(gate, DMV_E_INVALID_ARG, "adam_multi_gated: null gate");
+    return adam_multi_impl(params, grads, m, v, bf16_copy, n, count, state4, beta1, beta2, eps, grad_scale, gate, stream);
+}
+
+int dmv_set_flag(int* flag, int value, void* stream) {
+    DMV_REQUIRE(flag, DMV_E_INVALID_ARG, "set_flag: null pointer");
+    set_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    return dmv::check_launch("set_flag");
 }
 
 int dmv_act_fwd(const void* x, void* y, int dtype, long long n, int act, void* stream) {

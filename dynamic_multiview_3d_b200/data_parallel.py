@@ -91,7 +91,7 @@ class GradientAllReducer:
         self.launched = []
 
 
-def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None, big=1 << 20):
+def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None, big=1 << 20, skip=()):
     """Chunks of the flat buffer for the sharded mode.  Returns (chunks, var2chunks, expected):
     chunks = [(start, end)] tiling [0, alloc) (every length a multiple of world*256), var2chunks maps a variable name to
     the chunks it overlaps, expected[c] = number of trainable variables overlapping chunk c.
@@ -109,6 +109,9 @@ def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None, big=1 << 2
     for name, off, n in var_table:
         if n >= big and off % unit == 0 and 0 < off < alloc:
             cuts.add(off)
+        if name in skip:            # updated elsewhere (optimizer.py, fused FC update): its range gets chunks of its own,
+            cuts.add(off)           # which nothing reports to and nothing launches
+            cuts.add(off + n)
     cuts = sorted(cuts)
     chunks = []
     for g0, g1 in zip(cuts, cuts[1:]):
@@ -119,7 +122,7 @@ def plan_chunks(var_table, alloc, chunk_elems, world, trainable=None, big=1 << 2
     import bisect
     var2chunks, expected = {}, [0] * len(chunks)
     for name, off, n in var_table:
-        if trainable is not None and name not in trainable:
+        if (trainable is not None and name not in trainable) or name in skip:
             continue
         cs = list(range(bisect.bisect_right(starts, off) - 1, bisect.bisect_right(starts, off + n - 1)))
         var2chunks[name] = cs
@@ -146,7 +149,13 @@ class ShardedGradientReducer:
         self.shard_end = getattr(store, "shard_end", store.alloc)
         table = [(v.name, v.offset, -(-v.numel // 64) * 64) for v in store.vars.values() if v.offset < self.shard_end]
         trainable = {v.name for v in store.trainable_vars()}
-        self.chunks, self.var2chunks, self.expected = plan_chunks(table, self.shard_end, int(chunk_mb * (1 << 20) / 4), self.world, trainable)
+        # single process: the FC matrices that Adam updates inside their weight-gradient kernel (optimizer.py) take no part
+        fused = {v.name for v in store.vars.values() if getattr(v, "fused_adam", False)}
+        assert not (fused and self.world > 1), "attach() clears the fused-update marks when gradients are exchanged"
+        for v in store.vars.values():
+            assert v.name not in fused or (v.offset % (self.world * 256) == 0 and v.numel % (self.world * 256) == 0), v.name
+        self.chunks, self.var2chunks, self.expected = plan_chunks(table, self.shard_end, int(chunk_mb * (1 << 20) / 4), self.world, trainable,
+                                                                  skip=fused)
         self.pending = list(self.expected)
         self.rep_names = {v.name for v in store.vars.values() if v.offset >= self.shard_end and v.name in trainable}
         self.rep_pending = len(self.rep_names)
@@ -156,6 +165,90 @@ class ShardedGradientReducer:
         self.native = (not dist.is_initialized()) or dist.get_backend(group) == "nccl"
         self.adam = None        # ShardedTFAdam: when attached, a chunk's update and bf16 all-gather follow its reduce-scatter
         self.started = False
+        self._plan_deferred()
+
+    # -- deferred updates (single process) ------------------------------------------------------------------------
+    # The late FC matrices (a3, a4, a5: 85 M of the 139 M parameters) finish their weight gradients in the middle of
+    # backward, and their HBM-bound Adam pass (2.5 GB) then competes with the HBM-bound FC backward itself: that stretch
+    # of the step ran at the memory roofline for ~0.7 ms with the tensor cores idle (profiles/r02_timeline_*.txt).
+    # Nothing reads those weights again until the FC layers of the NEXT forward pass, which starts with ~0.35 ms of
+    # tensor-bound encoder convolutions -- so their chunks are updated there: apply_deferred() launches them on the side
+    # stream at the start of the next train_step, each FC layer's forward waits for its own chunks, and the result is
+    # bit-identical to updating at the end of the step (same gradients, same step scalars: the tick of the next step
+    # comes after its forward).  The launches are gated on a device flag (dmv_adam_multi_gated) so that a captured CUDA
+    # graph can contain them unconditionally: the first replay, with nothing pending, skips them.
+    def _plan_deferred(self):
+        import os
+        self.deferred, self.var_wait, self.chunk_done = [], {}, {}
+        self.gate, self.pending_host = None, False
+        env = os.environ.get("DMV_DEFER_ADAM", "auto")
+        if self.world != 1 or not self.cuda or env == "0":
+            return
+        big = [v for v in self.store.vars.values() if v.trainable and v.offset < self.shard_end and v.numel >= (1 << 20)
+               and v.name.endswith("/Matrix") and not getattr(v, "fused_adam", False)]
+        names = set(env.split(",")) if env not in ("auto", "1") else {v.name for v in big[1:]}    # all but the first-created (fc1):
+        for v in big:                                                                              # its gradient comes last
+            if v.name not in names:
+                continue
+            cs = [c for c, (s, e) in enumerate(self.chunks) if v.offset <= s and e <= v.offset + v.numel and self.expected[c] > 0]
+            if cs:
+                self.deferred += cs
+                self.var_wait[v.name] = cs[-1]
+        self.deferred.sort()                       # ascending offset = the order the forward pass uses them in
+        if self.deferred:
+            self.gate = torch.zeros(1, dtype=torch.int32, device=self.flat["grad"].device)
+            self.store.pre_use_hook = self.wait_var
+
+    def apply_deferred(self):
+        """Start of a train step (and before any other use of the weights): launch the pending updates on the side stream."""
+        if not self.deferred or self.adam is None:
+            return
+        from . import functional as F
+        dev = self.flat["grad"].device
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            for c in self.deferred:
+                self.adam.update_chunk(c, self.comm_stream.cuda_stream, gate=self.gate)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+                self.chunk_done[c] = done
+            F._tag[0] = "adam"
+            F.call("dmv_set_flag", self.gate.data_ptr(), 0, self.comm_stream.cuda_stream)
+            self.all_done = torch.cuda.Event()
+            self.all_done.record(self.comm_stream)
+        self.pending_host = False
+
+    def wait_var(self, var):
+        """Forward pass, before a layer reads ``var``: its deferred update must have landed."""
+        c = self.var_wait.get(var.name)
+        if c is None:
+            return
+        if self.pending_host:                      # a forward pass outside train_step (validation, visualisation)
+            self.apply_deferred()
+        done = self.chunk_done.get(c)
+        if done is not None:
+            torch.cuda.current_stream(self.flat["grad"].device).wait_event(done)
+
+    def flush(self):
+        """Apply what is pending and join: parameters, moments and bf16 copies are those of the completed steps."""
+        if self.deferred and self.adam is not None:
+            if self.pending_host:
+                self.apply_deferred()
+            torch.cuda.current_stream(self.flat["grad"].device).wait_stream(self.comm_stream)
+
+    def reset_deferred(self):
+        """Forget pending updates (the parameters were restored from a snapshot)."""
+        if self.gate is not None:
+            self.gate.zero_()
+            self.pending_host = False
+            self.chunk_done, self.all_done = {}, None      # events recorded during a graph capture are not waitable outside it
+
+    def mark_pending(self):
+        """A captured step was replayed: its deferred update is pending on the device; the events of the capture are void."""
+        self.pending_host = True
+        self.chunk_done, self.all_done = {}, None
 
     def owned(self, c):
         s, e = self.chunks[c]
@@ -167,6 +260,8 @@ class ShardedGradientReducer:
         if not self.started:
             self.started = True
             if self.adam is not None:
+                if self.deferred and getattr(self, "all_done", None) is not None:   # the deferred updates read the step scalars
+                    torch.cuda.current_stream(self.flat["grad"].device).wait_event(self.all_done)
                 self.adam.tick()            # on the main stream, ahead of every chunk of this step
         if name in self.rep_names:
             self.rep_pending -= 1
@@ -196,6 +291,8 @@ class ShardedGradientReducer:
         main stream reads these weights again in this step and the whole tail overlaps the rest of backward."""
         if c >= 0:
             self.launched.append(c)
+            if self.deferred and c in self._deferred_chunks():
+                return                     # updated at the start of the next step (apply_deferred)
         if self.cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.flat["grad"].device))
@@ -219,9 +316,20 @@ class ShardedGradientReducer:
         self.started = False
         if self.cuda:
             torch.cuda.current_stream(self.flat["grad"].device).wait_stream(self.comm_stream)
+        if self.deferred and self.adam is not None:
+            from . import functional as F
+            F._tag[0] = "adam"
+            F.call("dmv_set_flag", self.gate.data_ptr(), 1, torch.cuda.current_stream(self.flat["grad"].device).cuda_stream)
+            self.pending_host = True
         self.order = list(self.launched)
         self.pending = list(self.expected)
         self.launched = []
+
+    def _deferred_chunks(self):
+        ds = getattr(self, "_deferred_set", None)
+        if ds is None or len(ds) != len(self.deferred):
+            ds = self._deferred_set = set(self.deferred)
+        return ds
 
     def all_gather(self, key, c):
         """In-place all-gather of chunk c of flat[key] from the owners' slices."""
@@ -239,6 +347,7 @@ class ShardedGradientReducer:
 
     def gather_full_state(self):
         """Checkpoint time: every rank gets the complete fp32 masters and Adam moments."""
+        self.flush()
         for c in range(len(self.chunks)):
             if self.expected[c] > 0:
                 for key in ("master", "m", "v"):
@@ -276,11 +385,31 @@ class ShardedTFAdam:
         F._tag[0] = "adam"
         F.call("dmv_adam_tick", self.state.data_ptr(), self.lr, self.beta1, self.beta2, st)
 
-    def update_chunk(self, c, st):
+    def begin_step(self):
+        """Before backward (ModelBase.train_step): advance the step scalars; arm the fused FC update (optimizer.py)."""
+        red = self.red
+        if red.cuda:
+            # the tick goes on the stream train_step runs on, ahead of backward: every chunk's update -- whichever
+            # weight-gradient lane triggers it -- is ordered behind it
+            if red.deferred and getattr(red, "all_done", None) is not None:   # the deferred updates read the previous scalars
+                torch.cuda.current_stream(red.flat["grad"].device).wait_event(red.all_done)
+            self.tick()
+            red.started = True
+        if self.base.fused_vars():
+            red.store.adam_live = self
+
+    def end_backward(self):
+        self.red.store.adam_live = None
+
+    def update_chunk(self, c, st, gate=None):
         from . import functional as F
         p, g, m, v, h, n = self.args[c]
         F._tag[0] = "adam"
-        F.call("dmv_adam_multi", p, g, m, v, h, n, 1, self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale, st)
+        if gate is not None:
+            F.call("dmv_adam_multi_gated", p, g, m, v, h, n, 1, self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale,
+                   gate.data_ptr(), st)
+        else:
+            F.call("dmv_adam_multi", p, g, m, v, h, n, 1, self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale, st)
 
     def step(self):
         """Called after ShardedGradientReducer.finish(): the sharded chunks are already updated and gathered (side
@@ -403,6 +532,8 @@ def attach(model, bucket_mb=32.0, group=None, mode=None):
     import os
     store = model.store
     mode = mode or os.environ.get("DMV_DP_MODE", "fused")
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(model.optimizer, "disable_fusion"):
+        model.optimizer.disable_fusion()       # the gradients of the FC matrices must exist in memory to be exchanged
     if mode == "fused" and not (dist.is_initialized() and dist.get_world_size(group) > 1 and store.flat["grad"].is_cuda
                                 and model.optimizer is not None):
         mode = "sharded"

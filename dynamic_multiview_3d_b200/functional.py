@@ -115,6 +115,8 @@ def _p(t):
 # own scratch buffer, and the tensors it reads are kept alive until the join (the caching allocator does not know that
 # another stream still uses them).
 _side = {}
+_used = set()          # keys of _side whose stream took work in the current pass (only those are joined: a stream that
+                       # was not forked inside a graph capture must not be waited on inside it)
 _held = []
 _join_queued = [False]
 
@@ -136,7 +138,7 @@ class side_stream:
         st = _side.get(key)
         if st is None:
             st = _side[key] = torch.cuda.Stream(device=device)
-        self.stream, self.device = st, device
+        self.stream, self.device, self.key = st, device, key
         _held.extend(t for t in keep if t is not None)
 
     def __enter__(self):
@@ -150,6 +152,7 @@ class side_stream:
         ev = torch.cuda.Event()
         ev.record(main)
         self.stream.wait_event(ev)
+        _used.add(self.key)
         self.ctx = torch.cuda.stream(self.stream)
         self.ctx.__enter__()
         return self.stream
@@ -158,20 +161,69 @@ class side_stream:
         return self.ctx.__exit__(*a)
 
 
+class branch:
+    """Context: run an independent branch of the forward graph on its own stream, forked behind everything enqueued so
+    far on the current stream; ``join(t)`` makes the current stream wait for it and hands the result over.
+
+    The viewpoint FCs (three 64-wide linear layers on a [B, V] code) are single-CTA kernels: 26 us of pure latency in the
+    forward pass and -- because autograd replays a node on the stream its forward ran on -- ~200 us of the critical chain
+    in backward, where they sat between the a3 and fc1 input gradients with the rest of the GPU idle
+    (profiles/r02_timeline_immediate.txt).  On a branch stream they run next to the encoder (forward) and next to fc1's
+    backward.  The stream is joined with the weight-gradient lanes when backward ends (_auto_join)."""
+
+    def __init__(self, device, *inputs):
+        self.device = device
+        self.on = side_stream_enabled() and device.type == "cuda"
+        if self.on:
+            key = (device.type, device.index, "branch")
+            st = _side.get(key)
+            if st is None:
+                st = _side[key] = torch.cuda.Stream(device=device)
+            self.stream, self.key = st, key
+            for t in inputs:
+                t.record_stream(st)
+
+    def __enter__(self):
+        if self.on:
+            self.main = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.stream.wait_event(ev)
+            _used.add(self.key)
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.done = torch.cuda.Event()
+            self.done.record(self.stream)
+            return self.ctx.__exit__(*a)
+        return False
+
+    def join(self, t):
+        if self.on:
+            self.main.wait_event(self.done)
+            t.record_stream(self.main)
+        return t
+
+
 def reset_side_stream_state():
     """Start of a forward pass: forget a join that a failed backward pass left queued."""
     if _join_queued[0]:
         _join_queued[0] = False
-        for (kind, idx, _lane), st in list(_side.items()):
-            torch.cuda.current_stream(torch.device(kind, idx)).wait_stream(st)
+        for key in list(_used):
+            torch.cuda.current_stream(torch.device(key[0], key[1])).wait_stream(_side[key])
         del _held[:]
+    _used.clear()
 
 
 def _auto_join(device, main):
     _join_queued[0] = False
-    for (kind, idx, _lane), st in list(_side.items()):
-        if (kind, idx) == (device.type, device.index):
-            main.wait_stream(st)
+    for key in list(_used):
+        if (key[0], key[1]) == (device.type, device.index):
+            main.wait_stream(_side[key])
+            _used.discard(key)
     del _held[:]
 
 
@@ -206,8 +258,9 @@ def _wgrad_ctx(device, *keep, lane=0):
 
 
 def workspace(nbytes, device):
-    """One growable scratch buffer per device (all launches are stream-ordered on one stream)."""
-    key = (device.type, device.index)
+    """One growable scratch buffer per device AND stream: launches that share it are ordered on that stream (the
+    forward / dgrad chain on the main stream, an independent branch of the graph on its own)."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -426,6 +479,8 @@ class _Linear(torch.autograd.Function):
         assert wk == K, (wvar.name, wvar.shape, x.shape)
         y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
         _tag[0] = wvar.name
+        if wvar.store.pre_use_hook is not None:
+            wvar.store.pre_use_hook(wvar)        # a deferred optimizer update of this matrix must have landed
         ws = workspace(_lib.load().dmv_conv_workspace_size(M, 1, 1, K, N, 1, 1, 1), x.device)
         call("dmv_linear_fwd", _p(x), _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), M, K, N, ACT[act],
              _p(ws), ws.numel(), algo, _stream(x))
@@ -465,13 +520,25 @@ class _Linear(torch.autograd.Function):
                  ACT[in_cell.act] if in_cell is not None else 0, M, K, N, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
         wctx, wsf = _wgrad_ctx(x.device, x, dpre, lane=1 if K * N >= BIG_LINEAR else 0)
+        live = wvar.store.adam_live if wvar.fused_adam else None
         with wctx:
             ws = wsf(nws, x.device)
-            call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,
-                 _p(ws), ws.numel(), algo, _stream(x))
-            if bvar is not None:
-                wvar.store.notify_grad(bvar)
-            wvar.store.notify_grad(wvar)
+            if live is not None:
+                # single-process training: Adam consumes the weight-gradient tile in registers (optimizer.py); the gradient
+                # of this matrix is never written.  Ordered after the dgrad above, which reads the bf16 weights it rewrites.
+                if bvar is not None and not bias_done:        # bias gradient alone: column sums of dPre (act' == 1, in place)
+                    bws = wsf(_lib.load().dmv_act_bwd_bias_workspace_size(M, N), x.device)
+                    call("dmv_act_bwd_bias", _p(dpre), _p(dpre), _p(dpre), _p(bvar.grad), M, N, 0, _p(bws), bws.numel(), _stream(x))
+                call("dmv_linear_wgrad_adam", _p(x), _p(dpre), _p(wvar.master), _p(wvar.m), _p(wvar.v), _p(wvar.half), None, M, K, N,
+                     live.state.data_ptr(), live.beta1, live.beta2, live.eps, live.grad_scale, _stream(x))
+                if bvar is not None:
+                    wvar.store.notify_grad(bvar)
+            else:
+                call("dmv_linear_wgrad", _p(x), _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None, M, K, N,
+                     _p(ws), ws.numel(), algo, _stream(x))
+                if bvar is not None:
+                    wvar.store.notify_grad(bvar)
+                wvar.store.notify_grad(wvar)
         return None, dx, None, None, None, None, None, None
 
 

@@ -36,12 +36,27 @@ class ModelBase(object):
 
     def train_step(self, *args):
         """One sess.run([loss, train_op]) of train.py:122: forward, backward, (gradient exchange,) Adam."""
+        dp = getattr(self, "_dp", None)
+        if dp is not None and hasattr(dp, "apply_deferred"):
+            dp.apply_deferred()    # the late FC matrices take the previous step's update next to this step's encoder forward
         loss = self.step_loss(self._as_batch(args))
-        loss.backward()
+        opt = self.optimizer
+        opt.begin_step()           # single process: the big FC matrices are updated inside backward (optimizer.py)
+        try:
+            loss.backward()
+        finally:
+            opt.end_backward()
         if getattr(self, "_dp", None) is not None:
             self._dp.finish()
-        self.optimizer.step()
+        opt.step()
         return loss.detach()
+
+    def flush_updates(self):
+        """Make every parameter reflect the completed steps (a deferred optimizer update may still be pending after
+        train_step returns; forward passes and state_dict() do this themselves)."""
+        dp = getattr(self, "_dp", None)
+        if dp is not None and hasattr(dp, "flush"):
+            dp.flush()
 
     def eval_loss(self, *args):
         """The validation pass of train.py:128-132 (val_summ_op): loss only, no gradient, no update."""
@@ -69,6 +84,9 @@ class ModelBase(object):
         return sd
 
     def load_state_dict(self, sd):
+        dp = getattr(self, "_dp", None)
+        if dp is not None and hasattr(dp, "reset_deferred"):
+            dp.flush()
         self.store.load_state_dict({k: v for k, v in sd.items() if k in self.store.vars})
         if self.optimizer is not None:
             for k, v in self.store.vars.items():

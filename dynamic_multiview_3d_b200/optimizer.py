@@ -1,10 +1,19 @@
 """TF-flavoured Adam over the flat variable storage (replaces
 tf.train.AdamOptimizer(lr).minimize, appearance_flow_model.py:77)."""
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
+
+FUSE_MIN = 1 << 20      # elements: FC matrices this large take the weight-gradient + Adam kernel (dmv_linear_wgrad_adam)
+
+
+def fusable(v):
+    """An FC matrix whose weight gradient dmv_linear_wgrad_adam can consume in place (include/dmv3d.h)."""
+    return (v.trainable and v.name.endswith("/Matrix") and len(v.shape) == 2 and v.numel >= FUSE_MIN and v.shape[0] % 8 == 0
+            and v.shape[1] % 8 == 0 and v.numel % 256 == 0 and v.offset % 256 == 0)
 
 
 class TFAdam:
@@ -19,22 +28,31 @@ class TFAdam:
         self.lr, self.beta1, self.beta2, self.eps, self.grad_scale = float(lr), beta1, beta2, eps, float(grad_scale)
         self.state = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float32, device=store.device)
         self.vars = store.trainable_vars()
-        n = len(self.vars)
-        vp = C.c_void_p * n
-        self._p = vp(*[v.master.data_ptr() for v in self.vars])
-        self._g = vp(*[v.grad.data_ptr() for v in self.vars])
-        self._m = vp(*[v.m.data_ptr() for v in self.vars])
-        self._v = vp(*[v.v.data_ptr() for v in self.vars])
-        self._h = vp(*[v.half.data_ptr() for v in self.vars])
-        self._n = (C.c_longlong * n)(*[v.numel for v in self.vars])
-        self._count = n
+        # Single-process training, optional (DMV_FUSE_FC_ADAM): big FC matrices are updated by the kernel that forms their
+        # weight gradient, during backward (functional._Linear.backward) -- the gradient is never written.  The model's
+        # train_step brackets backward with begin_step() / step(); a bare loss.backward() still writes plain gradients.
+        # data_parallel.attach() clears the marks when the gradients must be exchanged first (world > 1).
+        # MEASURED (profiles/r02_fc_adam.txt): the fused kernel moves 26 instead of 34 B/parameter and is 14 % faster than
+        # the two calls when timed alone (715 vs 829 us for the four matrices), but inside the step the separate Adam
+        # chunks already hide behind the backward pass and the step time does not change (2.81 vs 2.82 ms) -- off by
+        # default; the deferred update of data_parallel.py is what shortens the step.
+        self._ticked = False
+        fuse = os.environ.get("DMV_FUSE_FC_ADAM", "0")       # "0" | "1" (every eligible matrix) | comma-separated variable names
+        if fuse != "0" and store.device.type == "cuda":
+            for v in self.vars:
+                v.fused_adam = fusable(v) and (fuse == "1" or v.name in fuse.split(","))
         # contiguous runs of trainable variables collapse into single tensors (the flat
         # buffers are contiguous), which keeps the launch count at one in the common case
         self._coalesce()
 
     def _coalesce(self):
+        self._tbl = self._table([v for v in self.vars if not v.fused_adam])
+        # the fused FC matrices, for a step() that was not bracketed by begin_step(): their plain gradients were written
+        self._fused_tbl = self._table([v for v in self.vars if v.fused_adam])
+
+    def _table(self, vs):
         runs = []
-        for v in sorted(self.vars, key=lambda u: u.offset):
+        for v in sorted(vs, key=lambda u: u.offset):
             pad_end = v.offset + -(-v.numel // 64) * 64
             if runs and runs[-1][1] == v.offset:
                 runs[-1][1] = pad_end
@@ -44,21 +62,47 @@ class TFAdam:
         n = len(runs)
         vp = C.c_void_p * n
         es = 4
-        self._p = vp(*[f["master"].data_ptr() + a * es for a, _ in runs])
-        self._g = vp(*[f["grad"].data_ptr() + a * es for a, _ in runs])
-        self._m = vp(*[f["m"].data_ptr() + a * es for a, _ in runs])
-        self._v = vp(*[f["v"].data_ptr() + a * es for a, _ in runs])
-        self._h = vp(*[f["half"].data_ptr() + a * 2 for a, _ in runs])
-        self._n = (C.c_longlong * n)(*[b - a for a, b in runs])
-        self._count = n
+        return (vp(*[f["master"].data_ptr() + a * es for a, _ in runs]), vp(*[f["grad"].data_ptr() + a * es for a, _ in runs]),
+                vp(*[f["m"].data_ptr() + a * es for a, _ in runs]), vp(*[f["v"].data_ptr() + a * es for a, _ in runs]),
+                vp(*[f["half"].data_ptr() + a * 2 for a, _ in runs]), (C.c_longlong * n)(*[b - a for a, b in runs]), n)
 
-    def step(self):
+    def disable_fusion(self):
+        for v in self.vars:
+            v.fused_adam = False
+        self._coalesce()
+
+    def fused_vars(self):
+        return [v for v in self.vars if v.fused_adam]
+
+    def tick(self):
         from . import functional as F
         st = torch.cuda.current_stream(self.store.device).cuda_stream
         F._tag[0] = "adam"
         F.call("dmv_adam_tick", self.state.data_ptr(), self.lr, self.beta1, self.beta2, st)
-        F.call("dmv_adam_multi", self._p, self._g, self._m, self._v, self._h, self._n, self._count,
-                  self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale, st)
+
+    def begin_step(self):
+        """Before backward: advance the step scalars and arm the in-backward update of the fused FC matrices."""
+        if self.fused_vars():
+            self.tick()
+            self._ticked = True
+            self.store.adam_live = self
+
+    def end_backward(self):
+        self.store.adam_live = None
+
+    def step(self):
+        from . import functional as F
+        st = torch.cuda.current_stream(self.store.device).cuda_stream
+        self.store.adam_live = None
+        tables = [self._tbl]
+        if not self._ticked:          # plain backward + step(): every gradient, the FC matrices' included, is in memory
+            self.tick()
+            tables.append(self._fused_tbl)
+        self._ticked = False
+        F._tag[0] = "adam"
+        for p, g, m, v, h, n, count in tables:
+            if count:
+                F.call("dmv_adam_multi", p, g, m, v, h, n, count, self.state.data_ptr(), self.beta1, self.beta2, self.eps, self.grad_scale, st)
 
     @property
     def t(self):

@@ -57,9 +57,16 @@ class GraphedTrainStep:
         from . import _lib
         m = self.model
         flat = m.store.flat
+        m.flush_updates()               # a deferred optimizer update belongs to the state that is snapshotted
         snap = {k: flat[k].clone() for k in ("master", "m", "v", "half")}
         opt_state = m.optimizer.state.clone()
-        side = torch.cuda.Stream(device=m.device)
+        # The step's own chain (forward, loss, the dgrad chain of backward) is captured from a HIGH-priority stream; the
+        # weight-gradient lanes and the Adam / exchange stream keep the default (lowest) priority.  Kernel nodes inherit
+        # the priority of the stream they were captured on, so the block scheduler dispatches the critical chain's CTAs
+        # ahead of queued side-stream CTAs instead of behind a 784-CTA weight-gradient or a 2368-CTA Adam grid
+        # (profiles/r02_timeline_*.txt: small kernels of the chain waited up to 50 us for SM slots).
+        prio = -1 if os.environ.get("DMV_MAIN_PRIORITY", "1") == "1" else 0
+        side = torch.cuda.Stream(device=m.device, priority=prio)
         side.wait_stream(torch.cuda.current_stream(m.device))
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
@@ -68,12 +75,16 @@ class GraphedTrainStep:
         torch.cuda.synchronize(m.device)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.loss = m.train_step(self.static)
         self.launches_per_step = _lib.launch_count() - n0
+        torch.cuda.synchronize(m.device)
         for k, t in snap.items():
             flat[k].copy_(t)
         m.optimizer.state.copy_(opt_state)
+        dp = getattr(m, "_dp", None)
+        if dp is not None and hasattr(dp, "reset_deferred"):
+            dp.reset_deferred()         # the warm-up steps' pending update is discarded with them
         return self
 
     def _copy_in(self, batch):
@@ -97,7 +108,15 @@ class GraphedTrainStep:
     def replay(self):
         """One more step on the batch that already sits in the static buffers (no copy at all)."""
         self.graph.replay()
+        self._after_replay()
         return self.loss
+
+    def _after_replay(self):
+        # the replayed step left the late FC matrices' update pending on the device (data_parallel.py: deferred updates);
+        # the host-side bookkeeping that an eager train_step does must follow
+        dp = getattr(self.model, "_dp", None)
+        if dp is not None and getattr(dp, "deferred", None):
+            dp.mark_pending()
 
     def prefetch(self, *args):
         """Start the host->device copy of the NEXT step's batch on a copy stream into staging buffers; it overlaps
@@ -136,6 +155,7 @@ class GraphedTrainStep:
         if prefetch_next is not None:
             self.prefetch(*(prefetch_next if isinstance(prefetch_next, (tuple, list)) else (prefetch_next,)))
         self.graph.replay()
+        self._after_replay()
         return self.loss
 
 

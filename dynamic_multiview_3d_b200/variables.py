@@ -21,7 +21,7 @@ BIG_VARIABLE = 1 << 20   # elements; variables this large (the FC matrices) begi
 
 
 class Variable:
-    __slots__ = ("name", "shape", "master", "grad", "m", "v", "half", "trainable", "offset", "numel", "store", "used")
+    __slots__ = ("name", "shape", "master", "grad", "m", "v", "half", "trainable", "offset", "numel", "store", "used", "fused_adam")
 
     def __init__(self, name, tensor, trainable=True):
         self.name = name
@@ -32,6 +32,7 @@ class Variable:
         self.trainable = trainable
         self.offset = -1
         self.used = False
+        self.fused_adam = False     # optimizer.py: the weight gradient of this FC matrix is consumed by Adam inside one kernel
 
 
 class VariableStore:
@@ -45,6 +46,8 @@ class VariableStore:
         self.grad_ready_hook = None     # called with a Variable when its gradient has been written
         self.flat = {}
         self.record = None              # dict: layer name -> activation, filled by tf_utils ops when set (tests)
+        self.adam_live = None           # the optimizer, between its begin_step() and the end of backward (fused FC update)
+        self.pre_use_hook = None        # called with a Variable before a layer reads it (deferred updates, data_parallel.py)
         # dummy differentiable leaf: keeps the autograd tape alive for layers whose only
         # differentiable inputs are parameters (gradients of parameters bypass autograd)
         self.anchor = None

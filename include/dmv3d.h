@@ -243,6 +243,27 @@ int dmv_adam_multi(float* const* params, const float* const* grads, float* const
                    const float* state4, float beta1, float beta2, float eps, float grad_scale,
                    void* stream);
 
+/* dmv_adam_multi that does nothing unless *gate != 0 (device int): an update whose launch is scheduled before it is
+ * known whether a gradient is pending -- the optimizer update of the late FC matrices is applied at the START of the next
+ * step, next to the encoder's forward pass, inside a captured CUDA graph (data_parallel.py).  dmv_set_flag writes the
+ * gate from the stream. */
+int dmv_adam_multi_gated(float* const* params, const float* const* grads, float* const* m,
+                         float* const* v, void* const* bf16_copy, const long long* n, int count,
+                         const float* state4, float beta1, float beta2, float eps, float grad_scale,
+                         const int* gate, void* stream);
+int dmv_set_flag(int* flag, int value, void* stream);
+
+/* dmv_linear_wgrad + dmv_adam_multi on one FC matrix in ONE pass (single-process training; the data-parallel exchange
+ * needs the gradient in memory and keeps the two calls): the tile of dW = x^T dy (tf.matmul's weight gradient,
+ * tf_utils.py:54-67) is formed in registers and consumed by ApplyAdam (appearance_flow_model.py:77) -- theta, m, v
+ * fp32 [K,N] and the bf16 compute copy are updated, the gradient is never written (26 instead of 34 B/parameter).
+ * dw_out (optional, fp32 [K,N]) also receives the gradient (tests).  K, N multiples of 8, 16-byte aligned pointers;
+ * state4 as advanced by dmv_adam_tick for this step.  The caller orders it after the layer's dgrad (it rewrites the
+ * bf16 weights that dgrad reads). */
+int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta, float* m, float* v,
+                          void* bf16_copy, float* dw_out, int M, int K, int N, const float* state4,
+                          float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* ---- data-parallel exchange (new work: the reference is single-GPU) -------------------- *
  * One chunk of the per-step exchange as ONE kernel over peer-mapped (symmetric) memory on the NVSwitch domain:
  *   reduce-scatter of the gradients  ->  TF-Adam on the slice this rank owns  ->  all-gather of the bf16 compute copy.

@@ -256,6 +256,40 @@ def test_adam_matches_tf_oracle():
         assert torch.equal(v.half, v.master.to(torch.bfloat16))          # bf16 compute copy refreshed in the same pass
 
 
+@pytest.mark.parametrize("M,K,N", [(64, 192, 256), (5, 72, 136), (130, 64, 128), (64, 4160, 512), (16, 128, 12544)])
+def test_linear_wgrad_adam_fused(M, K, N):
+    """dmv_linear_wgrad_adam: the weight gradient formed in registers equals x^T dy (oracle, float64 accumulate), and the
+    update applied to theta / m / v / the bf16 copy is ApplyAdam on exactly that gradient -- two consecutive steps, so
+    non-zero moments are read back.  Shapes cover row / column tails of the 64 x 128 tile and several sample chunks."""
+    from dynamic_multiview_3d_b200 import _lib
+    rng = np.random.default_rng(M * 7 + K + N)
+    theta = (rng.standard_normal((K, N)) * 0.05).astype(np.float32)
+    th, m, v = (torch.from_numpy(theta).cuda(), torch.zeros(K, N, device="cuda"), torch.zeros(K, N, device="cuda"))
+    half = torch.zeros(K, N, dtype=torch.bfloat16, device="cuda")
+    dw = torch.empty(K, N, device="cuda")
+    state = torch.tensor([1.0, 1.0, 0.0, 0.0], device="cuda")
+    ref = (theta.copy(), np.zeros((K, N), np.float32), np.zeros((K, N), np.float32))
+    st = torch.cuda.current_stream().cuda_stream
+    for t in (1, 2):
+        x = bf16_round(rng.standard_normal((M, K)))
+        dy = bf16_round(rng.standard_normal((M, N)) * 10.0 ** rng.integers(-4, 0))
+        xt, dyt = _t(x), _t(dy)
+        _lib.call("dmv_adam_tick", state.data_ptr(), 1e-3, 0.9, 0.999, st)
+        _lib.call("dmv_linear_wgrad_adam", xt.data_ptr(), dyt.data_ptr(), th.data_ptr(), m.data_ptr(), v.data_ptr(), half.data_ptr(),
+                  dw.data_ptr(), M, K, N, state.data_ptr(), 0.9, 0.999, 1e-8, 1.0, st)
+        torch.cuda.synchronize()
+        g = dw.cpu().numpy()
+        gref = (x.astype(np.float64).T @ dy.astype(np.float64)).astype(np.float32)
+        assert _rel(g, gref) < 1e-5
+        ref = T.adam_tf_step(ref[0], g, ref[1], ref[2], t, 1e-3)
+        # the kernel contracts m + (g - m)(1 - b1) into one FMA where NumPy rounds twice: a few ulp, amplified where g and m
+        # cancel -- so the moments are held relative to their scale, theta to a thousandth of one step (lr = 1e-3)
+        assert _rel(m.cpu().numpy(), ref[1]) < 1e-6
+        assert _rel(v.cpu().numpy(), ref[2]) < 1e-6
+        assert float(np.abs(th.cpu().numpy() - ref[0]).max()) < 1e-6
+        assert torch.equal(half, th.to(torch.bfloat16))
+
+
 def test_u8_to_f32_matches_reference_division():
     """dmv_u8_to_f32: float32(pixel) / 255 in IEEE division, bit for bit (read_tf_records.py:111)."""
     from dynamic_multiview_3d_b200 import _lib

@@ -315,3 +315,72 @@ def test_activation_derivative_fusion_matches_the_separate_pass(cls, monkeypatch
     for k in grads["1"]:
         a, r = grads["1"][k], grads["0"][k]
         assert float((a - r).norm() / (r.norm() + 1e-30)) < 1e-2, k
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_fused_fc_update_matches_the_separate_update(overlap, monkeypatch):
+    """Single-process train_step: the FC matrices are updated by dmv_linear_wgrad_adam inside backward (optimizer.py).
+    Against DMV_FUSE_FC_ADAM=0 (weight gradient written, Adam afterwards) three steps give the same parameters and
+    moments up to the summation order of the 64-sample contraction; with the chunked Adam of data_parallel.attach
+    (world 1) the FC ranges are left out of the chunk plan and the rest is updated exactly once."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200 import data_parallel
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "seed": 5}
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("DMV_FUSE_FC_ADAM", fuse)
+        m = pkg.AppearanceFlowModel(conf)
+        fused = [v.name for v in m.store.vars.values() if v.fused_adam]
+        assert set(fused) == ({"fc1/Matrix", "a3/Matrix", "a4/Matrix", "a5/Matrix"} if fuse == "1" else set()), fused
+        if overlap:
+            data_parallel.attach(m, bucket_mb=4.0)
+        losses = [float(m.train_step(*args)) for _ in range(3)]
+        m.flush_updates()
+        torch.cuda.synchronize()
+        assert m.optimizer.t == 3
+        out[fuse] = (losses, {k: (v.master.clone(), v.m.clone(), v.v.clone(), v.half.clone()) for k, v in m.store.vars.items()})
+    assert out["1"][0][0] == out["0"][0][0]                       # same forward before the first update
+    assert out["1"][0][2] == pytest.approx(out["0"][0][2], rel=1e-4)
+    for k, (th, mo, ve, hf) in out["1"][1].items():
+        th0, mo0, ve0, hf0 = out["0"][1][k]
+        assert float((mo - mo0).norm() / (mo0.norm() + 1e-30)) < 1e-3, k       # first moment ~ the gradient itself
+        assert float((th - th0).abs().max()) < 3.1e-4, k                         # three Adam steps of at most lr each
+        assert float((th - th0).norm() / (th0.norm() + 1e-30)) < 1e-3, k
+        assert torch.equal(hf, th.to(torch.bfloat16)), k
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_deferred_fc_update_is_bit_identical(graphed, monkeypatch):
+    """data_parallel.attach (single process): the Adam update of the late FC matrices (a3, a4, a5) is applied at the start
+    of the NEXT step, next to the encoder's forward pass.  Same gradients, same step scalars -> the parameters, moments
+    and bf16 copies after flush_updates() equal those of the immediate update bit for bit, a validation pass between steps
+    sees the updated weights, and a captured graph (whose first replay has nothing pending) behaves the same."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200 import data_parallel
+    from dynamic_multiview_3d_b200.train import GraphedTrainStep
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "seed": 9}
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    out = {}
+    for defer in ("auto", "0"):
+        monkeypatch.setenv("DMV_DEFER_ADAM", defer)
+        m = pkg.AppearanceFlowModel(conf)
+        red = data_parallel.attach(m, bucket_mb=4.0)
+        deferred_vars = sorted(red.var_wait)
+        assert deferred_vars == (["a3/Matrix", "a4/Matrix", "a5/Matrix"] if defer == "auto" else []), deferred_vars
+        step = GraphedTrainStep(m, warmup=2) if graphed else (lambda *a: m.train_step(*a))
+        losses = [float(step(*args)) for _ in range(2)]
+        val = float(m.eval_loss(*args))                   # forward outside train_step: must see step 2's update of a3..a5
+        losses += [float(step(*args)) for _ in range(2)]
+        sd = m.state_dict()                               # flushes
+        assert m.optimizer.t == 4
+        out[defer] = (losses, val, sd, {k: v.half.clone() for k, v in m.store.vars.items()})
+    assert out["auto"][0] == out["0"][0] and out["auto"][1] == out["0"][1]
+    for k, t in out["0"][2].items():
+        assert torch.equal(t, out["auto"][2][k]), k
+    for k, t in out["0"][3].items():
+        assert torch.equal(t, out["auto"][3][k]), k
