@@ -34,6 +34,7 @@ int dmv_act_bwd_bias(const void* dy_bf16, const void* y_bf16, void* dpre_bf16, f
 
 size_t dmv_thin_s2d_size(int N, int H, int W, int C_thin, int C_wide, int kh, int kw, int stride) {
     if (N <= 0 || H <= 0 || W <= 0 || C_thin <= 0 || !thin_s2d_eligible(H, W, C_thin, C_wide, kh, kw, stride)) return 0;
+    if (thin_mma_eligible(N, H, W, C_thin, C_wide, kh, kw, stride)) return 0;      // single-kernel form: no prep tensor
     return (size_t)N * (H / 2) * (W / 2) * 64;
 }
 
@@ -57,6 +58,8 @@ size_t dmv_wgrad_workspace_size(int B, int H, int W, int Cbig, int Csmall, int k
     if (b > a) a = b;
     if (thin_side(Cbig)) {
         size_t c = tc_thin_workspace(B, H, W, Cbig, Csmall, kh, kw, stride);
+        if (c > a) a = c;
+        c = thin_mma_wgrad_workspace(B, H, W, Cbig, Csmall, kh, kw, stride);
         if (c > a) a = c;
         if (thin_wgrad_eligible(taps, Cbig, Csmall)) {
             c = thin_wgrad_workspace(taps, Cbig);
@@ -91,7 +94,9 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias,
         return tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
     }
     if (algo != DMV_ALGO_SIMT && thin_side(Cin)) {
-        int rc = tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
+        int rc = thin_mma_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE) return rc;
+        rc = tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
     }
     if (algo != DMV_ALGO_SIMT) {
@@ -130,7 +135,9 @@ int dmv_conv2d_wgrad(const void* x, int x_dtype, const void* dy, float* dw, floa
         return rc;
     }
     if (algo != DMV_ALGO_SIMT && thin_side(Cin)) {   // e0: 3-channel image side
-        int rc = tc_thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        int rc = thin_mma_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc == DMV_E_UNSUPPORTED_SHAPE || rc == DMV_E_WORKSPACE)
+            rc = tc_thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc == DMV_E_UNSUPPORTED_SHAPE || rc == DMV_E_WORKSPACE) {
             if (!thin_wgrad_eligible(kh * kw, Cin, Cout)) goto generic;
             rc = thin_wgrad(x, x_dtype, dy, dw, B, H, W, Cin, kh, kw, stride, workspace, workspace_bytes, st);
@@ -158,6 +165,10 @@ int dmv_deconv2d_fwd(const void* x, const void* w, void* y, int y_dtype, int B, 
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "deconv2d_fwd: null pointer");
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {     // flow head: 2-channel output side
+        int rc = thin_mma_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cout, Cin, kh, kw, stride, act, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE) return rc;
+    }
     if (algo != DMV_ALGO_SIMT) {
         int rc = tc_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE || algo == DMV_ALGO_TCGEN05) return rc;
@@ -178,7 +189,9 @@ int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, co
             return tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
                                workspace_bytes, st);
         if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {   // flow head: dx = conv of the 2-channel gradient with w[r,s,c,ci]
-            int rc = tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
+            int rc = thin_mma_conv_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, st);
+            if (rc != DMV_E_UNSUPPORTED_SHAPE) return rc;
+            rc = tc_thin_fwd(dy, dy_dtype, w, nullptr, dx, DMV_DT_BF16, B, Hout, Wout, Cout, Cin, kh, kw, stride, DMV_ACT_NONE, workspace,
                                  workspace_bytes, st);
             if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
         }
@@ -200,7 +213,9 @@ int dmv_deconv2d_wgrad(const void* x, const void* dy, int dy_dtype, float* dw, i
         return tc_thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
     }
     if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {      // flow head: 2-channel output side
-        int rc = tc_thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+        int rc = thin_mma_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
+        if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
+        rc = tc_thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, Cin, kh, kw, stride, workspace, workspace_bytes, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE && rc != DMV_E_WORKSPACE) return rc;
         if (thin_wgrad_eligible(kh * kw, Cout, Cin))
             return thin_wgrad(dy, dy_dtype, x, dw, B, Hout, Wout, Cout, kh, kw, stride, workspace, workspace_bytes, st);

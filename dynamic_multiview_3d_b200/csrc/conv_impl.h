@@ -56,6 +56,16 @@ int thin_s2d_gather_dw(const float* dw2, float* dw, int Ct, int Cw, int kh, int 
 int thin_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int kh, int kw, int stride,
                void* ws, size_t ws_bytes, cudaStream_t st);
 
+// thin stride-2 5x5 layers as single mma.sync bandwidth kernels (thin_mma.cu): no prep pass, no patch matrix
+bool thin_mma_eligible(int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw, int stride);
+size_t thin_mma_wgrad_workspace(int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw, int stride);
+int thin_mma_conv_fwd(const void* thin, int thin_dtype, const void* w_bf16, const float* bias, void* out, int out_dtype, int N, int Hb, int Wb,
+                      int Ct, int Cw, int kh, int kw, int stride, int act, cudaStream_t st);
+int thin_mma_deconv_fwd(const void* x_bf16, const void* w_bf16, void* y, int y_dtype, int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw,
+                        int stride, int act, cudaStream_t st);
+int thin_mma_wgrad(const void* thin, int thin_dtype, const void* wide_bf16, float* dw, int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw,
+                   int stride, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // Activation-derivative fusion for input-gradient launches: after tc_set_dact(y, act) the next tc_*_dgrad / thin dgrad
 // launch of this thread writes dX * act'(y) (y: bf16, same shape as dX); tc_finish_dact() tells whether a launch applied
 // it (a path that did not must be followed by an elementwise pass) and clears the request.

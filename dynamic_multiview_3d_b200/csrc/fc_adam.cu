@@ -291,7 +291,7 @@ int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta,
         const char* e = getenv("DMV_FC_ADAM_CTAS");
         ctas_env = e ? atoi(e) : 0;
         const char* g = getenv("DMV_FC_ADAM_VARIANT");
-        variant = g ? atoi(g) : 4;
+        variant = g ? atoi(g) : 9;
         if (variant == 9 && cudaFuncSetAttribute(fc_wgrad_adam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STREAM_SMEM) !=
                                 cudaSuccess) {
             cudaGetLastError();

@@ -185,10 +185,10 @@ class ShardedGradientReducer:
         if self.world != 1 or not self.cuda or env == "0":
             return
         big = [v for v in self.store.vars.values() if v.trainable and v.offset < self.shard_end and v.numel >= (1 << 20)
-               and v.name.endswith("/Matrix") and not getattr(v, "fused_adam", False)]
+               and v.name.endswith("/Matrix")]
         names = set(env.split(",")) if env not in ("auto", "1") else {v.name for v in big[1:]}    # all but the first-created (fc1):
         for v in big:                                                                              # its gradient comes last
-            if v.name not in names:
+            if v.name not in names or getattr(v, "fused_adam", False):
                 continue
             cs = [c for c, (s, e) in enumerate(self.chunks) if v.offset <= s and e <= v.offset + v.numel and self.expected[c] > 0]
             if cs:

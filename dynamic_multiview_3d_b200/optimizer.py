@@ -32,15 +32,19 @@ class TFAdam:
         # weight gradient, during backward (functional._Linear.backward) -- the gradient is never written.  The model's
         # train_step brackets backward with begin_step() / step(); a bare loss.backward() still writes plain gradients.
         # data_parallel.attach() clears the marks when the gradients must be exchanged first (world > 1).
-        # MEASURED (profiles/r02_fc_adam.txt): the fused kernel moves 26 instead of 34 B/parameter and is 14 % faster than
-        # the two calls when timed alone (715 vs 829 us for the four matrices), but inside the step the separate Adam
-        # chunks already hide behind the backward pass and the step time does not change (2.81 vs 2.82 ms) -- off by
-        # default; the deferred update of data_parallel.py is what shortens the step.
+        # MEASURED (profiles/r02_fc_adam.txt, r02_fuse_defer_sweep.txt): the fused kernel moves 26 instead of 34 B/parameter
+        # and is 14 % faster than the two calls when timed alone (715 vs 829 us for the four matrices).  Inside the step the
+        # best split is: fc1 fused (its update has to finish inside the step anyway), a3 / a4 / a5 updated by the plain Adam
+        # chunks at the start of the next step (data_parallel.py, deferred): 2.72 ms against 2.77 with no fusion and 2.77
+        # with all four fused.
         self._ticked = False
-        fuse = os.environ.get("DMV_FUSE_FC_ADAM", "0")       # "0" | "1" (every eligible matrix) | comma-separated variable names
+        # "auto": the first-created eligible matrix (fc1 -- the one whose gradient arrives last and whose update cannot be
+        # deferred into the next forward pass, data_parallel.py) | "0" | "1" (every eligible matrix) | comma-separated names
+        fuse = os.environ.get("DMV_FUSE_FC_ADAM", "auto")
         if fuse != "0" and store.device.type == "cuda":
-            for v in self.vars:
-                v.fused_adam = fusable(v) and (fuse == "1" or v.name in fuse.split(","))
+            cand = [v for v in self.vars if fusable(v)]
+            for v in cand:
+                v.fused_adam = (fuse == "1") or (fuse == "auto" and v is cand[0]) or (v.name in fuse.split(","))
         # contiguous runs of trainable variables collapse into single tensors (the flat
         # buffers are contiguous), which keeps the launch count at one in the common case
         self._coalesce()

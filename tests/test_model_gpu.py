@@ -366,6 +366,7 @@ def test_deferred_fc_update_is_bit_identical(graphed, monkeypatch):
     b = _batch(B, H, V)
     args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
     out = {}
+    monkeypatch.setenv("DMV_FUSE_FC_ADAM", "0")           # the immediate / deferred comparison is about the same kernels
     for defer in ("auto", "0"):
         monkeypatch.setenv("DMV_DEFER_ADAM", defer)
         m = pkg.AppearanceFlowModel(conf)

@@ -269,3 +269,47 @@ def test_linear_dgrad_with_fused_activation_derivative(M, K, N):
     assert float(((two_pass - fused).abs() - 2.0 ** -7 * fused.abs()).max()) <= 0.0
     ref = (dy.float() @ w.float().t()) * torch.where(pos, 1.0, 0.2)
     assert float((fused - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("H,B,ct", [(32, 2, 3), (32, 3, 2), (64, 2, 4), (224, 2, 3), (224, 2, 2), (96, 1, 1)])
+def test_thin_layers_single_kernel_form(H, B, ct):
+    """csrc/thin_mma.cu: the thin stride-2 5x5 layers (e0: ct -> 32 conv on fp32 pixels; flow head: 32 -> ct deconv with fp32
+    output and fp32 output gradient) as one mma.sync kernel each, against the oracle: forward of both, the flow head's input
+    gradient (the same kernel as e0's forward) and both weight gradients (window staged once, contraction over pixels)."""
+    from dynamic_multiview_3d_b200 import _lib, functional as F
+    rng = np.random.default_rng(H * 10 + B + ct)
+    st = _store()
+    # --- conv side (e0): fp32 input in [0, 1] (rounded to bf16 inside the kernel: compare against the oracle on rounded pixels)
+    x = rng.random((B, H, H, ct), dtype=np.float32)
+    w = bf16_round(rng.standard_normal((5, 5, ct, 32)) * T.conv_stddev(5, 5, ct))
+    b = rng.standard_normal(32).astype(np.float32) * 0.1
+    y = T.conv2d_same(bf16_round(x), w, b, 2, 2)
+    gy = bf16_round(rng.standard_normal(y.shape))
+    _, gw, gb = T.conv2d_same_grads(bf16_round(x), w, gy, 2, 2)
+    wv, bv = _var(st, "e0/w", w), _var(st, "e0/b", b)
+    assert _lib.load().dmv_thin_s2d_size(B, H, H, ct, 32, 5, 5, 2) == 0           # no prep tensor on this path
+    xt = torch.from_numpy(x).cuda()
+    n0 = _lib.launch_count()
+    yo = F.conv2d(xt, wv, bv, 2, "lrelu", "auto")
+    assert _lib.launch_count() == n0 + 1, "e0 forward is one kernel"
+    assert _rel(yo.detach().float().cpu().numpy(), T.lrelu(y)) < 1e-2
+    yl = F.conv2d(xt, wv, bv, 2, None, "auto")
+    yl.backward(torch.from_numpy(gy).cuda().to(torch.bfloat16))
+    assert _rel(wv.grad.cpu().numpy(), gw) < 2e-4
+    assert _rel(bv.grad.cpu().numpy(), gb) < 1e-4
+    # --- deconv side (flow head): bf16 input, fp32 output, fp32 output gradient
+    h = H // 2
+    xd = bf16_round(rng.standard_normal((B, h, h, 32)))
+    wd = bf16_round(rng.standard_normal((5, 5, ct, 32)) * T.deconv_stddev(5, 5, 32, 2, 2))
+    yd = T.conv2d_transpose_same(xd, wd, (B, H, H, ct), 2, 2)
+    gyd = bf16_round(rng.standard_normal(yd.shape))
+    gxd, gwd = T.conv2d_transpose_same_grads(xd, wd, gyd, 2, 2)
+    wdv = _var(st, "flow/w", wd)
+    xdt = torch.from_numpy(xd).cuda().to(torch.bfloat16).requires_grad_(True)
+    n0 = _lib.launch_count()
+    ydo = F.deconv2d(xdt, wdv, (H, H), 2, None, "auto", torch.float32)
+    assert _lib.launch_count() == n0 + 1, "flow head forward is one kernel"
+    assert _rel(ydo.detach().cpu().numpy(), yd) < 1e-4
+    ydo.backward(torch.from_numpy(gyd).cuda())
+    assert _rel(xdt.grad.float().cpu().numpy(), gxd) < 1e-2
+    assert _rel(wdv.grad.cpu().numpy(), gwd) < 2e-4
