@@ -73,25 +73,37 @@ template <int CT, int NTHR>
 struct WindowRegs {
     static constexpr int ROWE = 35 * CT, TOTAL = 19 * ROWE, NR = (TOTAL + NTHR - 1) / NTHR;
     float v[NR];
-    __device__ __forceinline__ void load(const float* __restrict__ thin, const ThinGeo& g, int n, int oh0, int ow0, int tid) {
-        const int y0 = 2 * oh0 - g.pt, x0 = 2 * ow0 - g.pl;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            const int i = tid + j * NTHR;
-            const int row = i / ROWE, e = i - row * ROWE, px = e / CT;
-            const int gy = y0 + row, gx = x0 + px;
-            v[j] = 0.f;
-            if (i < TOTAL && gy >= 0 && gy < g.Hb && gx >= 0 && gx < g.Wb)
-                v[j] = __ldg(thin + ((long long)n * g.Hb + gy) * g.Wb * CT + (long long)x0 * CT + e);
-        }
-    }
-    __device__ __forceinline__ void store(bf16* win, int tid) const {
+    int goff[NR];      // element offset from the window's origin in the thin tensor (row * Wb * CT + e); -1: no element
+    int meta[NR];      // shared-memory element index | row << 12 | pixel << 17
+    // the element -> (row, pixel, channel) map does not depend on the tile: computed once per thread (the kernels are bound
+    // by instruction issue, not by memory: profiles/r02_thin_ncu.txt)
+    __device__ __forceinline__ void init(const ThinGeo& g, int tid) {
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             const int i = tid + j * NTHR;
             const int row = i / ROWE, e = i - row * ROWE, px = e / CT, c = e - px * CT;
-            if (i < TOTAL) win[(row * WC + px) * 4 + c] = __float2bfloat16_rn(v[j]);
+            goff[j] = i < TOTAL ? row * g.Wb * CT + e : -1;
+            meta[j] = ((row * WC + px) * 4 + c) | (row << 12) | (px << 17);
         }
+    }
+    __device__ __forceinline__ void load(const float* __restrict__ thin, const ThinGeo& g, int n, int oh0, int ow0) {
+        const int y0 = 2 * oh0 - g.pt, x0 = 2 * ow0 - g.pl;
+        const float* base = thin + (((long long)n * g.Hb + y0) * g.Wb + x0) * CT;
+        if (y0 >= 0 && x0 >= 0 && y0 + 19 <= g.Hb && x0 + 35 <= g.Wb) {          // interior tile: no bounds checks
+#pragma unroll
+            for (int j = 0; j < NR; ++j) v[j] = goff[j] >= 0 ? __ldg(base + goff[j]) : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const int gy = y0 + ((meta[j] >> 12) & 31), gx = x0 + (meta[j] >> 17);
+                v[j] = (goff[j] >= 0 && gy >= 0 && gy < g.Hb && gx >= 0 && gx < g.Wb) ? __ldg(base + goff[j]) : 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(bf16* win) const {
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+            if (goff[j] >= 0) win[meta[j] & 4095] = __float2bfloat16_rn(v[j]);
     }
 };
 
@@ -104,11 +116,12 @@ template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 __device__ __forceinline__ void tile_coords(const ThinGeo& g, long long tile, int& n, int& oh0, int& ow0) {
-    const int per = g.tiles_x * g.tiles_y;
-    n = (int)(tile / per);
-    const int rem = (int)(tile - (long long)n * per);
-    oh0 = (rem / g.tiles_x) * TH;
-    ow0 = (rem % g.tiles_x) * TW;
+    const unsigned per = (unsigned)(g.tiles_x * g.tiles_y), tl = (unsigned)tile;        // tiles < 2^31 (checked on the host)
+    n = (int)(tl / per);
+    const unsigned rem = tl - (unsigned)n * per;
+    const unsigned ty = rem / (unsigned)g.tiles_x;
+    oh0 = (int)ty * TH;
+    ow0 = (int)(rem - ty * (unsigned)g.tiles_x) * TW;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -118,7 +131,7 @@ __device__ __forceinline__ void tile_coords(const ThinGeo& g, long long tile, in
 // pixel's whole 64-byte row.  The weight fragments sit in shared memory in fragment order (one conflict-free 8-byte load
 // per MMA); persistent CTAs, the next tile's window is loaded into registers while the current one is contracted.
 template <int CT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 thin_conv_kernel(const float* __restrict__ thin, const bf16* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out, ThinGeo g,
                  int act) {
     __shared__ __align__(16) bf16 win[WR * WC * 4];
@@ -147,21 +160,31 @@ thin_conv_kernel(const float* __restrict__ thin, const bf16* __restrict__ w, con
 #pragma unroll
     for (int e = 0; e < 8; ++e) bv[e] = bias ? __ldg(bias + 8 * t + e) : 0.f;
 
+    // element offsets of this thread's k pairs inside the window, relative to the pixel's origin (row 2*oh_l, pixel 2*ow_l)
+    int koff[KS][2];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * ks + 8 * h + 2 * t;
+            koff[ks][h] = (k / 20) * (WC * 4) + (k % 20);
+        }
     WindowRegs<CT, 256> wr;
+    wr.init(g, tid);
     long long tile = blockIdx.x;
     int n = 0, oh0 = 0, ow0 = 0;
     if (tile < g.tiles) {
         tile_coords(g, tile, n, oh0, ow0);
-        wr.load(thin, g, n, oh0, ow0, tid);
+        wr.load(thin, g, n, oh0, ow0);
     }
     for (; tile < g.tiles; tile += gridDim.x) {
         __syncthreads();                                   // the previous tile's fragments have been read
-        wr.store(win, tid);
+        wr.store(win);
         __syncthreads();
         const int cn = n, coh0 = oh0, cow0 = ow0;
         if (tile + gridDim.x < g.tiles) {                  // the next tile's loads fly during this tile's contraction
             tile_coords(g, tile + gridDim.x, n, oh0, ow0);
-            wr.load(thin, g, n, oh0, ow0, tid);
+            wr.load(thin, g, n, oh0, ow0);
         }
         float acc[4][4];
 #pragma unroll
@@ -172,9 +195,7 @@ thin_conv_kernel(const float* __restrict__ thin, const bf16* __restrict__ w, con
         const bf16* p1 = p0 + 16 * 4;                                      // pixel gq + 8
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            // element offsets of this thread's two k pairs inside the window, relative to the pixel's origin
-            const int k0 = 16 * ks + 2 * t, k1 = k0 + 8;
-            const int o0 = (k0 / 20) * (WC * 4) + (k0 % 20), o1 = (k1 / 20) * (WC * 4) + (k1 % 20);
+            const int o0 = koff[ks][0], o1 = koff[ks][1];
             unsigned a[4];
             a[0] = *reinterpret_cast<const unsigned*>(p0 + o0);
             a[1] = *reinterpret_cast<const unsigned*>(p1 + o0);
@@ -236,17 +257,26 @@ thin_deconv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, OutT*
     const int mat = lane >> 3, rr = lane & 7;
     // source windows arrive by 16-byte cp.async (zero fill outside the image) into two buffers: tile i+1 is in flight while
     // tile i is contracted
+    constexpr int NU = ((TH + 2) * (TW + 2) * 4 + 255) / 256;          // 16-byte units per thread
+    int uoff[NU], umeta[NU];                                              // global offset (uint4) from the window origin; smem unit | wy << 12 | wx << 17
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+        const int i = tid + j * 256, pix = i >> 2, u = i & 3, wy = pix / (TW + 2), wx = pix - wy * (TW + 2);
+        uoff[j] = i < (TH + 2) * (TW + 2) * 4 ? (wy * g.Ws + wx) * 4 + u : -1;
+        umeta[j] = (pix * (XPITCH / 8) + u) | (wy << 12) | (wx << 17);
+    }
     auto issue = [&](long long tl, int buf) {
         if (tl < g.tiles) {
             int n, q0y, q0x;
             tile_coords(g, tl, n, q0y, q0x);
-            for (int i = tid; i < (TH + 2) * (TW + 2) * 4; i += 256) {          // 16-byte units: 4 per pixel
-                const int pix = i >> 2, u = i & 3;
-                const int wy = pix / (TW + 2), wx = pix - wy * (TW + 2);
-                const int sy = q0y - 1 + wy, sx = q0x - 1 + wx;
+            const uint4* base = reinterpret_cast<const uint4*>(x + (((long long)n * g.Hs + q0y - 1) * g.Ws + q0x - 1) * 32);
+            uint4* dst = reinterpret_cast<uint4*>(xw + buf * (TH + 2) * (TW + 2) * XPITCH);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                if (uoff[j] < 0) continue;
+                const int sy = q0y - 1 + ((umeta[j] >> 12) & 31), sx = q0x - 1 + (umeta[j] >> 17);
                 const bool ok = sy >= 0 && sy < g.Hs && sx >= 0 && sx < g.Ws;
-                const bf16* src = ok ? x + (((long long)n * g.Hs + sy) * g.Ws + sx) * 32 + u * 8 : x;
-                cp_async16_zfill(xw + (buf * (TH + 2) * (TW + 2) + pix) * XPITCH + u * 8, src, ok);
+                cp_async16_zfill(dst + (umeta[j] & 4095), ok ? (const void*)(base + uoff[j]) : (const void*)x, ok);
             }
         }
         cp_async_commit();
@@ -309,7 +339,7 @@ thin_deconv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, OutT*
 // r: 2 m16 tiles (cw) x 3 n8 tiles, 24 accumulators, over the CTA's tiles (persistent); the per-CTA partials are summed in CTA
 // order by the shared deterministic reduction, then gathered into dW[r][s][c][cw].
 template <int CT>
-__global__ void __launch_bounds__(160, 4)
+__global__ void __launch_bounds__(160, 3)
 thin_wgrad_mma_kernel(const float* __restrict__ thin, const bf16* __restrict__ wide, float* __restrict__ part, ThinGeo g) {
     __shared__ __align__(16) bf16 win[WR * WC * 4];
     __shared__ __align__(16) bf16 wd[TH * TW * XPITCH];
@@ -325,34 +355,39 @@ thin_wgrad_mma_kernel(const float* __restrict__ thin, const bf16* __restrict__ w
             for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
 
     WindowRegs<CT, 160> wr;
+    wr.init(g, tid);
     uint4 wq[4];                                             // this thread's 16-byte units of the wide tile (512 per tile)
-    auto load_wide = [&](int n, int oh0, int ow0) {
+    int woff[4];                                             // their offsets (in uint4) from the tile's first pixel
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = tid + j * 160;
-            const int pix = i >> 2, u = i & 3, oy = pix / TW, ox = pix - oy * TW;
-            if (i < TH * TW * 4) wq[j] = __ldg(reinterpret_cast<const uint4*>(wide + (((long long)n * g.Hs + oh0 + oy) * g.Ws + ow0 + ox) * 32) + u);
-        }
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * 160, pix = i >> 2, oy = pix / TW, ox = pix - oy * TW;
+        woff[j] = i < TH * TW * 4 ? (oy * g.Ws + ox) * 4 + (i & 3) : -1;
+    }
+    auto load_wide = [&](int n, int oh0, int ow0) {
+        const uint4* base = reinterpret_cast<const uint4*>(wide + (((long long)n * g.Hs + oh0) * g.Ws + ow0) * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (woff[j] >= 0) wq[j] = __ldg(base + woff[j]);
     };
     long long tile = blockIdx.x;
     int n = 0, oh0 = 0, ow0 = 0;
     if (tile < g.tiles) {
         tile_coords(g, tile, n, oh0, ow0);
-        wr.load(thin, g, n, oh0, ow0, tid);
+        wr.load(thin, g, n, oh0, ow0);
         load_wide(n, oh0, ow0);
     }
     for (; tile < g.tiles; tile += gridDim.x) {
         __syncthreads();
-        wr.store(win, tid);
+        wr.store(win);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int i = tid + j * 160;
-            if (i < TH * TW * 4) *reinterpret_cast<uint4*>(wd + (i >> 2) * XPITCH + (i & 3) * 8) = wq[j];
+            if (woff[j] >= 0) *reinterpret_cast<uint4*>(wd + (i >> 2) * XPITCH + (i & 3) * 8) = wq[j];
         }
         __syncthreads();
         if (tile + gridDim.x < g.tiles) {                    // next tile's loads fly during this tile's contraction
             tile_coords(g, tile + gridDim.x, n, oh0, ow0);
-            wr.load(thin, g, n, oh0, ow0, tid);
+            wr.load(thin, g, n, oh0, ow0);
             load_wide(n, oh0, ow0);
         }
 #pragma unroll 2
@@ -423,7 +458,7 @@ bool make_geo(ThinGeo& g, int N, int Hb, int Wb, int Ct, int Cw, int kh, int kw,
     if (g.pt != 1 || g.pl != 1) return false;              // even sizes, k = 5, stride 2: TF SAME pads 1 before, 2 after
     g.tiles_x = g.Ws / TW; g.tiles_y = g.Hs / TH;
     g.tiles = (long long)N * g.tiles_x * g.tiles_y;
-    return true;
+    return g.tiles < (1ll << 31) && (long long)N * Hb * Wb * 4 < (1ll << 31);      // 32-bit tile / offset arithmetic in the kernels
 }
 }  // namespace
 
