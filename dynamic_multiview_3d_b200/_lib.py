@@ -14,6 +14,7 @@ ACT = {None: 0, "none": 0, "lrelu": 1, "relu": 2, "tanh": 3}
 LOSS = {"l2": 0, "l1": 1}
 DT_BF16, DT_F32, DT_S2D = 0, 1, 2
 ALGO = {"auto": 0, "simt": 1, "tcgen05": 2}
+ALGO_PACK_ONLY, ALGO_PREPACKED = 0x100, 0x200
 SAMPLER_ADD_GRID, SAMPLER_GRID_XY = 1, 2
 
 _vp, _i, _ll, _f, _sz, _u = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t, C.c_uint

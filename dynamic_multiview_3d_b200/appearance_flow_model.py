@@ -85,19 +85,21 @@ class AppearanceFlowModel(ModelBase):
         a1 = linear_msra(a0, 64, "a1", act="lrelu", algo=self.algo)
         return linear_msra(a1, 64, "a2", act="lrelu", algo=self.algo)
 
-    def _viewpoint_code(self, disp):
-        """decodeAngle on a branch stream: independent of the image encoder until the concat (functional.branch)."""
+    def _viewpoint_fork(self, disp):
+        """decodeAngle on a branch stream, started BEFORE the image encoder is enqueued (it is independent of it until the
+        concat): returns a callable that joins the branch and yields the viewpoint code (functional.branch)."""
         if os.environ.get("DMV_VIEW_BRANCH", "1") != "1" or disp.device.type != "cuda":
-            return self.decodeAngle(disp)
+            return lambda: self.decodeAngle(disp)
         with F.branch(disp.device, disp) as br:
             code = self.decodeAngle(disp)
-        return br.join(code)
+        return lambda: br.join(code)
 
     def buildModel(self, image0, disp):
         """appearance_flow_model.py:83-127 with the shape rule; activations fused into the layers."""
         B, H = image0.shape[0], image0.shape[1]
         h5 = H // 32
         a, g = self.ACT, self.algo
+        viewpoint_code = self._viewpoint_fork(disp)
         e0 = conv2d_msra(image0, 32, 5, 5, 2, 2, "e0", act=a, algo=g)
         e0_0 = conv2d_msra(e0, 32, 5, 5, 1, 1, "e0_0", act=a, algo=g)
         e1 = conv2d_msra(e0_0, 32, 5, 5, 2, 2, "e1", act=a, algo=g)
@@ -111,7 +113,7 @@ class AppearanceFlowModel(ModelBase):
         e4r = F.reshape(e4_0, (B, h5 * h5 * 256))                       # NHWC flatten, (h, w, c) order
         e5 = linear_msra(e4r, 4096, "fc1", act=a, algo=g)
 
-        concated = torch.cat([e5, self._viewpoint_code(disp)], dim=1)
+        concated = torch.cat([e5, viewpoint_code()], dim=1)
 
         a3 = linear_msra(concated, 4096, "a3", act=a, algo=g)
         a4 = linear_msra(a3, 4096, "a4", act=a, algo=g)
@@ -220,13 +222,14 @@ class AppearanceFlowTinghui(AppearanceFlowModel):
     def buildModel(self, image0, disp):
         B, H = image0.shape[0], image0.shape[1]
         g = self.algo
+        viewpoint_code = self._viewpoint_fork(disp)
         e = image0
         for name, c in [("e0", 16), ("e1", 32), ("e2", 64), ("e3", 128), ("e4", 256)]:
             e = conv2d_msra(e, c, 3, 3, 2, 2, name, act="relu", algo=g)
         e4r = F.reshape(e, (B, (H // 32) ** 2 * 256))
         e_fc0 = linear_msra(e4r, 2048, "e_fc0", act="relu", algo=g)
         e_fc1 = linear_msra(e_fc0, 2048, "e_fc1", act="relu", algo=g)
-        concated = torch.cat([e_fc1, self._viewpoint_code(disp)], dim=1)
+        concated = torch.cat([e_fc1, viewpoint_code()], dim=1)
         d_fc0 = linear_msra(concated, 2048, "a3", act="relu", algo=g)
         d_fc1 = linear_msra(d_fc0, (H // 16) ** 2 * 32, "a4", act="relu", algo=g)
         d = F.reshape(d_fc1, (B, H // 16, H // 16, 32))

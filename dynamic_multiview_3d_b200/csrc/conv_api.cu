@@ -9,6 +9,19 @@ using namespace dmv;
 #define DMV_CHECK_ALGO(algo) \
     DMV_REQUIRE((algo) == DMV_ALGO_AUTO || (algo) == DMV_ALGO_SIMT || (algo) == DMV_ALGO_TCGEN05, DMV_E_INVALID_ARG, "unknown algo")
 
+// DMV_ALGO_PACK_ONLY / DMV_ALGO_PREPACKED (include/dmv3d.h): split off the flag bits, arm the tensor-core launchers for the
+// duration of the call.  ``run`` is the tensor-core attempt of the entry point; under PACK_ONLY nothing else may execute.
+struct PackScope {
+    int mode;
+    explicit PackScope(int& algo) : mode(algo & (DMV_ALGO_PACK_ONLY | DMV_ALGO_PREPACKED)) {
+        algo &= ~(DMV_ALGO_PACK_ONLY | DMV_ALGO_PREPACKED);
+        tc_set_pack_mode(mode);
+    }
+    ~PackScope() { tc_set_pack_mode(0); }
+    bool pack_only() const { return mode == DMV_ALGO_PACK_ONLY; }
+};
+static int pack_only_result(int rc) { return (rc == DMV_E_UNSUPPORTED_SHAPE || rc == DMV_E_WORKSPACE) ? DMV_OK : rc; }
+
 // Input gradients with the producer's activation derivative folded in: dx <- dx * act'(y_in).  ``run`` launches the
 // input-gradient kernels; the tensor-core paths apply the factor in their epilogue (before the bf16 rounding), any other
 // path is followed by one elementwise pass in place.
@@ -87,8 +100,13 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias,
                    int Cin, int Cout, int kh, int kw, int stride, int act, void* workspace, size_t workspace_bytes, int algo,
                    void* stream) {
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "conv2d_fwd: null pointer");
+    PackScope pk(algo);
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pk.pack_only()) {
+        if (algo == DMV_ALGO_SIMT || thin_side(Cin) || x_dtype != DMV_DT_BF16) return DMV_OK;
+        return pack_only_result(tc_conv_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st));
+    }
     if (x_dtype == DMV_DT_S2D) {        // caller-kept space-to-depth tensor: only the tensor-core thin path understands it
         DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cin), DMV_E_INVALID_ARG, "conv2d_fwd: DMV_DT_S2D needs the tensor-core thin path");
         return tc_thin_fwd(x, x_dtype, w, bias, y, y_dtype, B, H, W, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st);
@@ -109,8 +127,13 @@ int dmv_conv2d_fwd(const void* x, int x_dtype, const void* w, const float* bias,
 int dmv_conv2d_dgrad(const void* dy, const void* w, void* dx, const void* y_in, int act_in, int B, int H, int W, int Cin, int Cout,
                      int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "conv2d_dgrad: null pointer");
+    PackScope pk(algo);
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pk.pack_only()) {
+        if (algo == DMV_ALGO_SIMT) return DMV_OK;
+        return pack_only_result(tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st));
+    }
     return dgrad_with_dact(y_in, act_in, dx, (long long)B * H * W * Cin, st, [&]() -> int {
         if (algo != DMV_ALGO_SIMT) {
             int rc = tc_conv_dgrad(dy, w, dx, B, H, W, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st);
@@ -163,8 +186,13 @@ generic:
 int dmv_deconv2d_fwd(const void* x, const void* w, void* y, int y_dtype, int B, int Hout, int Wout, int Cin, int Cout, int kh,
                      int kw, int stride, int act, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(x && w && y, DMV_E_INVALID_ARG, "deconv2d_fwd: null pointer");
+    PackScope pk(algo);
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pk.pack_only()) {
+        if (algo == DMV_ALGO_SIMT || thin_side(Cout)) return DMV_OK;
+        return pack_only_result(tc_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cin, Cout, kh, kw, stride, act, workspace, workspace_bytes, st));
+    }
     if (algo != DMV_ALGO_SIMT && thin_side(Cout)) {     // flow head: 2-channel output side
         int rc = thin_mma_deconv_fwd(x, w, y, y_dtype, B, Hout, Wout, Cout, Cin, kh, kw, stride, act, st);
         if (rc != DMV_E_UNSUPPORTED_SHAPE) return rc;
@@ -179,8 +207,13 @@ int dmv_deconv2d_fwd(const void* x, const void* w, void* y, int y_dtype, int B, 
 int dmv_deconv2d_dgrad(const void* dy, int dy_dtype, const void* w, void* dx, const void* y_in, int act_in, int B, int Hout, int Wout,
                        int Cin, int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int algo, void* stream) {
     DMV_REQUIRE(dy && w && dx, DMV_E_INVALID_ARG, "deconv2d_dgrad: null pointer");
+    PackScope pk(algo);
     DMV_CHECK_ALGO(algo);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pk.pack_only()) {
+        if (algo == DMV_ALGO_SIMT || thin_side(Cout) || dy_dtype != DMV_DT_BF16) return DMV_OK;
+        return pack_only_result(tc_deconv_dgrad(dy, dy_dtype, w, dx, B, Hout, Wout, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, st));
+    }
     if (dy_dtype == DMV_DT_S2D)
         DMV_REQUIRE(algo != DMV_ALGO_SIMT && thin_side(Cout), DMV_E_INVALID_ARG, "deconv2d_dgrad: DMV_DT_S2D needs the tensor-core thin path");
     const SamePad ph = same_pad(Hout, kh, stride), pw = same_pad(Wout, kw, stride);

@@ -771,6 +771,7 @@ struct Problem {
 
 // The activation-derivative factor of the NEXT input-gradient launch of this thread (tc_set_dact): taken by launch_igemm
 // when it finalises the parameters of a bf16-output launch.
+thread_local int tl_pack_mode = 0;     // tc_set_pack_mode: 0, DMV_ALGO_PACK_ONLY or DMV_ALGO_PREPACKED
 thread_local const void* tl_dact_y = nullptr;
 thread_local int tl_dact = 0;
 thread_local bool tl_dact_taken = false;
@@ -910,9 +911,13 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         if (!workspace || ws_bytes < need) return fail(DMV_E_WORKSPACE, "tc: workspace too small for packed weights");
         long long blocks = ceil_div_ll((long long)taps_total * q.w_ci * q.w_co, 256);
         if (blocks > 2048) blocks = 2048;
-        pack_f_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)q.w_hwio, (bf16*)workspace, taps_total, q.w_ci, q.w_co);
-        int rc = check_launch("tc pack weights");
-        if (rc) return rc;
+        int rc = DMV_OK;
+        if (tl_pack_mode != DMV_ALGO_PREPACKED) {
+            pack_f_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)q.w_hwio, (bf16*)workspace, taps_total, q.w_ci, q.w_co);
+            rc = check_launch("tc pack weights");
+            if (rc) return rc;
+        }
+        if (tl_pack_mode == DMV_ALGO_PACK_ONLY) return DMV_OK;
         const cuuint64_t ktot = (cuuint64_t)taps_total * q.w_ci;
         cuuint64_t dims[3] = {ktot, (cuuint64_t)q.w_co, 1};
         cuuint64_t strides[2] = {ktot * 2, ktot * 2 * (cuuint64_t)q.w_co};
@@ -920,6 +925,7 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
         rc = encode_map(&map_b, workspace, 3, dims, strides, box, row_bytes);
         if (rc) return rc;
     }
+    if (tl_pack_mode == DMV_ALGO_PACK_ONLY) return DMV_OK;      // a form that reads the weights in place: nothing to pack
     // ---- halo variant (see halo_kernel)
     if (halo_ok) {
         CUtensorMap map_h;
@@ -1167,9 +1173,13 @@ int launch_f_s2(const void* src, int N, int Hs, int Ws, const void* w, int kh, i
         }
     const size_t need = (size_t)n_real * t.n * 64 * 2;
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 15)) return fail(DMV_E_WORKSPACE, "tc stride-2 halo: workspace too small");
-    pack_f_s2_kernel<<<ceil_div(n_real * t.n * 64, 256), 256, 0, st>>>((const bf16*)w, (bf16*)ws, kw, 32, n_real, t);
-    int rc = check_launch("tc pack stride-2");
-    if (rc) return rc;
+    int rc = DMV_OK;
+    if (tl_pack_mode != DMV_ALGO_PREPACKED) {
+        pack_f_s2_kernel<<<ceil_div(n_real * t.n * 64, 256), 256, 0, st>>>((const bf16*)w, (bf16*)ws, kw, 32, n_real, t);
+        rc = check_launch("tc pack stride-2");
+        if (rc) return rc;
+    }
+    if (tl_pack_mode == DMV_ALGO_PACK_ONLY) return DMV_OK;
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.num_classes = 1;
@@ -1219,9 +1229,12 @@ int launch_subpixel(const void* src, int N, int Hs, int Ws, int Cs, const void* 
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 15)) return fail(DMV_E_WORKSPACE, "tc subpixel: workspace too small");
     long long blocks = ceil_div_ll((long long)n_rows * t.S * Cs, 256);
     if (blocks > 1184) blocks = 1184;
-    pack_subpixel_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)w, (bf16*)ws, n_real, Cs, n_rows, t);
-    rc = check_launch("tc pack subpixel");
-    if (rc) return rc;
+    if (tl_pack_mode != DMV_ALGO_PREPACKED) {
+        pack_subpixel_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)w, (bf16*)ws, n_real, Cs, n_rows, t);
+        rc = check_launch("tc pack subpixel");
+        if (rc) return rc;
+    }
+    if (tl_pack_mode == DMV_ALGO_PACK_ONLY) return DMV_OK;
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.num_classes = 1;
@@ -1244,6 +1257,8 @@ int launch_subpixel(const void* src, int N, int Hs, int Ws, int Cs, const void* 
 // entry points used by conv_api.cu
 // ----------------------------------------------------------------------------------------------
 namespace dmv {
+void tc_set_pack_mode(int mode) { tl_pack_mode = mode; }
+
 void tc_set_dact(const void* y_bf16, int act) {
     tl_dact_y = (act != DMV_ACT_NONE) ? y_bf16 : nullptr;
     tl_dact = act;

@@ -14,7 +14,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT, ALGO, DT_BF16, DT_F32, DT_S2D, LOSS, SAMPLER_ADD_GRID, SAMPLER_GRID_XY
+from ._lib import ACT, ALGO, ALGO_PACK_ONLY, ALGO_PREPACKED, DT_BF16, DT_F32, DT_S2D, LOSS, SAMPLER_ADD_GRID, SAMPLER_GRID_XY
 from ._lib import call as _real_call
 
 _workspaces = {}
@@ -178,7 +178,9 @@ class branch:
             key = (device.type, device.index, "branch")
             st = _side.get(key)
             if st is None:
-                st = _side[key] = torch.cuda.Stream(device=device)
+                # same (high) priority as the captured main chain (train.py): the branch is a handful of tiny kernels, and at
+                # the default priority they starved behind the chain's persistent grids until the chain itself blocked on them
+                st = _side[key] = torch.cuda.Stream(device=device, priority=-1)
             self.stream, self.key = st, key
             for t in inputs:
                 t.record_stream(st)
@@ -268,6 +270,72 @@ def workspace(nbytes, device):
     return ws
 
 
+# --- weight packing off the critical chain ------------------------------------------------------------------------
+# Several tensor-core forms read the bf16 weights in a packed layout written by a small kernel in front of the layer
+# (include/dmv3d.h: DMV_ALGO_PACK_ONLY / DMV_ALGO_PREPACKED): ~20 launches of 2-8 us per step that sat on the forward /
+# input-gradient chain (profiles/r02_timeline_immediate.txt).  A layer registers its packing call the first time it runs;
+# from then on the train step replays all of them on a side stream at its start (the weights are final by then: Adam ran at
+# the end of the previous step) into per-layer buffers, and the layer waits for its event and skips the packing kernel.
+class Prepack(object):
+    def __init__(self, store):
+        self.store = store
+        self.entries = {}          # key -> [pack_call(ws, flags, stream), buffer, event or None]
+        self.live = False
+        self.stream = None
+
+    @staticmethod
+    def enabled(store):
+        import os
+        return store.device.type == "cuda" and os.environ.get("DMV_PREPACK", "1") == "1" and not _meta_depth[0] and _profile[0] is None
+
+    def register(self, key, nbytes, pack_call):
+        if key not in self.entries:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.store.device)
+            self.entries[key] = [pack_call, buf, None]
+
+    def begin(self):
+        """Start of a train step: pack every registered layer's weights on the side stream."""
+        if not self.entries:
+            return
+        dev = self.store.device
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            for e in self.entries.values():
+                e[0](e[1], ALGO_PACK_ONLY, self.stream.cuda_stream)
+                e[2] = torch.cuda.Event()
+                e[2].record(self.stream)
+        self.live = True
+
+    def take(self, key):
+        """(buffer, PREPACKED flag) if this step packed ``key`` -- the current stream then waits for it -- else None."""
+        if not self.live:
+            return None
+        e = self.entries.get(key)
+        if e is None or e[2] is None:
+            return None
+        torch.cuda.current_stream(self.store.device).wait_event(e[2])
+        return e[1]
+
+    def end(self):
+        if self.live:
+            self.live = False
+            torch.cuda.current_stream(self.store.device).wait_stream(self.stream)
+            for e in self.entries.values():
+                e[2] = None
+
+
+def _prepack_of(store):
+    pp = getattr(store, "prepack", None)
+    if pp is None and Prepack.enabled(store):
+        pp = store.prepack = Prepack(store)
+    return pp if (pp is not None and Prepack.enabled(store)) else None
+
+
 def same_out(n, s):
     return -(-n // s)
 
@@ -346,8 +414,19 @@ class _Conv2d(torch.autograd.Function):
             xs = torch.empty(n2, dtype=torch.uint8, device=x.device)
             call("dmv_thin_s2d_prep", _p(x), _dt(x), _p(xs), B, H, W, Cin, _stream(x))
             xs_dt = DT_S2D
+        pp = _prepack_of(wvar.store) if (Cin >= 8 and xs_dt == DT_BF16) else None
+        flags = 0
+        if pp is not None:
+            key, ydt, a = (wvar.name, "fwd"), _dt(y), ACT[act]
+            pre = pp.take(key)
+            if pre is not None:
+                ws, flags = pre, ALGO_PREPACKED
+            else:                  # (pointers are read at packing time: data_parallel.attach may re-home the bf16 buffer)
+                pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                    "dmv_conv2d_fwd", buf.data_ptr(), DT_BF16, wvar.half.data_ptr(), None, buf.data_ptr(), ydt, B, H, W, Cin, Cout, kh, kw, stride, a,
+                    buf.data_ptr(), buf.numel(), algo | fl, s_))
         call("dmv_conv2d_fwd", _p(xs), xs_dt, _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
-             B, H, W, Cin, Cout, kh, kw, stride, ACT[act], _p(ws), ws.numel(), algo, _stream(x))
+             B, H, W, Cin, Cout, kh, kw, stride, ACT[act], _p(ws), ws.numel(), algo | flags, _stream(x))
         ctx.save_for_backward(x if ctx.needs_input_grad[1] or not n2 else xs, y, xs)
         ctx.xshape, ctx.xdtype, ctx.xs_dt = tuple(x.shape), x.dtype, xs_dt
         ctx.cfg = (wvar, bvar, stride, act, algo)
@@ -386,8 +465,19 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx = torch.empty(ctx.xshape, dtype=torch.bfloat16, device=y.device)
             ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), y.device)
+            pp = _prepack_of(wvar.store) if in_cell is None else None
+            flags = 0
+            if pp is not None:
+                key = (wvar.name, "dgrad")
+                pre = pp.take(key)
+                if pre is not None:
+                    ws, flags = pre, ALGO_PREPACKED
+                else:
+                    pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                        "dmv_conv2d_dgrad", buf.data_ptr(), wvar.half.data_ptr(), buf.data_ptr(), None, 0, B, H, W, Cin, Cout, kh, kw, stride,
+                        buf.data_ptr(), buf.numel(), algo | fl, s_))
             call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
-                 ACT[in_cell.act] if in_cell is not None else 0, B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
+                 ACT[in_cell.act] if in_cell is not None else 0, B, H, W, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo | flags, st)
             if ctx.xdtype != torch.bfloat16:
                 dxf = torch.empty(ctx.xshape, dtype=ctx.xdtype, device=y.device)
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
@@ -420,8 +510,19 @@ class _Deconv2d(torch.autograd.Function):
         y = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
         ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
+        pp = _prepack_of(wvar.store) if Cout >= 8 else None
+        flags = 0
+        if pp is not None:
+            key, ydt, a = (wvar.name, "fwd"), _dt(y), ACT[act]
+            pre = pp.take(key)
+            if pre is not None:
+                ws, flags = pre, ALGO_PREPACKED
+            else:
+                pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                    "dmv_deconv2d_fwd", buf.data_ptr(), wvar.half.data_ptr(), buf.data_ptr(), ydt, B, Ho, Wo, Cin, Cout, kh, kw, stride, a, buf.data_ptr(),
+                    buf.numel(), algo | fl, s_))
         call("dmv_deconv2d_fwd", _p(x), _p(wvar.half), _p(y), _dt(y), B, Ho, Wo, Cin, Cout, kh, kw, stride, ACT[act], _p(ws),
-             ws.numel(), algo, _stream(x))
+             ws.numel(), algo | flags, _stream(x))
         ctx.save_for_backward(x, y)
         ctx.cfg = (wvar, stride, act, algo)
         ctx.cells = (in_cell, out_cell)
@@ -455,8 +556,19 @@ class _Deconv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
             ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
+            pp = _prepack_of(wvar.store) if (in_cell is None and Cout >= 8 and dps_dt == DT_BF16) else None
+            flags = 0
+            if pp is not None:
+                key = (wvar.name, "dgrad")
+                pre = pp.take(key)
+                if pre is not None:
+                    ws, flags = pre, ALGO_PREPACKED
+                else:
+                    pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                        "dmv_deconv2d_dgrad", buf.data_ptr(), DT_BF16, wvar.half.data_ptr(), buf.data_ptr(), None, 0, B, Ho, Wo, Cin, Cout, kh, kw, stride,
+                        buf.data_ptr(), buf.numel(), algo | fl, s_))
             call("dmv_deconv2d_dgrad", _p(dps), dps_dt, _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
-                 ACT[in_cell.act] if in_cell is not None else 0, B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo, st)
+                 ACT[in_cell.act] if in_cell is not None else 0, B, Ho, Wo, Cin, Cout, kh, kw, stride, _p(ws), ws.numel(), algo | flags, st)
         nws = _lib.load().dmv_wgrad_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
         wctx, wsf = _wgrad_ctx(x.device, x, dps)
         with wctx:

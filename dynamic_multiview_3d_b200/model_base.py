@@ -39,6 +39,16 @@ class ModelBase(object):
         dp = getattr(self, "_dp", None)
         if dp is not None and hasattr(dp, "apply_deferred"):
             dp.apply_deferred()    # the late FC matrices take the previous step's update next to this step's encoder forward
+        pp = getattr(self.store, "prepack", None)
+        if pp is not None:
+            pp.begin()             # every layer's packed weights for this step, on a side stream (functional.Prepack)
+        try:
+            return self._train_step_body(args)
+        finally:
+            if pp is not None:
+                pp.end()
+
+    def _train_step_body(self, args):
         loss = self.step_loss(self._as_batch(args))
         opt = self.optimizer
         opt.begin_step()           # single process: the big FC matrices are updated inside backward (optimizer.py)

@@ -48,6 +48,7 @@ class VariableStore:
         self.record = None              # dict: layer name -> activation, filled by tf_utils ops when set (tests)
         self.adam_live = None           # the optimizer, between its begin_step() and the end of backward (fused FC update)
         self.pre_use_hook = None        # called with a Variable before a layer reads it (deferred updates, data_parallel.py)
+        self.prepack = None             # functional.Prepack: per-step weight packing on a side stream
         # dummy differentiable leaf: keeps the autograd tape alive for layers whose only
         # differentiable inputs are parameters (gradients of parameters bypass autograd)
         self.anchor = None

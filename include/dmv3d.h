@@ -61,6 +61,14 @@ extern "C" {
 #define DMV_ALGO_AUTO 0    /* tcgen05/TMEM/TMA implicit GEMM where the shape allows, else SIMT */
 #define DMV_ALGO_SIMT 1    /* straightforward CUDA-core kernels (bring-up + on-GPU cross-check)  */
 #define DMV_ALGO_TCGEN05 2 /* force the tensor-core path; DMV_E_UNSUPPORTED_SHAPE if it cannot  */
+/* Weight packing split from the layer call (OR-ed into `algo` of dmv_conv2d_fwd / dmv_conv2d_dgrad / dmv_deconv2d_fwd /
+ * dmv_deconv2d_dgrad).  Some tensor-core forms read the bf16 weights in a packed layout that the call writes into the head
+ * of `workspace` first.  PACK_ONLY: do just that (same shape arguments, same workspace; x / y / dx may be any non-null
+ * pointers) and return -- a no-op for forms that need no packing.  PREPACKED: the workspace already holds this layer's
+ * packed weights (a PACK_ONLY call with identical arguments ran after the last weight update): skip the packing kernel.
+ * The train step packs every layer once per step on a side stream, off the forward / input-gradient chain. */
+#define DMV_ALGO_PACK_ONLY 0x100
+#define DMV_ALGO_PREPACKED 0x200
 
 /* ---- library info ------------------------------------------------------------------- */
 int dmv_version(void);                      /* MAJOR*10000 + MINOR*100 + PATCH */

@@ -385,3 +385,27 @@ def test_deferred_fc_update_is_bit_identical(graphed, monkeypatch):
         assert torch.equal(t, out["auto"][2][k]), k
     for k, t in out["0"][3].items():
         assert torch.equal(t, out["auto"][3][k]), k
+
+
+def test_prepacked_weights_give_identical_steps(monkeypatch):
+    """functional.Prepack: from the second train step on, every layer's packed weight layout is written once per step on a
+    side stream (DMV_ALGO_PACK_ONLY) and the layers skip their packing kernel (DMV_ALGO_PREPACKED).  Same kernels, same
+    operands: losses and parameters equal those of the inline packing bit for bit, with fewer launches on the main chain."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200 import _lib
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "seed": 13}
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DMV_PREPACK", mode)
+        m = pkg.AppearanceFlowModel(conf)
+        losses = [float(m.train_step(*args)) for _ in range(4)]
+        val = float(m.eval_loss(*args))                  # outside train_step: inline packing again
+        out[mode] = (losses, val, {k: v.master.clone() for k, v in m.store.vars.items()})
+        if mode == "1":
+            assert m.store.prepack is not None and len(m.store.prepack.entries) >= 10
+    assert out["1"][0] == out["0"][0] and out["1"][1] == out["0"][1]
+    for k, t in out["0"][2].items():
+        assert torch.equal(t, out["1"][2][k]), k
