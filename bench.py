@@ -64,7 +64,11 @@ def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full summary
     (profiles/r01_traffic.json, written by tools/summarise_ncu.py); None when the kernel was not captured."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kernel)
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+            if v is not None:
+                return v
+        return None
     except Exception:
         return None
 
@@ -459,7 +463,7 @@ def main():
                 nbytes = 24.0 * var.numel
                 gbs = nbytes / (dms * 1e-3) / 1e9
                 roof = {"bound": "hbm", "kernel": "dmv_linear_wgrad_adam[%s]" % dtag, "achieved": round(gbs, 1), "peak": pk["hbm_gbs"],
-                        "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": ncu_traffic("fc_wgrad_adam_kernel"),
+                        "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": ncu_traffic("fc_wgrad_adam_stream_kernel"),
                         "peak_src": pk["src"], "bytes_per_launch": nbytes, "bytes_moved_per_launch": 26.0 * var.numel,
                         "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
             elif lname in gf:
@@ -471,11 +475,12 @@ def main():
             elif dtag == "adam":
                 # 28 B/param (read theta, g, m, v; write theta, m, v).  The kernel also writes the bf16 compute
                 # copy (2 B/param), reported separately as bytes_moved_per_launch; `achieved` uses the 8(d) figure.
-                nbytes = 28.0 * pmodel.store.total
+                n_adam = pmodel.store.total - sum(v.numel for v in pmodel.store.vars.values() if v.fused_adam)   # fc1 is updated by its
+                nbytes = 28.0 * n_adam                                                                        # weight-gradient kernel
                 gbs = nbytes / (dms * 1e-3) / 1e9
                 roof = {"bound": "hbm", "kernel": "dmv_adam_multi", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": ncu_traffic("adam_multi_kernel"), "peak_src": pk["src"],
-                        "bytes_per_launch": nbytes, "bytes_moved_per_launch": 30.0 * pmodel.store.total,
+                        "bytes_per_launch": nbytes, "bytes_moved_per_launch": 30.0 * n_adam, "params": n_adam,
                         "ms": round(dms, 4), "share_of_step": round(dms / total, 4)}
         except Exception as ex:      # the profile is explanatory; never lose the bench line over it
             roof = {"error": repr(ex)[:200]}

@@ -153,7 +153,7 @@ fc_wgrad_adam_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 // tiles (104 KB) are in flight per SM while the third is consumed.  Row pitches are padded (576 B / 80 B) so that the
 // float4 reads and the ldmatrix rows are conflict-free.  (Row-wise cp.async.bulk copies were measured first: 160 small
 // bulk requests per tile ran at 2 TB/s.)
-constexpr int SR = 32, SC = 128, STAGES = 3;
+constexpr int SR = 32, SC = 128, STAGES = 3, STREAM_THREADS = 512;
 constexpr int PP = SC + 16;                   // floats per parameter row in shared memory (576 B)
 constexpr int SXP = SR + 8;                   // bf16 per x row (80 B)
 constexpr size_t STREAM_PAR_BYTES = (size_t)STAGES * 3 * SR * PP * sizeof(float);
@@ -168,7 +168,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
 fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ theta,
                             float* __restrict__ mom, float* __restrict__ vel, __nv_bfloat16* __restrict__ half, float* __restrict__ dw_out,
                             int M, int K, int N, const float* __restrict__ state, float omb1, float omb2, float eps, float gscale) {
@@ -177,7 +177,7 @@ fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bflo
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + STREAM_PAR_BYTES);                  // [STAGES][64][SXP]
     __nv_bfloat16* ds = reinterpret_cast<__nv_bfloat16*>(smem + STREAM_PAR_BYTES + STREAM_X_BYTES);   // [64][DP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wk = warp & 1, wn = warp >> 1;            // 2 x 4 warps: 16 rows x 32 columns each
+    const int wk = warp & 1, wn = warp >> 1;            // 2 x 8 warps: 16 rows x 16 columns each (one column group)
     const int g = lane >> 2, t = lane & 3, mat = lane >> 3, r = lane & 7;
     const int KT = K / SR;
     const long long T = (long long)(N / SC) * KT;
@@ -186,19 +186,19 @@ fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bflo
     if (ntiles <= 0) return;
 
     // sample rows >= M of the x tiles stay zero for the whole kernel (the copies only write rows < M)
-    for (int i = tid; i < (int)(STREAM_X_BYTES / 16); i += 256) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(STREAM_X_BYTES / 16); i += STREAM_THREADS) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
-    // a tile's copies: 3 arrays x 32 rows x 32 chunks of 16 B (12 per thread) + M rows x 4 chunks of the x tile
-    const int prow = tid >> 5, pch = tid & 31;          // this thread copies chunk pch of rows prow + 8 j
+    // a tile's copies: 3 arrays x 32 rows x 32 chunks of 16 B (6 per thread) + M rows x 4 chunks of the x tile
+    const int prow = tid >> 5, pch = tid & 31;          // this thread copies chunk pch of rows prow + 16 j
     auto issue = [&](int i) {
         if (i < ntiles) {
             const long long tl = first + i;
             const int strip = (int)(tl / KT), kt = (int)(tl % KT), s = i % STAGES;
             const long long base = (long long)kt * SR * N + (long long)strip * SC + pch * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int row = prow + 8 * j;
+            for (int j = 0; j < 2; ++j) {
+                const int row = prow + 16 * j;
                 const long long o = base + (long long)row * N;
                 float* d = par + (s * 3 * SR + row) * PP + pch * 4;
                 cp_async16(d, theta + o);
@@ -206,7 +206,7 @@ fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bflo
                 cp_async16(d + 2 * SR * PP, vel + o);
             }
             const int c = tid >> 2, q = tid & 3;
-            if (c < M) cp_async16(xs + (s * TC + c) * SXP + q * 8, x + (long long)c * K + kt * SR + q * 8);
+            if (tid < 4 * TC && c < M) cp_async16(xs + (s * TC + c) * SXP + q * 8, x + (long long)c * K + kt * SR + q * 8);
         }
         cp_async_commit();
     };
@@ -221,7 +221,7 @@ fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bflo
         const int strip = (int)(tl / KT), kt = (int)(tl % KT), s = i % STAGES;
         if (strip != cur_strip) {                  // (every warp passed the __syncthreads that ended the previous tile)
             cur_strip = strip;
-            for (int j = tid; j < TC * (SC / 8); j += 256) {
+            for (int j = tid; j < TC * (SC / 8); j += STREAM_THREADS) {
                 const int c = j >> 4, u = j & 15;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (c < M) v = __ldg(reinterpret_cast<const uint4*>(dy + (long long)c * N + strip * SC + u * 8));
@@ -231,33 +231,26 @@ fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bflo
         cp_async_wait<STAGES - 1>();               // this thread's copies of tile i have landed ...
         __syncthreads();                           // ... and everybody else's
 
-        float acc[2][2][4];
+        float acc[2][4];
 #pragma unroll
-        for (int G = 0; G < 2; ++G)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[G][j][e] = 0.f;
+            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
         const __nv_bfloat16* xt = xs + s * TC * SXP;
         for (int q = 0; q < ksteps; ++q) {
             unsigned a[4];
             ldsm_x4_t(a[0], a[1], a[2], a[3], xt + (q * 16 + r + (mat >> 1) * 8) * SXP + wk * 16 + (mat & 1) * 8);
-#pragma unroll
-            for (int G = 0; G < 2; ++G) {
-                unsigned b0, b1, b2, b3;
-                ldsm_x4_t(b0, b1, b2, b3, ds + (q * 16 + r + (mat & 1) * 8) * DP + wn * 32 + G * 16 + (mat >> 1) * 8);
-                mma_bf16(acc[G][0], a, b0, b1);
-                mma_bf16(acc[G][1], a, b2, b3);
-            }
+            unsigned b0, b1, b2, b3;
+            ldsm_x4_t(b0, b1, b2, b3, ds + (q * 16 + r + (mat & 1) * 8) * DP + wn * 16 + (mat >> 1) * 8);
+            mma_bf16(acc[0], a, b0, b1);
+            mma_bf16(acc[1], a, b2, b3);
         }
         const float* pt = par + (s * 3) * SR * PP;
 #pragma unroll
-        for (int G = 0; G < 2; ++G)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int row = wk * 16 + g + 8 * h, col = wn * 32 + G * 16 + 4 * t;
+        for (int h = 0; h < 2; ++h) {
+                const int row = wk * 16 + g + 8 * h, col = wn * 16 + 4 * t;
                 const long long o = ((long long)kt * SR + row) * N + (long long)strip * SC + col;
-                const float gr[4] = {acc[G][0][2 * h], acc[G][0][2 * h + 1], acc[G][1][2 * h], acc[G][1][2 * h + 1]};
+                const float gr[4] = {acc[0][2 * h], acc[0][2 * h + 1], acc[1][2 * h], acc[1][2 * h + 1]};
                 adam4_store(*reinterpret_cast<const float4*>(pt + row * PP + col), *reinterpret_cast<const float4*>(pt + (SR + row) * PP + col),
                             *reinterpret_cast<const float4*>(pt + (2 * SR + row) * PP + col), gr, theta, mom, vel, half, dw_out, o, lr_t, omb1,
                             omb2, eps, gscale);
@@ -302,7 +295,7 @@ int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta,
         const long long tiles = (long long)(K / SR) * (N / SC);
         long long grid = ctas_env > 0 ? ctas_env : sms;
         if (grid > tiles) grid = tiles;
-        fc_wgrad_adam_stream_kernel<<<(unsigned)grid, 256, STREAM_SMEM, st>>>((const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy_bf16, theta, m,
+        fc_wgrad_adam_stream_kernel<<<(unsigned)grid, STREAM_THREADS, STREAM_SMEM, st>>>((const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy_bf16, theta, m,
                                                                             v, (__nv_bfloat16*)bf16_copy, dw_out, M, K, N, state4, omb1, omb2,
                                                                             eps, grad_scale);
         return dmv::check_launch("linear_wgrad_adam (stream)");
