@@ -32,19 +32,18 @@ class TFAdam:
         # weight gradient, during backward (functional._Linear.backward) -- the gradient is never written.  The model's
         # train_step brackets backward with begin_step() / step(); a bare loss.backward() still writes plain gradients.
         # data_parallel.attach() clears the marks when the gradients must be exchanged first (world > 1).
-        # MEASURED (profiles/r02_fc_adam.txt, r02_fuse_defer_sweep.txt): the fused kernel moves 26 instead of 34 B/parameter
-        # and is 14 % faster than the two calls when timed alone (715 vs 829 us for the four matrices).  Inside the step the
-        # best split is: fc1 fused (its update has to finish inside the step anyway), a3 / a4 / a5 updated by the plain Adam
-        # chunks at the start of the next step (data_parallel.py, deferred): 2.72 ms against 2.77 with no fusion and 2.77
-        # with all four fused.
+        # MEASURED (profiles/r02_fc_adam_512.txt, r02_fuse_defer_sweep.txt): the fused kernel moves 26 instead of 34
+        # B/parameter and runs at 0.88 of the HBM peak: 640 us for the four matrices against 827 us for the two calls.
+        # Inside the step the best split is fc1 / a3 / a4 fused and a5 updated by the plain Adam chunks at the start of the
+        # next step (deferred, data_parallel.py): 2.58 ms, against 2.63 with all four fused and 2.61 with fc1 alone.
         self._ticked = False
-        # "auto": the first-created eligible matrix (fc1 -- the one whose gradient arrives last and whose update cannot be
-        # deferred into the next forward pass, data_parallel.py) | "0" | "1" (every eligible matrix) | comma-separated names
+        # "auto": every eligible matrix but the last-created one (a5: its gradient is the first to arrive, and its plain Adam
+        # chunks are deferred into the next forward pass, data_parallel.py) | "0" | "1" (every eligible matrix) | names
         fuse = os.environ.get("DMV_FUSE_FC_ADAM", "auto")
         if fuse != "0" and store.device.type == "cuda":
             cand = [v for v in self.vars if fusable(v)]
             for v in cand:
-                v.fused_adam = (fuse == "1") or (fuse == "auto" and v is cand[0]) or (v.name in fuse.split(","))
+                v.fused_adam = (fuse == "1") or (fuse == "auto" and (v is not cand[-1] or len(cand) == 1)) or (v.name in fuse.split(","))
         # contiguous runs of trainable variables collapse into single tensors (the flat
         # buffers are contiguous), which keeps the launch count at one in the common case
         self._coalesce()
