@@ -288,7 +288,7 @@ int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta,
         if (variant == 9 && cudaFuncSetAttribute(fc_wgrad_adam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STREAM_SMEM) !=
                                 cudaSuccess) {
             cudaGetLastError();
-            variant = 4;
+            variant = 1;
         }
     }
     if (variant == 9 && M <= TC && K % SR == 0 && N % SC == 0) {
@@ -306,8 +306,8 @@ int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta,
     fc_wgrad_adam_kernel<PFV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy_bf16, theta, m, v,             \
                                                    (__nv_bfloat16*)bf16_copy, dw_out, M, K, N, state4, omb1, omb2, eps, grad_scale)
     if (variant == 0) DMV_FC_LAUNCH(0);
-    else if (variant == 1) DMV_FC_LAUNCH(1);
-    else DMV_FC_LAUNCH(4);
+    else if (variant == 4) DMV_FC_LAUNCH(4);
+    else DMV_FC_LAUNCH(1);            // the best generic form (profiles/r02_fc_adam.txt): shapes the streaming kernel does not take
 #undef DMV_FC_LAUNCH
     return dmv::check_launch("linear_wgrad_adam");
 }

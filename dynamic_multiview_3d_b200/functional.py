@@ -262,7 +262,10 @@ def _wgrad_ctx(device, *keep, lane=0):
 def workspace(nbytes, device):
     """One growable scratch buffer per device AND stream: launches that share it are ordered on that stream (the
     forward / dgrad chain on the main stream, an independent branch of the graph on its own)."""
-    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
+    # keyed by the ROLE of the current stream, not by the stream object: capture streams come and go (one per captured
+    # graph) and a buffer per stream object would never be released
+    br = _side.get((device.type, device.index, "branch")) if device.type == "cuda" else None
+    key = (device.type, device.index, "branch" if (br is not None and torch.cuda.current_stream(device) == br) else "main")
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -406,7 +409,8 @@ class _Conv2d(torch.autograd.Function):
         assert wcin == Cin, (wvar.name, wvar.shape, x.shape)
         y = torch.empty((B, same_out(H, stride), same_out(W, stride), Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
-        ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), x.device)
+        need = _lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
+        ws = workspace(need, x.device)
         # thin stride-2 layer (e0): build the space-to-depth tensor once and keep it for the weight gradient
         xs, xs_dt = x, _dt(x)
         n2 = _lib.load().dmv_thin_s2d_size(B, H, W, Cin, Cout, kh, kw, stride) if (Cin < 8 and algo != ALGO["simt"] and not _meta_depth[0]) else 0
@@ -422,7 +426,7 @@ class _Conv2d(torch.autograd.Function):
             if pre is not None:
                 ws, flags = pre, ALGO_PREPACKED
             else:                  # (pointers are read at packing time: data_parallel.attach may re-home the bf16 buffer)
-                pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                pp.register(key, need, lambda buf, fl, s_: call(
                     "dmv_conv2d_fwd", buf.data_ptr(), DT_BF16, wvar.half.data_ptr(), None, buf.data_ptr(), ydt, B, H, W, Cin, Cout, kh, kw, stride, a,
                     buf.data_ptr(), buf.numel(), algo | fl, s_))
         call("dmv_conv2d_fwd", _p(xs), xs_dt, _p(wvar.half), _p(bvar.master) if bvar is not None else None, _p(y), _dt(y),
@@ -464,7 +468,8 @@ class _Conv2d(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty(ctx.xshape, dtype=torch.bfloat16, device=y.device)
-            ws = workspace(_lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride), y.device)
+            need = _lib.load().dmv_conv_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
+            ws = workspace(need, y.device)
             pp = _prepack_of(wvar.store) if in_cell is None else None
             flags = 0
             if pp is not None:
@@ -473,7 +478,7 @@ class _Conv2d(torch.autograd.Function):
                 if pre is not None:
                     ws, flags = pre, ALGO_PREPACKED
                 else:
-                    pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                    pp.register(key, need, lambda buf, fl, s_: call(
                         "dmv_conv2d_dgrad", buf.data_ptr(), wvar.half.data_ptr(), buf.data_ptr(), None, 0, B, H, W, Cin, Cout, kh, kw, stride,
                         buf.data_ptr(), buf.numel(), algo | fl, s_))
             call("dmv_conv2d_dgrad", _p(dpre), _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
@@ -509,7 +514,8 @@ class _Deconv2d(torch.autograd.Function):
         assert same_out(Ho, stride) == Hin and same_out(Wo, stride) == Win, "output_shape inconsistent with input"
         y = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
         _tag[0] = wvar.name
-        ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
+        need = _lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
+        ws = workspace(need, x.device)
         pp = _prepack_of(wvar.store) if Cout >= 8 else None
         flags = 0
         if pp is not None:
@@ -518,7 +524,7 @@ class _Deconv2d(torch.autograd.Function):
             if pre is not None:
                 ws, flags = pre, ALGO_PREPACKED
             else:
-                pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                pp.register(key, need, lambda buf, fl, s_: call(
                     "dmv_deconv2d_fwd", buf.data_ptr(), wvar.half.data_ptr(), buf.data_ptr(), ydt, B, Ho, Wo, Cin, Cout, kh, kw, stride, a, buf.data_ptr(),
                     buf.numel(), algo | fl, s_))
         call("dmv_deconv2d_fwd", _p(x), _p(wvar.half), _p(y), _dt(y), B, Ho, Wo, Cin, Cout, kh, kw, stride, ACT[act], _p(ws),
@@ -555,7 +561,8 @@ class _Deconv2d(torch.autograd.Function):
             dps_dt = DT_S2D
         if ctx.needs_input_grad[1]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            ws = workspace(_lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride), x.device)
+            need = _lib.load().dmv_conv_workspace_size(B, Ho, Wo, Cout, Cin, kh, kw, stride)
+            ws = workspace(need, x.device)
             pp = _prepack_of(wvar.store) if (in_cell is None and Cout >= 8 and dps_dt == DT_BF16) else None
             flags = 0
             if pp is not None:
@@ -564,7 +571,7 @@ class _Deconv2d(torch.autograd.Function):
                 if pre is not None:
                     ws, flags = pre, ALGO_PREPACKED
                 else:
-                    pp.register(key, ws.numel(), lambda buf, fl, s_: call(
+                    pp.register(key, need, lambda buf, fl, s_: call(
                         "dmv_deconv2d_dgrad", buf.data_ptr(), DT_BF16, wvar.half.data_ptr(), buf.data_ptr(), None, 0, B, Ho, Wo, Cin, Cout, kh, kw, stride,
                         buf.data_ptr(), buf.numel(), algo | fl, s_))
             call("dmv_deconv2d_dgrad", _p(dps), dps_dt, _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
@@ -589,6 +596,7 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         wk, N = wvar.shape
         assert wk == K, (wvar.name, wvar.shape, x.shape)
+        wvar.rows = M
         y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
         _tag[0] = wvar.name
         if wvar.store.pre_use_hook is not None:

@@ -11,9 +11,11 @@ FUSE_MIN = 1 << 20      # elements: FC matrices this large take the weight-gradi
 
 
 def fusable(v):
-    """An FC matrix whose weight gradient dmv_linear_wgrad_adam can consume in place (include/dmv3d.h)."""
+    """An FC matrix whose weight gradient dmv_linear_wgrad_adam can consume in place (include/dmv3d.h), fed by at most 64
+    samples: the streaming form of the kernel holds one 64-sample operand tile (with the 4 source frames of config 5 folded
+    into the batch, 256 rows, the generic form lost 3 % against the separate calls)."""
     return (v.trainable and v.name.endswith("/Matrix") and len(v.shape) == 2 and v.numel >= FUSE_MIN and v.shape[0] % 8 == 0
-            and v.shape[1] % 8 == 0 and v.numel % 256 == 0 and v.offset % 256 == 0)
+            and v.shape[1] % 8 == 0 and v.numel % 256 == 0 and v.offset % 256 == 0 and 0 < v.rows <= 64)
 
 
 class TFAdam:

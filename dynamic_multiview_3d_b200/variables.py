@@ -21,7 +21,7 @@ BIG_VARIABLE = 1 << 20   # elements; variables this large (the FC matrices) begi
 
 
 class Variable:
-    __slots__ = ("name", "shape", "master", "grad", "m", "v", "half", "trainable", "offset", "numel", "store", "used", "fused_adam")
+    __slots__ = ("name", "shape", "master", "grad", "m", "v", "half", "trainable", "offset", "numel", "store", "used", "fused_adam", "rows")
 
     def __init__(self, name, tensor, trainable=True):
         self.name = name
@@ -33,6 +33,7 @@ class Variable:
         self.offset = -1
         self.used = False
         self.fused_adam = False     # optimizer.py: the weight gradient of this FC matrix is consumed by Adam inside one kernel
+        self.rows = 0               # FC matrices: rows (samples) of the layer's input when it last ran forward
 
 
 class VariableStore:
