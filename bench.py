@@ -247,7 +247,7 @@ def conv_microbench(torch, pk, iters=20):
     calls = {
         "fwd": lambda: _lib.call("dmv_conv2d_fwd", x.data_ptr(), 0, w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, B, Hc, Hc, C, C, k, k, 1, 1,
                                  ws.data_ptr(), ws.numel(), 0, st),
-        "dgrad": lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), x.data_ptr(), 1, B, Hc, Hc, C, C, k, k, 1, ws.data_ptr(),
+        "dgrad": lambda: _lib.call("dmv_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), None, 0, B, Hc, Hc, C, C, k, k, 1, ws.data_ptr(),
                                    ws.numel(), 0, st),
         "wgrad": lambda: _lib.call("dmv_conv2d_wgrad", x.data_ptr(), 0, dy.data_ptr(), dw.data_ptr(), None, B, Hc, Hc, C, C, k, k, 1,
                                    ws.data_ptr(), ws.numel(), 0, st),
