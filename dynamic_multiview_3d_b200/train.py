@@ -136,7 +136,7 @@ class GraphedTrainStep:
             self._staged_ev.record(self._copy_stream)
         self._pending = True
 
-    def __call__(self, *args, staged=False, prefetch_next=None):
+    def __call__(self, *args, staged=False, prefetch_next=None, async_loss=False):
         """One train step.  ``staged=True``: take the batch handed to prefetch() (a device-side move instead of a PCIe
         copy in front of the step).  ``prefetch_next=batch``: start copying the next step's batch before this step is
         replayed, so the PCIe transfer overlaps it."""
@@ -156,7 +156,32 @@ class GraphedTrainStep:
             self.prefetch(*(prefetch_next if isinstance(prefetch_next, (tuple, list)) else (prefetch_next,)))
         self.graph.replay()
         self._after_replay()
+        if async_loss:
+            return self._loss_future(main)
         return self.loss
+
+    def _loss_future(self, main):
+        """The step's loss on its way to pinned host memory (4 bytes, D2H behind the step): the caller can enqueue the next
+        step before it blocks on ``result()``, so the GPU does not idle between steps while the host reads a scalar.  Two
+        slots: read step k's future before calling step k + 2."""
+        if not hasattr(self, "_loss_host"):
+            self._loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_k = 0
+        slot = self._loss_host[self._loss_k & 1]
+        self._loss_k += 1
+        slot.copy_(self.loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        return LossFuture(slot, ev)
+
+
+class LossFuture(object):
+    def __init__(self, slot, event):
+        self.slot, self.event = slot, event
+
+    def result(self):
+        self.event.synchronize()
+        return float(self.slot)
 
 
 def install_reference_aliases():

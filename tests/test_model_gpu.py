@@ -409,3 +409,25 @@ def test_prepacked_weights_give_identical_steps(monkeypatch):
     assert out["1"][0] == out["0"][0] and out["1"][1] == out["0"][1]
     for k, t in out["0"][2].items():
         assert torch.equal(t, out["1"][2][k]), k
+
+
+def test_async_loss_readback_matches_the_synchronous_read():
+    """GraphedTrainStep(..., async_loss=True): the step's loss travels to pinned host memory behind the step and is awaited
+    one step later -- same values as float(step(...)), in order."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200.train import GraphedTrainStep
+    B, H, V = 4, 64, 19
+    conf = {"batch_size": B, "learning_rate": 1e-4, "image_size": H, "viewpoint_dim": V, "seed": 21}
+    b = _batch(B, H, V)
+    args = [torch.from_numpy(b[k]).cuda() for k in ("image0", "image1", "disp")]
+    ref_step = GraphedTrainStep(pkg.AppearanceFlowModel(conf), warmup=2)
+    ref = [float(ref_step(*args)) for _ in range(5)]
+    step = GraphedTrainStep(pkg.AppearanceFlowModel(conf), warmup=2)
+    got, fut = [], None
+    for _ in range(5):
+        nxt = step(*args, async_loss=True)
+        if fut is not None:
+            got.append(fut.result())
+        fut = nxt
+    got.append(fut.result())
+    assert got == ref
