@@ -19,6 +19,18 @@ import torch
 import torch.distributed as dist
 
 
+def _wait_for_gradients(stream, device):
+    """``stream`` waits for everything enqueued so far on the current stream AND on every weight-gradient lane: the variables
+    of one chunk may have reported from different lanes (conv weights on lane 0, big FC matrices on lane 1), and the lanes are
+    not ordered against each other."""
+    from . import functional as F
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    stream.wait_event(ev)
+    for e in F.lane_events(device):
+        stream.wait_event(e)
+
+
 def plan_buckets(var_table, bucket_elems):
     """var_table: [(name, offset, padded_numel)] in creation order -> buckets, last variable first.
     Each bucket is (start, end, [names]) with start/end offsets into the flat buffer."""
@@ -71,9 +83,7 @@ class GradientAllReducer:
         if self.world == 1:
             return
         if self.cuda:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.flat.device))
-            self.comm_stream.wait_event(ev)
+            _wait_for_gradients(self.comm_stream, self.flat.device)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
         else:
@@ -294,9 +304,7 @@ class ShardedGradientReducer:
             if self.deferred and c in self._deferred_chunks():
                 return                     # updated at the start of the next step (apply_deferred)
         if self.cuda:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.flat["grad"].device))
-            self.comm_stream.wait_event(ev)
+            _wait_for_gradients(self.comm_stream, self.flat["grad"].device)
             with torch.cuda.stream(self.comm_stream):
                 if self.world > 1:
                     self._reduce_scatter(c)
@@ -515,9 +523,7 @@ class FusedShardedReducer(ShardedGradientReducer):
             self.launched.append(c)
         if self.adam is None:
             raise RuntimeError("the fused exchange needs the optimizer attached (build_loss=True)")
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.flat["grad"].device))
-        self.comm_stream.wait_event(ev)
+        _wait_for_gradients(self.comm_stream, self.flat["grad"].device)
         with torch.cuda.stream(self.comm_stream):
             self._exchange(c, self.comm_stream.cuda_stream)
         if c < 0:

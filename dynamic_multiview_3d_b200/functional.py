@@ -210,6 +210,19 @@ class branch:
         return t
 
 
+def lane_events(device):
+    """One event per side stream that took work in this pass, recorded now.  The weight-gradient lanes are not ordered against
+    each other: whoever consumes gradients written on several lanes (a data-parallel chunk whose variables reported from
+    different lanes) waits for all of them, not only for the lane that delivered the last one."""
+    evs = []
+    for key in _used:
+        if (key[0], key[1]) == (device.type, device.index):
+            ev = torch.cuda.Event()
+            ev.record(_side[key])
+            evs.append(ev)
+    return evs
+
+
 def reset_side_stream_state():
     """Start of a forward pass: forget a join that a failed backward pass left queued."""
     if _join_queued[0]:
