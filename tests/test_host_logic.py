@@ -420,3 +420,48 @@ def test_synthetic_batches_are_deterministic_and_in_range():
     assert a["depth0"].max() == 1.0 and 0.3 <= a["depth0"].min() <= 0.6
     c = make_batch(2, 64, "disp2", views=4)
     assert c["image0"].shape == (2, 4, 64, 64, 3) and c["disp"].shape == (2, 2)
+
+
+def test_chunk_plan_leaves_out_variables_updated_elsewhere():
+    """plan_chunks(skip=...): an FC matrix that Adam updates inside its weight-gradient kernel (optimizer.py) gets chunks of its own
+    that nothing reports to and nothing launches; every other variable still lies inside live chunks, and no live chunk touches
+    the skipped range."""
+    import dynamic_multiview_3d_b200 as pkg
+    from dynamic_multiview_3d_b200.data_parallel import plan_chunks
+    m = pkg.AppearanceFlowModel({"batch_size": 2, "learning_rate": 1e-4, "image_size": 224, "viewpoint_dim": 19}, device="meta")
+    st = m.store
+    table = [(v.name, v.offset, -(-v.numel // 64) * 64) for v in st.vars.values() if v.offset < st.shard_end]
+    live = {v.name for v in st.trainable_vars()}
+    skip = {"fc1/Matrix", "a3/Matrix", "a4/Matrix"}
+    chunks, v2c, exp = plan_chunks(table, st.shard_end, 8 << 20, 1, live - skip, skip=skip)
+    assert chunks[0][0] == 0 and chunks[-1][1] == st.shard_end and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+    for name in skip:
+        v = st.vars[name]
+        assert name not in v2c
+        inside = [c for c, (s, e) in enumerate(chunks) if s < v.offset + v.numel and e > v.offset]
+        assert inside and all(exp[c] == 0 for c in inside), name                 # dead chunks: never launched, never updated
+        assert chunks[inside[0]][0] == v.offset and chunks[inside[-1]][1] == v.offset + v.numel
+    for name, o, n in table:
+        if name in skip or name not in live:
+            continue
+        cs = v2c[name]
+        assert all(exp[c] > 0 for c in cs) and chunks[cs[0]][0] <= o and o + n <= chunks[cs[-1]][1]
+
+
+def test_fused_update_candidates():
+    """optimizer.fusable: big 2-D ``*/Matrix`` variables fed by at most 64 rows; nothing else."""
+    import types
+    from dynamic_multiview_3d_b200.optimizer import fusable
+    def var(name, shape, rows, off=0, trainable=True):
+        n = 1
+        for d in shape:
+            n *= d
+        return types.SimpleNamespace(name=name, shape=shape, numel=n, offset=off, trainable=trainable, rows=rows)
+    assert fusable(var("fc1/Matrix", (12544, 4096), 64))
+    assert fusable(var("a3/Matrix", (4160, 4096), 2, off=16384))
+    assert not fusable(var("a3/Matrix", (4160, 4096), 256))          # 4 source frames folded into the batch (config 5)
+    assert not fusable(var("a3/Matrix", (4160, 4096), 0))            # never ran forward
+    assert not fusable(var("a0/Matrix", (19, 64), 64))               # small
+    assert not fusable(var("e3/w", (3, 3, 64, 128), 64))             # not an FC matrix
+    assert not fusable(var("fc1/Matrix", (12544, 4096), 64, trainable=False))
+    assert not fusable(var("fc1/Matrix", (12544, 4096), 64, off=64))  # not on a chunk-plan boundary
