@@ -340,9 +340,11 @@ def main(argv=None):
         model.load_state_dict(torch.load(args.pretrained, map_location="cpu"))
         itr_0 = checkpoint_iteration(args.pretrained)
         print("resuming training at iteration: ", itr_0)
-    if world > 1:
+    # world > 1: the data-parallel exchange.  world == 1: the same chunk pipeline without an exchange -- Adam chunk by chunk
+    # behind its gradients, the last FC matrix's update deferred into the next forward pass (data_parallel.py)
+    if world > 1 or os.environ.get("DMV_OVERLAP_ADAM", "1") == "1":
         from . import data_parallel
-        data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128")))
+        data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128" if world > 1 else "32")))
     step = model.train_step if args.eager else GraphedTrainStep(model)
     writer = SummaryWriter(out_dir) if rank == 0 else None
     t_iter = []
@@ -360,9 +362,16 @@ def main(argv=None):
             b = synthetic_batch(model, seed=(10 ** 6 if val else 1234) + itr, rank=rank)
         return {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
 
-    for itr in range(itr_0, conf["num_iterations"] + 1):
+    # the next batch is produced (synthetic generator or TFRecord reader + pinning) by a worker thread while the current step
+    # runs, so the loop is not bound by the host-side batch construction
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=1)
+    last_itr = conf["num_iterations"]
+    ahead = pool.submit(next_batch, itr_0) if itr_0 <= last_itr else None
+    for itr in range(itr_0, last_itr + 1):
         t0 = time.time()
-        batch = next_batch(itr)
+        batch = ahead.result()
+        ahead = pool.submit(next_batch, itr + 1) if itr < last_itr else None
         loss = step(to_device_f32(batch, model.device, model.image_shape[0])) if args.eager else step(batch)
         if itr % 10 == 0 and rank == 0:
             print("%d %g" % (itr, float(loss)))
@@ -381,6 +390,7 @@ def main(argv=None):
         # train.py:150 writes on every iteration NOT divisible by 400 (a bug); the intended cadence is kept
         if itr % SUMMARY_INTERVAL == 0 and writer is not None:
             writer.add_scalar("training_loss", float(loss), itr)
+    pool.shutdown()
     sd = model.state_dict()
     if rank == 0:
         torch.save(sd, os.path.join(out_dir, "model"))
