@@ -324,6 +324,8 @@ class ShardedGradientReducer:
         self.started = False
         if self.cuda:
             torch.cuda.current_stream(self.flat["grad"].device).wait_stream(self.comm_stream)
+            if getattr(self, "tail_stream", None) is not None and getattr(self, "tail_done", False):
+                torch.cuda.current_stream(self.flat["grad"].device).wait_stream(self.tail_stream)
         if self.deferred and self.adam is not None:
             from . import functional as F
             F._tag[0] = "adam"
@@ -504,6 +506,7 @@ class FusedShardedReducer(ShardedGradientReducer):
         self.px = PeerExchange(store, len(self.chunks) + 1, group)
         self.flat = store.flat
         self.tail_done = False
+        self.tail_stream = torch.cuda.Stream(device=store.flat["grad"].device)
 
     def _exchange(self, c, st):
         from . import functional as F
@@ -523,9 +526,13 @@ class FusedShardedReducer(ShardedGradientReducer):
             self.launched.append(c)
         if self.adam is None:
             raise RuntimeError("the fused exchange needs the optimizer attached (build_loss=True)")
-        _wait_for_gradients(self.comm_stream, self.flat["grad"].device)
-        with torch.cuda.stream(self.comm_stream):
-            self._exchange(c, self.comm_stream.cuda_stream)
+        # The bias tail and the first chunk (encoder convolutions) both complete with the very last gradients of the step and
+        # are tiny: each is two cross-GPU handshakes of latency (~35 us) whatever its size.  They run side by side, the tail
+        # on a stream of its own (profiles/r02_timeline_2gpu.txt: 72 us of serialised tail after backward).
+        st = self.tail_stream if c < 0 else self.comm_stream
+        _wait_for_gradients(st, self.flat["grad"].device)
+        with torch.cuda.stream(st):
+            self._exchange(c, st.cuda_stream)
         if c < 0:
             self.tail_done = True
 

@@ -18,12 +18,17 @@ from dynamic_multiview_3d_b200.train import GraphedTrainStep, synthetic_batch  #
 
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.txt"
-    dev = torch.device("cuda:0")
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                      # under torchrun: the data-parallel step (rank 0 writes its timeline)
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     conf = {"batch_size": 64, "learning_rate": 1e-4, "image_size": 224, "viewpoint_dim": 19, "loss": "l2", "seed": 0}
     model = pkg.AppearanceFlowModel(conf)
-    if os.environ.get("DMV_OVERLAP_ADAM", "1") == "1":
-        data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "32")))
-    b = synthetic_batch(model, seed=1234, rank=0)
+    if world > 1 or os.environ.get("DMV_OVERLAP_ADAM", "1") == "1":
+        data_parallel.attach(model, bucket_mb=float(os.environ.get("DMV_DP_CHUNK_MB", "128" if world > 1 else "32")))
+    b = synthetic_batch(model, seed=1234, rank=rank)
     devb = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
     step = GraphedTrainStep(model, warmup=2)
     step(devb)
@@ -35,6 +40,9 @@ def main():
         for _ in range(3):
             step.replay()
         torch.cuda.synchronize()
+    if rank != 0:
+        torch.cuda.synchronize()
+        os._exit(0)
     path = os.path.join(tempfile.mkdtemp(), "trace.json")
     prof.export_chrome_trace(path)
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and e.get("ph") == "X"]
@@ -63,6 +71,9 @@ def main():
             name = name.split("(")[0]
             f.write("%9.1f %8.1f %3s %6s %s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream", -1), str(e["args"].get("grid", "")).replace(" ", ""), name[:70]))
     print(open(out).read()[:1500])
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)                    # a process group whose collectives live in a captured graph can block in destroy
 
 
 if __name__ == "__main__":
