@@ -220,6 +220,7 @@ def sampler_microbench(torch, pk, iters=20):
         v = math.sin(a) * (ii - c0) + math.cos(a) * (jj - c0) + c0
         sets[k] = (sets[k][0], torch.stack([u - ii, v - jj], -1).unsqueeze(0).repeat(BATCH, 1, 1, 1).contiguous(), sets[k][2])
     res["smooth"] = {"fwd": timeit(fwd, px * (8 + 8 * 3)), "bwd_grad_flow": timeit(bwd_flow, px * (16 + 8 * 3)),
+                     "bwd_both": timeit(bwd_both, px * (16 + 12 * 3)),
                      "shape": "same tensors, flow = rotation field of 8..11 degrees"}
     return res
 

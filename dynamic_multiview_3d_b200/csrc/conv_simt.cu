@@ -395,7 +395,10 @@ int reduce_partials(const float* part, float* out, long long n, int splits, cuda
     // few columns: spread z over many warps; many columns: enough CTAs already, keep the chains per thread short anyway
     if (blocks >= 148 * 8 || splits <= 8) reduce_partials_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(part, out, n, splits);
     else if (blocks >= 148 || splits <= 32) reduce_partials_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(part, out, n, splits);
-    else reduce_partials_kernel<32><<<(unsigned)blocks, 1024, 0, st>>>(part, out, n, splits);
+    // few columns, many partials (bias gradients): 16 warps.  (32 warps of 32 registers are half a register file: such a
+    // CTA cannot become resident next to a persistent 512-thread kernel and stalled the input-gradient chain behind the
+    // fused FC update for up to 190 us, profiles/r02_timeline_final.txt.)
+    else reduce_partials_kernel<16><<<(unsigned)blocks, 512, 0, st>>>(part, out, n, splits);
     return check_launch("reduce_partials");
 }
 

@@ -990,7 +990,15 @@ int launch_igemm(const Problem& q, IgemmParams& p, void* workspace, size_t ws_by
     // The pipeline is latency-bound (one TMA box per tap): keep as many bytes in flight per SM as
     // possible.  Narrow layers (N <= 64) run two CTAs per SM, each with half of the shared memory.
     const bool two_per_sm = p.n_pad <= 64;
-    int stages = ((two_per_sm ? 106 : 200) * 1024) / stage_bytes;
+    // DMV_IGEMM_SMEM2_KB: budget of the two-per-SM form (A/B: a smaller footprint lets a CTA of the chain run next to the
+    // persistent fused FC update, fc_adam.cu)
+    static int budget2_kb = 0;
+    if (!budget2_kb) {
+        const char* e = getenv("DMV_IGEMM_SMEM2_KB");
+        budget2_kb = e ? atoi(e) : 106;
+        if (budget2_kb < 32 || budget2_kb > 106) budget2_kb = 106;
+    }
+    int stages = ((two_per_sm ? budget2_kb : 200) * 1024) / stage_bytes;
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;

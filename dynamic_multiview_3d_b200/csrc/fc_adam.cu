@@ -153,13 +153,17 @@ fc_wgrad_adam_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 // tiles (104 KB) are in flight per SM while the third is consumed.  Row pitches are padded (576 B / 80 B) so that the
 // float4 reads and the ldmatrix rows are conflict-free.  (Row-wise cp.async.bulk copies were measured first: 160 small
 // bulk requests per tile ran at 2 TB/s.)
-constexpr int SR = 32, SC = 128, STAGES = 3, STREAM_THREADS = 512;
+//
+// STAGES = 3 (194 KB) is the fastest form in isolation; STAGES = 2 (138 KB, one tile in flight while one is consumed) leaves
+// 88 KB of the SM to a co-resident CTA of the input-gradient chain (DMV_FC_ADAM_STAGES; measurements in
+// profiles/r02_fc_coresidency.txt).
+constexpr int SR = 32, SC = 128, STREAM_THREADS = 512;
 constexpr int PP = SC + 16;                   // floats per parameter row in shared memory (576 B)
 constexpr int SXP = SR + 8;                   // bf16 per x row (80 B)
-constexpr size_t STREAM_PAR_BYTES = (size_t)STAGES * 3 * SR * PP * sizeof(float);
-constexpr size_t STREAM_X_BYTES = (size_t)STAGES * TC * SXP * sizeof(__nv_bfloat16);
 constexpr size_t STREAM_D_BYTES = (size_t)TC * DP * sizeof(__nv_bfloat16);
-constexpr size_t STREAM_SMEM = STREAM_PAR_BYTES + STREAM_X_BYTES + STREAM_D_BYTES;
+constexpr size_t stream_par_bytes(int stages) { return (size_t)stages * 3 * SR * PP * sizeof(float); }
+constexpr size_t stream_x_bytes(int stages) { return (size_t)stages * TC * SXP * sizeof(__nv_bfloat16); }
+constexpr size_t stream_smem(int stages) { return stream_par_bytes(stages) + stream_x_bytes(stages) + STREAM_D_BYTES; }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -168,10 +172,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
+template <int STAGES>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
 fc_wgrad_adam_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ theta,
                             float* __restrict__ mom, float* __restrict__ vel, __nv_bfloat16* __restrict__ half, float* __restrict__ dw_out,
                             int M, int K, int N, const float* __restrict__ state, float omb1, float omb2, float eps, float gscale) {
+    constexpr size_t STREAM_PAR_BYTES = stream_par_bytes(STAGES), STREAM_X_BYTES = stream_x_bytes(STAGES);
     extern __shared__ __align__(128) unsigned char smem[];
     float* par = reinterpret_cast<float*>(smem);                                                  // [STAGES][3][SR][PP]
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + STREAM_PAR_BYTES);                  // [STAGES][64][SXP]
@@ -276,17 +282,20 @@ int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta,
     const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
     // DMV_FC_ADAM_VARIANT: 0 / 1 / 4 = generic kernel with that register prefetch depth, 9 = streaming kernel where the shape
     // allows (A/B measurements, profiles/r02_fc_adam.txt); default: see below
-    static int variant = -2, sms = 0, ctas_env = 0;
+    static int variant = -2, sms = 0, ctas_env = 0, stages = 3;
     if (variant == -2) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const char* e = getenv("DMV_FC_ADAM_CTAS");
         ctas_env = e ? atoi(e) : 0;
+        const char* s2 = getenv("DMV_FC_ADAM_STAGES");
+        stages = (s2 && atoi(s2) == 2) ? 2 : 3;
         const char* g = getenv("DMV_FC_ADAM_VARIANT");
         variant = g ? atoi(g) : 9;
-        if (variant == 9 && cudaFuncSetAttribute(fc_wgrad_adam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STREAM_SMEM) !=
-                                cudaSuccess) {
+        if (variant == 9 &&
+            (cudaFuncSetAttribute(fc_wgrad_adam_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem(3)) != cudaSuccess ||
+             cudaFuncSetAttribute(fc_wgrad_adam_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem(2)) != cudaSuccess)) {
             cudaGetLastError();
             variant = 1;
         }
@@ -295,9 +304,13 @@ int dmv_linear_wgrad_adam(const void* x_bf16, const void* dy_bf16, float* theta,
         const long long tiles = (long long)(K / SR) * (N / SC);
         long long grid = ctas_env > 0 ? ctas_env : sms;
         if (grid > tiles) grid = tiles;
-        fc_wgrad_adam_stream_kernel<<<(unsigned)grid, STREAM_THREADS, STREAM_SMEM, st>>>((const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy_bf16, theta, m,
-                                                                            v, (__nv_bfloat16*)bf16_copy, dw_out, M, K, N, state4, omb1, omb2,
-                                                                            eps, grad_scale);
+#define DMV_FC_STREAM(ST)                                                                                                               \
+    fc_wgrad_adam_stream_kernel<ST><<<(unsigned)grid, STREAM_THREADS, stream_smem(ST), st>>>(                                            \
+        (const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy_bf16, theta, m, v, (__nv_bfloat16*)bf16_copy, dw_out, M, K, N, state4, omb1, omb2, \
+        eps, grad_scale)
+        if (stages == 2) DMV_FC_STREAM(2);
+        else DMV_FC_STREAM(3);
+#undef DMV_FC_STREAM
         return dmv::check_launch("linear_wgrad_adam (stream)");
     }
     dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(K, TK));

@@ -13,11 +13,11 @@
 //       sampler_tile_kernel (any C <= 16, any alignment, 1-D sample lists): cp.async staging,
 //         predicated taps.
 //   grad_data : owner-computes scatter.  One CTA owns a 32x16 SOURCE tile; it visits every
-//     output tile whose tap box intersects it (box table from a pre-pass), and each warp
-//     accumulates into a warp-private shared-memory copy of the tile.  Lanes that hit the
-//     same cell in one step are serialised by lane rank (__match_any_sync), warps are
-//     summed in warp order, and every grad_data element is written exactly once: no global
-//     atomics, no memset, same inputs -> same bits.
+//     32-pixel warp chunk of the output whose tap box intersects it (two-level box table from a
+//     pre-pass), and each warp accumulates into a warp-private shared-memory copy of the tile.
+//     Lanes whose samples share a floor cell are serialised by lane rank (one __match_any_sync
+//     per sample), warps are summed in warp order, and every grad_data element is written
+//     exactly once: no atomics, no memset, same inputs -> same bits.
 //
 // HBM-bound: algorithmic bytes per output pixel are 8 + 8C (fwd), 16 + 8C (grad_warp only),
 // 8 + 8C (grad_data pass).
@@ -46,11 +46,19 @@ using namespace dmv;
 #ifndef SAMPLER_TMA_MINBLOCKS
 #define SAMPLER_TMA_MINBLOCKS 5
 #endif
+#ifndef SAMPLER_TMA_MINBLOCKS_FWD3
+#define SAMPLER_TMA_MINBLOCKS_FWD3 6   // the RGB forward kernel fits 42 registers: a sixth CTA per SM
+#endif
+// Source window boxes of the TMA kernel, pixels per side.  The row pitch of the staged window is box * C floats, and the
+// bank of a tap is (pitch * row + C * col + c) mod 32: with 48 pixels of RGB the pitch is 144 = 16 mod 32, so rows two
+// apart collide, and the lanes of a warp read 32 different rows under the reference's (Y,X) grid.  44 pixels (pitch 132 =
+// 4 mod 32) spread eight consecutive rows over the banks, and fetch 16 % fewer bytes per tile
+// (profiles/r02_sampler_window_variants.txt: 33.1 -> 31.2 us forward, 35.4 -> 33.0 us grad_flow under +-3 pixel jitter).
 #ifndef SAMPLER_BOX
-#define SAMPLER_BOX 40         // source window box of the TMA kernel, pixels per side
+#define SAMPLER_BOX 36         // first box: clipped edge tiles, small displacements
 #endif
 #ifndef SAMPLER_BOX_L
-#define SAMPLER_BOX_L 48       // second, larger box tried when the tap box does not fit the first
+#define SAMPLER_BOX_L 44       // second, larger box tried when the tap box does not fit the first
 #endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -71,9 +79,9 @@ struct Sample {
     bool valid;
 };
 
-__device__ __forceinline__ Sample load_sample(const float* __restrict__ wf, const Geom& g, int b, int i, int j) {
+// warp = flow + grid (tf_utils.py:35-52, fused) and the resampler's validity rule for one sample
+__device__ __forceinline__ Sample make_sample(float2 f, const Geom& g, int i, int j) {
     Sample s;
-    const float2 f = __ldg(reinterpret_cast<const float2*>(wf) + ((long long)b * g.Ho + i) * g.Wo + j);
     s.x = f.x;
     s.y = f.y;
     if (g.flags & DMV_SAMPLER_ADD_GRID) {
@@ -89,6 +97,10 @@ __device__ __forceinline__ Sample load_sample(const float* __restrict__ wf, cons
     return s;
 }
 
+__device__ __forceinline__ Sample load_sample(const float* __restrict__ wf, const Geom& g, int b, int i, int j) {
+    return make_sample(__ldg(reinterpret_cast<const float2*>(wf) + ((long long)b * g.Ho + i) * g.Wo + j), g, i, j);
+}
+
 __device__ __forceinline__ void tile_origin(const Geom& g, int tile, int& b, int& i0, int& j0) {
     const int per_img = g.tiles_x * g.tiles_y;
     b = tile / per_img;
@@ -100,7 +112,7 @@ __device__ __forceinline__ void tile_origin(const Geom& g, int tile, int& b, int
 }
 
 // Reduce the tap bounding box of a tile into s_box = {xmin, xmax, ymin, ymax} (clipped to the image).
-__device__ __forceinline__ void reduce_box(int* s_box, bool valid, int fx, int fy, int W, int H) {
+[[maybe_unused]] __device__ __forceinline__ void reduce_box(int* s_box, bool valid, int fx, int fy, int W, int H) {
     int xlo = 0x7fffffff, xhi = -0x7fffffff, ylo = 0x7fffffff, yhi = -0x7fffffff;
     if (valid) {
         xlo = max(fx, 0);
@@ -294,6 +306,8 @@ __global__ void __launch_bounds__(kThreads, SAMPLER_MINBLOCKS) sampler_tile_kern
 //     edges are clipped by the tensor map); MODE 1 receives grad_out the same way (bulk load);
 //   * lanes own consecutive pixels of a row: scalar LDS/STS at stride C are bank-conflict-free for
 //     smooth flows, flow loads / grad_flow stores are coalesced 8-byte accesses.
+// floats reserved for the source window: the tiles behind it are bulk-tensor destinations / sources (128-byte aligned)
+__host__ __device__ constexpr int win_floats(int C) { return (SAMPLER_BOX_L * SAMPLER_BOX_L * C + 31) & ~31; }
 constexpr int kBoxS = SAMPLER_BOX, kBoxL = SAMPLER_BOX_L;   // source window box (pixels); tap boxes beyond the larger one fall back to global gathers
 
 // MODE 2 (training step): forward + reconstruction loss + grad wrt flow in ONE pass -- the warped tile never leaves
@@ -311,14 +325,14 @@ struct FuseArgs {
 };
 
 template <int C, int MODE>
-__global__ void __launch_bounds__(kThreads, SAMPLER_TMA_MINBLOCKS) sampler_tma_kernel(
+__global__ void __launch_bounds__(kThreads, (C == 3 && MODE == 0) ? SAMPLER_TMA_MINBLOCKS_FWD3 : SAMPLER_TMA_MINBLOCKS) sampler_tma_kernel(
     const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_src_l,
     const __grid_constant__ CUtensorMap map_io, const __grid_constant__ CUtensorMap map_tgt, const float* __restrict__ data,
     const float* __restrict__ wf, float* __restrict__ out, int32_t* __restrict__ dbg_idx, uint8_t* __restrict__ dbg_mask, Geom g,
     const FuseArgs fa) {
     extern __shared__ __align__(128) float s_dyn[];
     float* s_win = s_dyn;                              // [box][box * C], box = kBoxS or kBoxL
-    float* s_io = s_dyn + kBoxL * kBoxL * C;           // [32][32 * C]: MODE 0/2 results, MODE 1 grad_out
+    float* s_io = s_dyn + win_floats(C);               // [32][32 * C]: MODE 0/2 results, MODE 1 grad_out
     float* s_tgt = s_io + 32 * 32 * C;                 // MODE 2: target tile
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_box[4];
@@ -550,7 +564,26 @@ int encode_f32_map(CUtensorMap* map, const float* base, int inner, int rows, int
     return DMV_OK;
 }
 
-// Pre-pass of grad_data: tap box of every output tile.
+// Pre-pass of grad_data: tap box of every output tile and of each of its 32 warp chunks (32 pixels of the tile: an
+// 8 x 4 patch of an image, 32 consecutive samples of a 1-D list; chunk_pixel below).  Layout: boxes[tile * kBoxesPerTile] = tile box,
+// boxes[tile * kBoxesPerTile + 1 + q] = box of chunk q; an empty box has xmin > xmax.
+constexpr int kChunks = kTilePix / 32;
+constexpr int kBoxesPerTile = 1 + kChunks;
+
+// Pixel (di, dj) of a tile that lane `lane` of chunk q owns.  Image tiles (32 x 32) are cut into 8-wide x 4-tall patches:
+// a compact patch has a compact tap box whatever the orientation of the grid (a 32 x 1 row segment has a 40 x 8 box that
+// reaches 2-3 source tiles along its long side).  1-D sample lists (1 x 1024 tiles) are cut into runs of 32 samples.
+__device__ __forceinline__ void chunk_pixel(const Geom& g, int q, int lane, int& di, int& dj) {
+    if (g.tw_shift == 5) {
+        di = (q >> 2) * 4 + (lane >> 3);
+        dj = (q & 3) * 8 + (lane & 7);
+    } else {
+        const int p = q * 32 + lane;
+        di = p >> g.tw_shift;
+        dj = p & ((1 << g.tw_shift) - 1);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) sampler_box_kernel(const float* __restrict__ wf, int4* __restrict__ boxes, Geom g) {
     __shared__ int s_box[4];
     const int tid = threadIdx.x;
@@ -558,44 +591,65 @@ __global__ void __launch_bounds__(kThreads) sampler_box_kernel(const float* __re
     tile_origin(g, blockIdx.x, b, i0, j0);
     if (tid < 4) s_box[tid] = (tid & 1) ? -0x7fffffff : 0x7fffffff;
     __syncthreads();
-    const int tw_mask = (1 << g.tw_shift) - 1;
+    int4* tile_boxes = boxes + (long long)blockIdx.x * kBoxesPerTile;
 #pragma unroll
     for (int k = 0; k < kPPT; ++k) {
-        const int p = k * kThreads + tid;
-        const int i = i0 + (p >> g.tw_shift), j = j0 + (p & tw_mask);
+        const int q = k * kWarps + (tid >> 5);                  // this warp's chunk
+        int di, dj;
+        chunk_pixel(g, q, tid & 31, di, dj);
+        const int i = i0 + di, j = j0 + dj;
         Sample s;
         s.valid = false;
         s.x = s.y = 0.f;
         if (i < g.Ho && j < g.Wo) s = load_sample(wf, g, b, i, j);
-        reduce_box(s_box, s.valid, s.valid ? (int)floorf(s.x) : 0, s.valid ? (int)floorf(s.y) : 0, g.W, g.H);
+        int xlo = 0x7fffffff, xhi = -0x7fffffff, ylo = 0x7fffffff, yhi = -0x7fffffff;
+        if (s.valid) {
+            const int fx = (int)floorf(s.x), fy = (int)floorf(s.y);
+            xlo = max(fx, 0);
+            xhi = min(fx + 1, g.W - 1);
+            ylo = max(fy, 0);
+            yhi = min(fy + 1, g.H - 1);
+        }
+        xlo = __reduce_min_sync(0xffffffffu, xlo);
+        xhi = __reduce_max_sync(0xffffffffu, xhi);
+        ylo = __reduce_min_sync(0xffffffffu, ylo);
+        yhi = __reduce_max_sync(0xffffffffu, yhi);
+        if ((tid & 31) == 0) {
+            tile_boxes[1 + q] = make_int4(xlo, xhi, ylo, yhi);
+            atomicMin(&s_box[0], xlo);
+            atomicMax(&s_box[1], xhi);
+            atomicMin(&s_box[2], ylo);
+            atomicMax(&s_box[3], yhi);
+        }
     }
     __syncthreads();
-    if (tid == 0) boxes[blockIdx.x] = make_int4(s_box[0], s_box[1], s_box[2], s_box[3]);
+    if (tid == 0) tile_boxes[0] = make_int4(s_box[0], s_box[1], s_box[2], s_box[3]);
 }
 
-template <int CT>
-__device__ __forceinline__ void accumulate_ranked(float* acc, int key, const float (&val)[CT ? CT : 8], int C) {
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-    const int rank = __popc(peers & lt);
-    const int rounds = __reduce_max_sync(0xffffffffu, key >= 0 ? __popc(peers) : 0);
-    for (int r = 0; r < rounds; ++r) {
-        if (key >= 0 && rank == r) {
-#pragma unroll
-            for (int c = 0; c < (CT ? CT : 8); ++c) {
-                if (!CT && c >= C) break;
-                acc[key * C + c] += val[c];
-            }
-        }
-        __syncwarp();
-    }
-}
+// grad wrt the source.  One CTA owns a 32x16 SOURCE tile and visits the warp chunks whose tap box intersects it.  The
+// candidates are found in parallel, not by a serial scan (a dependent box load per output tile made the first version of
+// this kernel latency-bound: 49 L2 round trips per CTA): (A) every thread tests one output tile's box and the hits are
+// compacted, in tile order, into a shared list; (B) for eight listed tiles at a time, warp w tests the 32 chunk boxes of
+// tile w with one coalesced load and publishes the hit mask; (C) the hits, enumerated in (tile, chunk) order, are dealt
+// round-robin to the warps -- a fixed assignment for given inputs -- and each warp brings in the flow vectors and output
+// gradients of up to G chunks at once before it accumulates them.  Under a few pixels of displacement a chunk's box is
+// ~15 x 11 source pixels, so an output pixel is visited by ~2.5 source tiles.
+// Each warp accumulates into a warp-private copy of the source tile with plain shared-memory read-modify-writes.  Two lanes
+// can hit the same cell in the same tap pass only if their samples share the floor cell (a tap pass maps floor cells to
+// tap cells one to one), so ONE __match_any_sync on the floor cell ranks the lanes for all four taps; ranks take turns,
+// warps are summed in warp order, every grad_data element is written exactly once: same inputs -> same bits.
+__host__ __device__ constexpr int grad_data_pitch(int C) { return kSrcTileW * C + 1; }
 
 template <int CT>
 __global__ void __launch_bounds__(kThreads) sampler_grad_data_kernel(
     const float* __restrict__ wf, const float* __restrict__ grad_out, const int4* __restrict__ boxes,
     float* __restrict__ grad_data, Geom g, int src_tiles_x, int src_tiles_y) {
-    extern __shared__ float s_acc[];  // [kWarps][kSrcTileH*kSrcTileW*C]
+    constexpr int CC = CT ? CT : 8;
+    constexpr int G = CT ? 4 : 2;
+    extern __shared__ float s_acc[];  // [kWarps][kSrcTileH][kSrcTileW*C + 1]
+    __shared__ int s_tiles[kThreads];
+    __shared__ int s_wcount[kWarps];
+    __shared__ unsigned s_mask[kWarps];
     const int C = CT ? CT : g.C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int per_img = src_tiles_x * src_tiles_y;
@@ -604,53 +658,132 @@ __global__ void __launch_bounds__(kThreads) sampler_grad_data_kernel(
     const int sty = st / src_tiles_x, stx = st - sty * src_tiles_x;
     const int sx0 = stx * kSrcTileW, sy0 = sty * kSrcTileH;
     const int sx1 = min(sx0 + kSrcTileW, g.W) - 1, sy1 = min(sy0 + kSrcTileH, g.H) - 1;
-    const int tile_floats = kSrcTileH * kSrcTileW * C;
+    // Row pitch of the private tiles: 32 C + 1 floats.  With a multiple of 32 the bank of a cell would depend on its column
+    // only, and under the reference's (Y,X) grid the 32 lanes of a chunk hit a handful of columns on 32 different rows
+    // (7-way bank conflicts on every read-modify-write: the kernel was bound by the shared-memory pipe); with the odd pitch
+    // the row index walks the banks.
+    const int pitch = grad_data_pitch(C);
+    const int tile_floats = kSrcTileH * pitch;
     for (int e = tid; e < kWarps * tile_floats; e += kThreads) s_acc[e] = 0.f;
-    __syncthreads();
     float* acc = s_acc + warp * tile_floats;
 
     const int out_tiles = g.tiles_x * g.tiles_y;
-    const int tw_mask = (1 << g.tw_shift) - 1;
-    for (int t = 0; t < out_tiles; ++t) {
-        const int4 box = __ldg(boxes + (long long)b * out_tiles + t);
-        if (box.x > sx1 || box.y < sx0 || box.z > sy1 || box.w < sy0) continue;  // CTA-uniform
-        const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
-        const int i0 = ty * (kTilePix >> g.tw_shift), j0 = tx << g.tw_shift;
-        for (int q = warp; q < kTilePix / 32; q += kWarps) {  // fixed chunk -> warp assignment
-            const int p = q * 32 + lane;
-            const int i = i0 + (p >> g.tw_shift), j = j0 + (p & tw_mask);
-            Sample s;
-            s.valid = false;
-            s.x = s.y = 0.f;
-            if (i < g.Ho && j < g.Wo) s = load_sample(wf, g, b, i, j);
-            int key[4] = {-1, -1, -1, -1};
-            float wgt[4] = {0.f, 0.f, 0.f, 0.f};
-            if (s.valid) {
-                const int fx = (int)floorf(s.x), fy = (int)floorf(s.y);
-                const int cx = fx + 1, cy = fy + 1;
-                const float dx = (float)cx - s.x, dy = (float)cy - s.y;
-                const bool fxo = fx >= sx0 && fx <= sx1, cxo = cx >= sx0 && cx <= sx1;
-                const bool fyo = fy >= sy0 && fy <= sy1, cyo = cy >= sy0 && cy <= sy1;
-                if (fxo && fyo) { key[0] = (fy - sy0) * kSrcTileW + (fx - sx0); wgt[0] = dx * dy; }
-                if (cxo && cyo) { key[1] = (cy - sy0) * kSrcTileW + (cx - sx0); wgt[1] = (1.f - dx) * (1.f - dy); }
-                if (fxo && cyo) { key[2] = (cy - sy0) * kSrcTileW + (fx - sx0); wgt[2] = dx * (1.f - dy); }
-                if (cxo && fyo) { key[3] = (fy - sy0) * kSrcTileW + (cx - sx0); wgt[3] = (1.f - dx) * dy; }
-            }
-            const bool mine = key[0] >= 0 || key[1] >= 0 || key[2] >= 0 || key[3] >= 0;
-            if (!__any_sync(0xffffffffu, mine)) continue;
-            float gv[CT ? CT : 8];
+    const unsigned lt = (1u << lane) - 1u;
+    const int4* img_boxes = boxes + (long long)b * out_tiles * kBoxesPerTile;
+    auto misses = [&](const int4& bx) { return bx.x > sx1 || bx.y < sx0 || bx.z > sy1 || bx.w < sy0; };
+
+    for (int tbase = 0; tbase < out_tiles; tbase += kThreads) {
+        // (A) output tiles whose tap box intersects this source tile, compacted in tile order
+        const int t = tbase + tid;
+        bool hit = false;
+        if (t < out_tiles) hit = !misses(__ldg(img_boxes + (long long)t * kBoxesPerTile));
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        __syncthreads();                         // the previous round's lists are no longer read (and s_acc is zeroed)
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, nt = 0;
 #pragma unroll
-            for (int c = 0; c < (CT ? CT : 8); ++c) {
-                gv[c] = 0.f;
-                if ((CT || c < C) && mine) gv[c] = __ldg(grad_out + (((long long)b * g.Ho + i) * g.Wo + j) * C + c);
-            }
+        for (int w = 0; w < kWarps; ++w) {
+            const int c = s_wcount[w];
+            if (w < warp) off += c;
+            nt += c;
+        }
+        if (hit) s_tiles[off + __popc(bal & lt)] = t;
+        __syncthreads();
+        for (int cb = 0; cb < nt; cb += kWarps) {
+            // (B) chunk boxes of tiles cb .. cb+7: one tile per warp, one chunk per lane
+            unsigned m = 0;
+            if (cb + warp < nt) m = __ballot_sync(0xffffffffu, !misses(__ldg(img_boxes + (long long)s_tiles[cb + warp] * kBoxesPerTile + 1 + lane)));
+            if (lane == 0) s_mask[warp] = m;
+            __syncthreads();
+            int total = 0;
 #pragma unroll
-            for (int tap = 0; tap < 4; ++tap) {
-                float val[CT ? CT : 8];
+            for (int w = 0; w < kWarps; ++w) total += __popc(s_mask[w]);
+            // (C) entry e of the (tile, chunk)-ordered hit list goes to warp e % kWarps
+            for (int e0 = warp; e0 < total; e0 += kWarps * G) {
+                int pi[G], pj[G];
+                bool inb[G];
+                float2 fl[G];
+                float gv[G][CC];
 #pragma unroll
-                for (int c = 0; c < (CT ? CT : 8); ++c) val[c] = gv[c] * wgt[tap];
-                accumulate_ranked<CT>(acc, key[tap], val, C);
+                for (int u = 0; u < G; ++u) {
+                    const int e = e0 + u * kWarps;
+                    inb[u] = false;
+                    pi[u] = pj[u] = 0;
+                    fl[u] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < CC; ++c) gv[u][c] = 0.f;
+                    if (e < total) {                          // warp-uniform
+                        int k = 0, base = 0;
+                        for (;;) {
+                            const int n = __popc(s_mask[k]);
+                            if (e < base + n) break;
+                            base += n;
+                            ++k;
+                        }
+                        const int q = (int)__fns(s_mask[k], 0, e - base + 1);
+                        const int tl = s_tiles[cb + k];
+                        const int ty = tl / g.tiles_x, tx = tl - ty * g.tiles_x;
+                        int di, dj;
+                        chunk_pixel(g, q, lane, di, dj);
+                        pi[u] = ty * (kTilePix >> g.tw_shift) + di;
+                        pj[u] = (tx << g.tw_shift) + dj;
+                        inb[u] = pi[u] < g.Ho && pj[u] < g.Wo;
+                        if (inb[u]) {
+                            const long long px = ((long long)b * g.Ho + pi[u]) * g.Wo + pj[u];
+                            fl[u] = __ldg(reinterpret_cast<const float2*>(wf) + px);
+#pragma unroll
+                            for (int c = 0; c < CC; ++c)
+                                if (CT || c < C) gv[u][c] = __ldg(grad_out + px * C + c);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    if (e0 + u * kWarps >= total) break;      // warp-uniform
+                    Sample s;
+                    s.valid = false;
+                    s.x = s.y = 0.f;
+                    if (inb[u]) s = make_sample(fl[u], g, pi[u], pj[u]);
+                    int key[4] = {-1, -1, -1, -1};     // float offset of the tap's cell in the private tile
+                    float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+                    int cell = -1 - lane;        // floor cell of the sample; lanes with nothing to add get distinct dummies
+                    if (s.valid) {
+                        const int fx = (int)floorf(s.x), fy = (int)floorf(s.y);
+                        const int cx = fx + 1, cy = fy + 1;
+                        const float dx = (float)cx - s.x, dy = (float)cy - s.y;
+                        const bool fxo = fx >= sx0 && fx <= sx1, cxo = cx >= sx0 && cx <= sx1;
+                        const bool fyo = fy >= sy0 && fy <= sy1, cyo = cy >= sy0 && cy <= sy1;
+                        if (fxo && fyo) { key[0] = (fy - sy0) * pitch + (fx - sx0) * C; wgt[0] = dx * dy; }
+                        if (cxo && cyo) { key[1] = (cy - sy0) * pitch + (cx - sx0) * C; wgt[1] = (1.f - dx) * (1.f - dy); }
+                        if (fxo && cyo) { key[2] = (cy - sy0) * pitch + (fx - sx0) * C; wgt[2] = dx * (1.f - dy); }
+                        if (cxo && fyo) { key[3] = (fy - sy0) * pitch + (cx - sx0) * C; wgt[3] = (1.f - dx) * dy; }
+                        // fx, fy >= -1 for a valid sample; both lie within one pixel of the source tile when a key is set
+                        if ((fxo || cxo) && (fyo || cyo)) cell = (fy - sy0 + 1) * (kSrcTileW + 2) + (fx - sx0 + 1);
+                    }
+                    const bool mine = cell >= 0;
+                    if (!__any_sync(0xffffffffu, mine)) continue;
+                    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+                    const int rank = __popc(peers & lt);
+                    const int rounds = __reduce_max_sync(0xffffffffu, mine ? __popc(peers) : 0);
+                    for (int r = 0; r < rounds; ++r) {
+                        const bool on = mine && rank == r;
+#pragma unroll
+                        for (int tap = 0; tap < 4; ++tap) {
+                            if (on && key[tap] >= 0) {
+                                float* cellp = acc + key[tap];
+#pragma unroll
+                                for (int c = 0; c < CC; ++c) {
+                                    if (!CT && c >= C) break;
+                                    cellp[c] += gv[u][c] * wgt[tap];
+                                }
+                            }
+                            __syncwarp();     // the next tap pass may touch a cell another lane wrote in this one
+                        }
+                    }
+                }
             }
+            __syncthreads();                     // s_mask is rewritten by the next batch
         }
     }
     __syncthreads();
@@ -661,7 +794,7 @@ __global__ void __launch_bounds__(kThreads) sampler_grad_data_kernel(
         for (int e = lane; e < seg; e += 32) {
             float sum = 0.f;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) sum += s_acc[w * tile_floats + r * kSrcTileW * C + e];
+            for (int w = 0; w < kWarps; ++w) sum += s_acc[w * tile_floats + r * pitch + e];
             dst[e] = sum;
         }
     }
@@ -693,7 +826,7 @@ int launch_tile(const float* data, const float* wf, const float* go, float* out,
         if (rc) return rc;
         rc = encode_f32_map(&map_io, MODE == 0 ? out : go, g.Wo * g.C, g.Ho, g.B, 32 * g.C, 32);
         if (rc) return rc;
-        const size_t wsm = (size_t)(kBoxL * kBoxL + 32 * 32) * g.C * sizeof(float);
+        const size_t wsm = (size_t)(win_floats(g.C) + 32 * 32 * g.C) * sizeof(float);
 #define DMV_LAUNCH_TMA(CT)                                                                               \
     do {                                                                                                 \
         static bool attr_done = false;                                                                   \
@@ -749,7 +882,7 @@ size_t dmv_sampler_bwd_workspace_size(int B, int H, int W, int C, int Hout, int 
     if (B <= 0 || Hout <= 0 || Wout <= 0) return 0;
     const int tw_shift = (Hout == 1) ? 10 : 5;
     const long long tiles = (long long)B * ceil_div(Wout, 1 << tw_shift) * ceil_div(Hout, kTilePix >> tw_shift);
-    return (size_t)tiles * sizeof(int4);
+    return (size_t)tiles * kBoxesPerTile * sizeof(int4);
 }
 
 int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out, float* grad_data, float* grad_wf,
@@ -778,7 +911,7 @@ int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out, f
         if (rc) return rc;
         const int stx = ceil_div(W, kSrcTileW), sty = ceil_div(H, kSrcTileH);
         const int grid = B * stx * sty;
-        const size_t smem = (size_t)kWarps * kSrcTileH * kSrcTileW * C * sizeof(float);
+        const size_t smem = (size_t)kWarps * kSrcTileH * grad_data_pitch(C) * sizeof(float);
 #define DMV_LAUNCH_GD(CT)                                                                                         \
     do {                                                                                                          \
         cudaFuncSetAttribute(sampler_grad_data_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -828,7 +961,7 @@ int dmv_sampler_loss_fused(const float* data, const float* wf, const float* targ
     fa.counter = reinterpret_cast<unsigned*>(workspace);                 // fixed place: survives calls with other grid sizes
     fa.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
     fa.loss_out = loss_out; fa.grad_wf = grad_wf;
-    const size_t wsm = (size_t)(kBoxL * kBoxL + 2 * 32 * 32) * C * sizeof(float);
+    const size_t wsm = (size_t)(win_floats(C) + 2 * 32 * 32 * C) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define DMV_LAUNCH_FUSED(CT)                                                                                  \
     do {                                                                                                      \

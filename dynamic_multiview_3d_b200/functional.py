@@ -126,6 +126,21 @@ def side_stream_enabled():
     return os.environ.get("DMV_SIDE_WGRAD", "1") == "1" and not _meta_depth[0] and _profile[0] is None
 
 
+def stream_priority(role):
+    """CUDA stream priority of a role in the captured step (lower = dispatched first; kernel nodes of a graph inherit the
+    priority of the stream they were captured on).  Default: the step's own chain -- forward, loss, the input-gradient chain
+    of backward, the viewpoint branch -- one level above everything else (weight-gradient lanes, Adam / exchange streams).
+    ``DMV_MAIN_PRIORITY`` / ``DMV_LANE0_PRIORITY`` / ``DMV_LANE1_PRIORITY`` = n set a role to level -n (0 = default
+    priority).  MEASURED (profiles/r02_fc_variant_priority_sweep.txt): three levels (chain -2, convolution weight gradients
+    -1, FC lane 0) cost 1 % with the persistent fused FC kernel (2.607 against 2.578 ms/step) -- that kernel occupies the
+    shared memory of every SM whatever its priority; they only pay with the one-tile-per-CTA form of the kernel, which is
+    slower overall (2.69 ms)."""
+    import os
+    default = {"main": -1}.get(role, 0)
+    env = os.environ.get("DMV_%s_PRIORITY" % role.upper())
+    return default if env is None else -abs(int(env))
+
+
 class side_stream:
     """Context: run the enclosed launches on one of the device's side streams ("lanes"), ordered after everything
     enqueued so far on the current stream.  ``keep`` are tensors the side work reads.  Lane 0 carries the convolution
@@ -137,7 +152,7 @@ class side_stream:
         key = (device.type, device.index, lane)
         st = _side.get(key)
         if st is None:
-            st = _side[key] = torch.cuda.Stream(device=device)
+            st = _side[key] = torch.cuda.Stream(device=device, priority=stream_priority("lane%d" % lane))
         self.stream, self.device, self.key = st, device, key
         _held.extend(t for t in keep if t is not None)
 
@@ -180,7 +195,7 @@ class branch:
             if st is None:
                 # same (high) priority as the captured main chain (train.py): the branch is a handful of tiny kernels, and at
                 # the default priority they starved behind the chain's persistent grids until the chain itself blocked on them
-                st = _side[key] = torch.cuda.Stream(device=device, priority=-1)
+                st = _side[key] = torch.cuda.Stream(device=device, priority=stream_priority("main"))
             self.stream, self.key = st, key
             for t in inputs:
                 t.record_stream(st)
@@ -260,6 +275,7 @@ class _main_stream_ctx:
 
 
 BIG_LINEAR = 1 << 20      # weights; linear layers this large take side-stream lane 1
+TAIL_LANE = 2 if __import__("os").environ.get("DMV_TAIL_LANE", "1") == "1" else 0
 
 
 def _wgrad_ctx(device, *keep, lane=0):
@@ -501,7 +517,9 @@ class _Conv2d(torch.autograd.Function):
                 call("dmv_cast_bf16_to_f32", _p(dx), _p(dxf), dx.numel(), st)
                 dx = dxf
         nws = _lib.load().dmv_wgrad_workspace_size(B, H, W, Cin, Cout, kh, kw, stride)
-        wctx, wsf = _wgrad_ctx(y.device, xs, dpre)
+        # the LAST weight gradient of the step (e0: the 3-channel image layer) does not queue behind e0_0's on lane 0: the two
+        # run side by side at the end of backward, where nothing else is left to overlap with
+        wctx, wsf = _wgrad_ctx(y.device, xs, dpre, lane=TAIL_LANE if Cin <= 4 else 0)
         with wctx:
             ws = wsf(nws, y.device)
             call("dmv_conv2d_wgrad", _p(xs), ctx.xs_dt, _p(dpre), _p(wvar.grad), _p(bvar.grad) if (bvar is not None and not bias_done) else None,
@@ -652,7 +670,9 @@ class _Linear(torch.autograd.Function):
             call("dmv_linear_dgrad", _p(dpre), _p(wvar.half), _p(dx), _p(x) if in_cell is not None else None,
                  ACT[in_cell.act] if in_cell is not None else 0, M, K, N, _p(ws), ws.numel(), algo, st)
         nws = _lib.load().dmv_wgrad_workspace_size(M, 1, 1, K, N, 1, 1, 1)
-        wctx, wsf = _wgrad_ctx(x.device, x, dpre, lane=1 if K * N >= BIG_LINEAR else 0)
+        # small matrices (the viewpoint FCs): autograd runs their nodes last, so on lane 0 their few-microsecond kernels would
+        # sit behind every convolution weight gradient, at the very end of the step
+        wctx, wsf = _wgrad_ctx(x.device, x, dpre, lane=1 if K * N >= BIG_LINEAR else TAIL_LANE)
         live = wvar.store.adam_live if wvar.fused_adam else None
         with wctx:
             ws = wsf(nws, x.device)

@@ -65,7 +65,8 @@ class GraphedTrainStep:
         # the priority of the stream they were captured on, so the block scheduler dispatches the critical chain's CTAs
         # ahead of queued side-stream CTAs instead of behind a 784-CTA weight-gradient or a 2368-CTA Adam grid
         # (profiles/r02_timeline_*.txt: small kernels of the chain waited up to 50 us for SM slots).
-        prio = -1 if os.environ.get("DMV_MAIN_PRIORITY", "1") == "1" else 0
+        from .functional import stream_priority
+        prio = stream_priority("main")
         side = torch.cuda.Stream(device=m.device, priority=prio)
         side.wait_stream(torch.cuda.current_stream(m.device))
         with torch.cuda.stream(side):

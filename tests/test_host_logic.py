@@ -42,7 +42,7 @@ def test_error_reporting_without_gpu():
     assert rc == -1 and "null" in _lib.last_error()
     with pytest.raises(_lib.DmvError):
         _lib.check(rc, "dmv_sampler_fwd")
-    assert lib.dmv_sampler_bwd_workspace_size(64, 224, 224, 3, 224, 224) == 64 * 49 * 16
+    assert lib.dmv_sampler_bwd_workspace_size(64, 224, 224, 3, 224, 224) == 64 * 49 * 33 * 16      # tile box + 32 chunk boxes
     assert lib.dmv_wgrad_workspace_size(64, 112, 112, 32, 32, 5, 5, 1) > 0
     assert lib.dmv_conv_workspace_size(64, 224, 224, 3, 32, 5, 5, 2) >= 64 * 112 * 112 * 96 * 2
 

@@ -10,10 +10,12 @@ while read -r name flags; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $flags -shared -o tools/variants/$name.so $CS/sampler.cu $CS/api.cu &
 done <<LIST
 a_tile -DSAMPLER_TMA=0
-tma_40_48_mb5 -DSAMPLER_TMA_MINBLOCKS=5
-tma_40_56_mb4 -DSAMPLER_TMA_MINBLOCKS=4 -DSAMPLER_BOX_L=56
-tma_40_40_mb5 -DSAMPLER_TMA_MINBLOCKS=5 -DSAMPLER_BOX_L=40
-tma_40_40_mb6 -DSAMPLER_TMA_MINBLOCKS=6 -DSAMPLER_BOX_L=40
+tma_40_48_f5 -DSAMPLER_BOX=40 -DSAMPLER_BOX_L=48 -DSAMPLER_TMA_MINBLOCKS_FWD3=5
+tma_36_44_f5 -DSAMPLER_TMA_MINBLOCKS_FWD3=5
+tma_36_44_f6
+tma_40_44_f6 -DSAMPLER_BOX=40
+tma_36_44_f7 -DSAMPLER_TMA_MINBLOCKS_FWD3=7
+tma_28_44_f6 -DSAMPLER_BOX=28
 LIST
 wait
 ls tools/variants
