@@ -547,6 +547,9 @@ def attach(model, bucket_mb=32.0, group=None, mode=None):
     mode = mode or os.environ.get("DMV_DP_MODE", "fused")
     if dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(model.optimizer, "disable_fusion"):
         model.optimizer.disable_fusion()       # the gradients of the FC matrices must exist in memory to be exchanged
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        from . import functional as F
+        F.set_tail_lane(False)                 # the exchange's tail chunk follows the last gradients: keep them on lane 0
     if mode == "fused" and not (dist.is_initialized() and dist.get_world_size(group) > 1 and store.flat["grad"].is_cuda
                                 and model.optimizer is not None):
         mode = "sharded"

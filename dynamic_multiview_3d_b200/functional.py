@@ -275,7 +275,15 @@ class _main_stream_ctx:
 
 
 BIG_LINEAR = 1 << 20      # weights; linear layers this large take side-stream lane 1
+# Lane of the step's last weight gradients (e0, the viewpoint FCs): a third lane in single-process training, so that they
+# do not queue behind e0_0's on lane 0 at the end of the step, where nothing else is left to overlap with.  Under data
+# parallelism (data_parallel.attach) they stay on lane 0: that path was validated on 2 - 8 GPUs with two lanes.
 TAIL_LANE = 2 if __import__("os").environ.get("DMV_TAIL_LANE", "1") == "1" else 0
+
+
+def set_tail_lane(on):
+    global TAIL_LANE
+    TAIL_LANE = 2 if (on and __import__("os").environ.get("DMV_TAIL_LANE", "1") == "1") else 0
 
 
 def _wgrad_ctx(device, *keep, lane=0):
