@@ -95,8 +95,11 @@ int dmv_sampler_fwd(const float* data, const float* wf, float* out, int32_t* dbg
  * tf.train.AdamOptimizer.minimize, appearance_flow_model.py:77).
  *   grad_data [B,H,W,C] f32 or NULL (skip: the source is a network input)
  *   grad_wf   [B,Hout,Wout,2] f32 (gradient wrt warp == wrt flow)
- * grad_data is produced by a deterministic owner-computes scatter (no fp32 atomics on
- * global memory): same inputs -> same bits.  workspace: dmv_sampler_bwd_workspace_size. */
+ * grad_data is produced by a deterministic owner-computes scatter (no atomics): same
+ * inputs -> same bits.  workspace (only read / written when grad_data != NULL):
+ * dmv_sampler_bwd_workspace_size bytes, 16-byte aligned -- a pre-pass fills it with the tap
+ * bounding box of every 1024-pixel output tile and of each of its 32 warp chunks
+ * (33 int4 per tile); it needs no initialisation and may be shared by calls on one stream. */
 size_t dmv_sampler_bwd_workspace_size(int B, int H, int W, int C, int Hout, int Wout);
 int dmv_sampler_bwd(const float* data, const float* wf, const float* grad_out,
                     float* grad_data, float* grad_wf, int B, int H, int W, int C, int Hout,

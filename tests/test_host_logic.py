@@ -465,3 +465,28 @@ def test_fused_update_candidates():
     assert not fusable(var("e3/w", (3, 3, 64, 128), 64))             # not an FC matrix
     assert not fusable(var("fc1/Matrix", (12544, 4096), 64, trainable=False))
     assert not fusable(var("fc1/Matrix", (12544, 4096), 64, off=64))  # not on a chunk-plan boundary
+
+
+def test_stream_roles_and_tail_lane(monkeypatch):
+    """Scheduling knobs of the captured step (functional.py): the chain one priority level above the weight-gradient lanes by
+    default, overridable per role; the third weight-gradient lane only in single-process training."""
+    from dynamic_multiview_3d_b200 import functional as F
+    for k in ("DMV_MAIN_PRIORITY", "DMV_LANE0_PRIORITY", "DMV_LANE1_PRIORITY", "DMV_TAIL_LANE"):
+        monkeypatch.delenv(k, raising=False)
+    assert (F.stream_priority("main"), F.stream_priority("lane0"), F.stream_priority("lane1"), F.stream_priority("lane2")) == (-1, 0, 0, 0)
+    monkeypatch.setenv("DMV_MAIN_PRIORITY", "0")            # historical switch: 0 = the chain at the default priority
+    assert F.stream_priority("main") == 0
+    monkeypatch.setenv("DMV_MAIN_PRIORITY", "2")
+    monkeypatch.setenv("DMV_LANE0_PRIORITY", "1")
+    assert (F.stream_priority("main"), F.stream_priority("lane0"), F.stream_priority("lane1")) == (-2, -1, 0)
+    before = F.TAIL_LANE
+    try:
+        F.set_tail_lane(True)
+        assert F.TAIL_LANE == 2
+        F.set_tail_lane(False)                               # what data_parallel.attach does when gradients are exchanged
+        assert F.TAIL_LANE == 0
+        monkeypatch.setenv("DMV_TAIL_LANE", "0")
+        F.set_tail_lane(True)
+        assert F.TAIL_LANE == 0
+    finally:
+        F.TAIL_LANE = before
