@@ -164,3 +164,25 @@ def test_workspace_holds_one_box_per_tile_and_chunk():
     lib = _lib.load()
     assert lib.dmv_sampler_bwd_workspace_size(2, 44, 52, 3, 40, 72) == 2 * (2 * 3) * 33 * 16
     assert lib.dmv_sampler_bwd_workspace_size(1, 20, 36, 3, 1, 2500) == 3 * 33 * 16
+
+
+def test_schedule_model_on_random_ragged_shapes():
+    """Random source / output sizes (not multiples of the tiles) and displacement scales, C in {1, 3, 4}."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=12, deadline=None, derandomize=True)
+    @given(H=st.integers(3, 50), W=st.integers(3, 70), Ho=st.integers(2, 45), Wo=st.integers(2, 70), C=st.sampled_from([1, 3, 4]),
+           amp=st.sampled_from([0.5, 3.0, 12.0]), xy=st.booleans(), seed=st.integers(0, 1000))
+    def check(H, W, Ho, Wo, C, amp, xy, seed):
+        rng = np.random.default_rng(seed)
+        ii, jj = np.meshgrid(np.arange(Ho, dtype=np.float32), np.arange(Wo, dtype=np.float32), indexing="ij")
+        a, b = (jj, ii) if xy else (ii, jj)
+        warp = np.stack([a * (W / max(Ho, Wo)) + rng.uniform(-amp, amp, (Ho, Wo)), b * (H / max(Ho, Wo)) + rng.uniform(-amp, amp, (Ho, Wo))],
+                        -1).astype(np.float32)
+        go = rng.standard_normal((Ho, Wo, C)).astype(np.float32)
+        data = rng.random((1, H, W, C), dtype=np.float32)
+        gd, _ = model_grad_data(warp, go, H, W)
+        ref, _ = tf_ops.resampler_grad(data, warp[None], go[None])
+        assert float(np.abs(gd - ref[0]).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+
+    check()
